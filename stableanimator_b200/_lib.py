@@ -1,0 +1,88 @@
+"""ctypes binding of ``libsa_b200.so`` (the C ABI declared in ``include/sa_b200.h``).
+
+The product path has no CPU / PyTorch fallback: if the library is missing or a call fails the
+binding raises (``SaLibraryError`` / ``SaKernelError``) instead of computing anything elsewhere.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "libsa_b200.so"
+
+
+class SaLibraryError(RuntimeError):
+    pass
+
+
+class SaKernelError(RuntimeError):
+    pass
+
+
+class GemmArgs(C.Structure):
+    """Mirror of ``sa_gemm_args`` (include/sa_b200.h)."""
+
+    _fields_ = [
+        ("a0", C.c_void_p), ("a1", C.c_void_p),
+        ("c0", C.c_int32), ("c1", C.c_int32),
+        ("lda0", C.c_int32), ("lda1", C.c_int32),
+        ("d1", C.c_int32), ("d2", C.c_int32), ("d3", C.c_int32),
+        ("ntaps", C.c_int32),
+        ("tap_off", C.c_int32 * 27),
+        ("w", C.c_void_p),
+        ("n", C.c_int32),
+        ("bias", C.c_void_p), ("row_bias", C.c_void_p), ("row_scale", C.c_void_p),
+        ("rows_per_group", C.c_int32),
+        ("residual", C.c_void_p), ("ldr", C.c_int32),
+        ("blend_x", C.c_void_p), ("ldx", C.c_int32),
+        ("alpha", C.c_float),
+        ("geglu", C.c_int32),
+        ("out", C.c_void_p), ("ldc", C.c_int32),
+        ("out_f32", C.c_int32),
+        ("tile_n", C.c_int32),
+    ]
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load (once) and return the CUDA library; raises SaLibraryError if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise SaLibraryError(
+            f"{LIB_PATH} is missing: build it with `python -m stableanimator_b200.build` "
+            "(there is no CPU fallback for the hot path)")
+    try:
+        l = C.CDLL(str(LIB_PATH))
+    except OSError as e:  # pragma: no cover
+        raise SaLibraryError(f"cannot load {LIB_PATH}: {e}") from e
+    l.sa_version.restype = C.c_int
+    l.sa_last_error.restype = C.c_char_p
+    _declare(l)
+    _lib = l
+    return l
+
+
+# name -> argtypes; every function returns int (0 = ok)
+_P, _I, _F, _L = C.c_void_p, C.c_int32, C.c_float, C.c_int64
+SIGNATURES: dict[str, list] = {
+    "sa_gemm_tap": [C.POINTER(GemmArgs), _P],
+    "sa_gemm_pick_tile": [_I, _I, _I],
+}
+
+
+def _declare(l: C.CDLL) -> None:
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(l, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().sa_last_error().decode("utf-8", "replace")
+        raise SaKernelError(f"{what} failed with code {rc}: {msg}")

@@ -1,0 +1,424 @@
+// Tapped implicit GEMM on tcgen05 / TMEM, operands staged by TMA (SWIZZLE_128B), sm_100a.
+//
+// One CTA computes one 128 x BN output tile:
+//   warp 0 (one elected lane) : TMA producer  -- per K block (64 channels of one tap) one 4-D box
+//                                (64, b1, b2, b3) of A at the tap-shifted position (out-of-grid
+//                                positions are zero-filled by TMA = conv zero padding) and one
+//                                2-D box (64, BN) of W, both landing on the stage's mbarrier;
+//   warp 1 (one elected lane) : MMA issuer    -- 4 x tcgen05.mma (K=16 each) per stage into the
+//                                fp32 accumulator in TMEM, tcgen05.commit frees the stage;
+//   warps 0-3                 : epilogue      -- tcgen05.ld 32 columns at a time (thread = row),
+//                                scale / bias / GEGLU / residual / alpha-blend in fp32, bf16 store.
+// Two CTAs are co-resident per SM (<= ~110 KB smem, <= 256 TMEM columns each) so one CTA's epilogue
+// overlaps the other's main loop.
+//
+// Replaces: nn.Linear / nn.Conv2d 3x3 & 1x1 / nn.Conv3d (3,1,1) call sites of
+// animation/modules/unet.py (see include/sa_b200.h for the per-site citations).
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace sa {
+
+struct GemmKParams {
+  int M, N;              // N = MMA output columns (before GEGLU halving)
+  int kc0, kcpt;         // 64-chunks in source 0, chunks per tap (both sources)
+  int ntaps;
+  int d1, d2, d3;        // position grid
+  int b1, b2, b3;        // box (b1*b2*b3 == 128)
+  int t1, t2;            // tile counts along dims 1, 2
+  int tap_off[27];
+  const float* bias;
+  const float* row_bias;
+  const float* row_scale;
+  int rows_per_group;
+  const __nv_bfloat16* residual;
+  int ldr;
+  const __nv_bfloat16* blend_x;
+  int ldx;
+  float alpha;
+  int geglu;
+  void* out;
+  int ldc;
+  int out_f32;
+};
+
+template <int BN>
+struct TmemCols {
+  static constexpr int value = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(128)
+gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                const __grid_constant__ CUtensorMap tmB, const GemmKParams p) {
+  constexpr int A_BYTES = 128 * 128;
+  constexpr int B_BYTES = BN * 128;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int TCOLS = TmemCols<BN>::value;
+
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B operands need 1024-byte aligned tiles
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* acc_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int n0 = blockIdx.x * BN;
+  const int mt = blockIdx.y;
+  const int t1i = mt % p.t1;
+  const int t2i = (mt / p.t1) % p.t2;
+  const int t3i = mt / (p.t1 * p.t2);
+  const int q1 = t1i * p.b1, q2 = t2i * p.b2, q3 = t3i * p.b3;  // tile origin in the grid
+  const int KB = p.ntaps * p.kcpt;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmA1);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(acc_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<TCOLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int tap = 0, ch = 0;
+      for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+        uint8_t* sa_ = smem + s * STAGE_BYTES;
+        const int o1 = p.tap_off[tap * 3 + 0], o2 = p.tap_off[tap * 3 + 1],
+                  o3 = p.tap_off[tap * 3 + 2];
+        if (ch < p.kc0)
+          tma_load_4d(sa_, &tmA0, &full_bar[s], ch * 64, q1 + o1, q2 + o2, q3 + o3);
+        else
+          tma_load_4d(sa_, &tmA1, &full_bar[s], (ch - p.kc0) * 64, q1 + o1, q2 + o2, q3 + o3);
+        tma_load_2d(sa_ + A_BYTES, &tmB, &full_bar[s], kb * 64, n0);
+        if (++ch == p.kcpt) {
+          ch = 0;
+          ++tap;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+      for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+        const uint64_t da = umma_desc_sw128(a_addr);
+        const uint64_t db = umma_desc_sw128(a_addr + A_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+        umma_commit(&empty_bar[s]);  // stage reusable once these MMAs have read it
+      }
+      umma_commit(acc_bar);  // accumulator complete
+    }
+    __syncwarp();
+  }
+
+  // ------------------------------------------------------------------ epilogue (all 4 warps)
+  mbar_wait(acc_bar, 0);
+  tc_fence_after();
+
+  const int r = threadIdx.x;  // tile row == TMEM lane
+  const int i1 = r % p.b1, i2 = (r / p.b1) % p.b2, i3 = r / (p.b1 * p.b2);
+  const int p1 = q1 + i1, p2 = q2 + i2, p3 = q3 + i3;
+  const bool valid = (p1 < p.d1) && (p2 < p.d2) && (p3 < p.d3);
+  const long long row = (static_cast<long long>(p3) * p.d2 + p2) * p.d1 + p1;
+  const int grp = valid ? static_cast<int>(row / p.rows_per_group) : 0;
+  const float rs = (p.row_scale && valid) ? p.row_scale[grp] : 1.0f;
+  const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+  const float alpha = p.alpha, beta = 1.0f - p.alpha;
+
+  // output-column geometry: plain -> BN columns at n0; GEGLU -> BN/2 columns at n0/2, MMA columns
+  // come in 128-wide groups [64 value | 64 gate]
+  const int n_out_total = p.geglu ? p.N / 2 : p.N;
+  const int out_cols_tile = p.geglu ? BN / 2 : BN;
+  const int nout0 = p.geglu ? n0 / 2 : n0;
+
+  for (int c = 0; c < out_cols_tile; c += 32) {
+    if (nout0 + c >= n_out_total) break;  // warp-uniform
+    float v[32];
+    {
+      uint32_t u[32];
+      const int mc = p.geglu ? ((c >> 6) * 128 + (c & 63)) : c;  // MMA column of this chunk
+      tmem_ld_32x32(lane_addr + mc, u);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(u[j]) * rs;
+      if (p.bias) {
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + mc);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (n0 + mc + 4 * j < p.N) {
+            const float4 b = __ldg(b4 + j);
+            v[4 * j + 0] += b.x;
+            v[4 * j + 1] += b.y;
+            v[4 * j + 2] += b.z;
+            v[4 * j + 3] += b.w;
+          }
+        }
+      }
+      if (p.geglu) {
+        uint32_t g[32];
+        tmem_ld_32x32(lane_addr + mc + 64, g);
+        tmem_ld_wait();
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + mc + 64);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias) b = __ldg(b4 + j);
+          v[4 * j + 0] *= gelu_erf(__uint_as_float(g[4 * j + 0]) * rs + b.x);
+          v[4 * j + 1] *= gelu_erf(__uint_as_float(g[4 * j + 1]) * rs + b.y);
+          v[4 * j + 2] *= gelu_erf(__uint_as_float(g[4 * j + 2]) * rs + b.z);
+          v[4 * j + 3] *= gelu_erf(__uint_as_float(g[4 * j + 3]) * rs + b.w);
+        }
+      }
+    }
+    if (!valid) continue;
+    const int ncol = nout0 + c;  // first output column of this chunk
+    if (p.row_bias) {
+      const float4* b4 =
+          reinterpret_cast<const float4*>(p.row_bias + static_cast<long long>(grp) * n_out_total + ncol);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (ncol + 4 * j < n_out_total) {
+          const float4 b = __ldg(b4 + j);
+          v[4 * j + 0] += b.x;
+          v[4 * j + 1] += b.y;
+          v[4 * j + 2] += b.z;
+          v[4 * j + 3] += b.w;
+        }
+      }
+    }
+    if (p.residual) {
+      const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + row * p.ldr + ncol);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (ncol + 8 * j < n_out_total) {
+          const uint4 q = __ldg(r4 + j);
+          const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float2 f = unpack_bf16x2(w[t]);
+            v[8 * j + 2 * t] += f.x;
+            v[8 * j + 2 * t + 1] += f.y;
+          }
+        }
+      }
+    }
+    if (p.blend_x) {
+      const uint4* x4 = reinterpret_cast<const uint4*>(p.blend_x + row * p.ldx + ncol);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (ncol + 8 * j < n_out_total) {
+          const uint4 q = __ldg(x4 + j);
+          const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float2 f = unpack_bf16x2(w[t]);
+            v[8 * j + 2 * t] = alpha * f.x + beta * v[8 * j + 2 * t];
+            v[8 * j + 2 * t + 1] = alpha * f.y + beta * v[8 * j + 2 * t + 1];
+          }
+        }
+      }
+    }
+    if (p.out_f32) {
+      float4* o4 = reinterpret_cast<float4*>(static_cast<float*>(p.out) + row * p.ldc + ncol);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (ncol + 4 * j < n_out_total)
+          o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else {
+      uint4* o4 =
+          reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + row * p.ldc + ncol);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (ncol + 8 * j < n_out_total)
+          o4[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                             pack_bf16x2(v[8 * j + 4], v[8 * j + 5]),
+                             pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<TCOLS>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------ host side
+template <int BN, int STAGES>
+static int launch(const CUtensorMap* a0, const CUtensorMap* a1, const CUtensorMap* b,
+                  const GemmKParams& p, int m_tiles, cudaStream_t stream) {
+  constexpr int SMEM = STAGES * (128 * 128 + BN * 128) + 1024 + 256;
+  static bool configured = false;
+  if (!configured) {
+    SA_CUDA_CHECK(cudaFuncSetAttribute(gemm_tap_kernel<BN, STAGES>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    configured = true;
+  }
+  dim3 grid((p.N + BN - 1) / BN, m_tiles, 1);
+  gemm_tap_kernel<BN, STAGES><<<grid, 128, SMEM, stream>>>(*a0, *a1, *b, p);
+  SA_CUDA_CHECK(cudaGetLastError());
+  return SA_OK;
+}
+
+static int pick_tile(int m, int n, int geglu) {
+  // cost model: an SM works through ceil(ctas / sms) tiles, each costing ~ (bn + overhead) columns
+  // of MMA time; pick the exact divisor of n that minimises it (ties -> larger tile).
+  const long long m_tiles = (m + 127) / 128;
+  const int sms = num_sms();
+  const int cand[5] = {256, 160, 128, 64, 32};
+  int best = 0;
+  long long best_cost = 0;
+  for (int i = 0; i < 5; ++i) {
+    const int bn = cand[i];
+    if (n % bn != 0) continue;
+    if (geglu && bn != 256 && bn != 128) continue;
+    const long long ctas = m_tiles * (n / bn);
+    const long long cost = ((ctas + sms - 1) / sms) * (bn + 32);
+    if (best == 0 || cost < best_cost) {
+      best = bn;
+      best_cost = cost;
+    }
+  }
+  if (best) return best;
+  // no exact divisor: smallest tile that covers n with least padding
+  if (n <= 32) return 32;
+  if (n <= 64) return 64;
+  return 128;
+}
+
+// choose a box (b1,b2,b3), b1*b2*b3 == 128, each a power of two <= 128, maximising the fraction of
+// useful rows over the whole grid; ties go to the widest b1 (longest contiguous TMA rows).
+static void pick_box(int d1, int d2, int d3, int* b1, int* b2, int* b3) {
+  double best = -1.0;
+  for (int e1 = 7; e1 >= 0; --e1)
+    for (int e2 = 7 - e1; e2 >= 0; --e2) {
+      const int x1 = 1 << e1, x2 = 1 << e2, x3 = 128 / (x1 * x2);
+      const double cover = static_cast<double>((d1 + x1 - 1) / x1 * x1) *
+                           ((d2 + x2 - 1) / x2 * x2) * ((d3 + x3 - 1) / x3 * x3);
+      const double eff = static_cast<double>(d1) * d2 * d3 / cover;
+      if (eff > best + 1e-9) {
+        best = eff;
+        *b1 = x1;
+        *b2 = x2;
+        *b3 = x3;
+      }
+    }
+}
+
+}  // namespace sa
+
+extern "C" int sa_gemm_pick_tile(int32_t m, int32_t n, int32_t geglu) {
+  return sa::pick_tile(m, n, geglu);
+}
+
+extern "C" int sa_gemm_tap(const sa_gemm_args* a, void* stream_) {
+  using namespace sa;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!a || !a->a0 || !a->w || !a->out) return fail(SA_ERR_INVALID, "sa_gemm_tap: null pointer");
+  if (a->c0 <= 0 || a->c0 % 64 || a->c1 < 0 || a->c1 % 64 || (a->c1 > 0 && !a->a1))
+    return fail(SA_ERR_INVALID, "sa_gemm_tap: channels must be multiples of 64 (c0=%d c1=%d)", a->c0,
+                a->c1);
+  if (a->ntaps < 1 || a->ntaps > 9) return fail(SA_ERR_INVALID, "sa_gemm_tap: ntaps=%d", a->ntaps);
+  if (a->n <= 0 || a->n % 8) return fail(SA_ERR_INVALID, "sa_gemm_tap: n=%d must be a multiple of 8", a->n);
+  if (a->d1 <= 0 || a->d2 <= 0 || a->d3 <= 0) return fail(SA_ERR_INVALID, "sa_gemm_tap: empty grid");
+  if (a->lda0 < a->c0 || a->lda0 % 8 || (a->c1 > 0 && (a->lda1 < a->c1 || a->lda1 % 8)))
+    return fail(SA_ERR_INVALID, "sa_gemm_tap: bad lda");
+  if (a->geglu && (a->n % 128)) return fail(SA_ERR_INVALID, "sa_gemm_tap: geglu needs n %% 128 == 0");
+  const int n_out = a->geglu ? a->n / 2 : a->n;
+  if (a->ldc < n_out || a->ldc % (a->out_f32 ? 4 : 8)) return fail(SA_ERR_INVALID, "sa_gemm_tap: bad ldc");
+  if (a->residual && (a->ldr < n_out || a->ldr % 8)) return fail(SA_ERR_INVALID, "sa_gemm_tap: bad ldr");
+  if (a->blend_x && (a->ldx < n_out || a->ldx % 8)) return fail(SA_ERR_INVALID, "sa_gemm_tap: bad ldx");
+  const long long M = static_cast<long long>(a->d1) * a->d2 * a->d3;
+  if (M > 0x7fffffffLL) return fail(SA_ERR_INVALID, "sa_gemm_tap: M too large");
+
+  GemmKParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = static_cast<int>(M);
+  p.N = a->n;
+  p.kc0 = a->c0 / 64;
+  p.kcpt = (a->c0 + a->c1) / 64;
+  p.ntaps = a->ntaps;
+  p.d1 = a->d1;
+  p.d2 = a->d2;
+  p.d3 = a->d3;
+  pick_box(a->d1, a->d2, a->d3, &p.b1, &p.b2, &p.b3);
+  p.t1 = (a->d1 + p.b1 - 1) / p.b1;
+  p.t2 = (a->d2 + p.b2 - 1) / p.b2;
+  const int t3 = (a->d3 + p.b3 - 1) / p.b3;
+  const long long m_tiles = static_cast<long long>(p.t1) * p.t2 * t3;
+  if (m_tiles > 65535) return fail(SA_ERR_INVALID, "sa_gemm_tap: too many row tiles (%lld)", m_tiles);
+  for (int i = 0; i < a->ntaps * 3; ++i) p.tap_off[i] = a->tap_off[i];
+  p.bias = a->bias;
+  p.row_bias = a->row_bias;
+  p.row_scale = a->row_scale;
+  p.rows_per_group = a->rows_per_group > 0 ? a->rows_per_group : 1;
+  p.residual = static_cast<const __nv_bfloat16*>(a->residual);
+  p.ldr = a->ldr;
+  p.blend_x = static_cast<const __nv_bfloat16*>(a->blend_x);
+  p.ldx = a->ldx;
+  p.alpha = a->alpha;
+  p.geglu = a->geglu;
+  p.out = a->out;
+  p.ldc = a->ldc;
+  p.out_f32 = a->out_f32;
+
+  int bn = a->tile_n ? a->tile_n : pick_tile(p.M, p.N, p.geglu);
+  if (p.geglu && bn != 128 && bn != 256) return fail(SA_ERR_INVALID, "sa_gemm_tap: geglu tile must be 128/256");
+
+  // tensor maps: A sources as rank-4 (C, d1, d2, d3); W as rank-2 (K, N)
+  const CUtensorMap* tma[2] = {nullptr, nullptr};
+  for (int s = 0; s < 2; ++s) {
+    const void* base = s == 0 ? a->a0 : a->a1;
+    const int c = s == 0 ? a->c0 : a->c1;
+    const long long ld = s == 0 ? a->lda0 : a->lda1;
+    if (s == 1 && c == 0) {
+      tma[1] = tma[0];
+      break;
+    }
+    uint64_t dims[4] = {static_cast<uint64_t>(c), static_cast<uint64_t>(a->d1),
+                        static_cast<uint64_t>(a->d2), static_cast<uint64_t>(a->d3)};
+    uint64_t strides[3] = {static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(ld) * 2 * a->d1,
+                           static_cast<uint64_t>(ld) * 2 * a->d1 * a->d2};
+    uint32_t box[4] = {64, static_cast<uint32_t>(p.b1), static_cast<uint32_t>(p.b2),
+                       static_cast<uint32_t>(p.b3)};
+    tma[s] = get_tmap_bf16(base, 4, dims, strides, box);
+    if (!tma[s]) return SA_ERR_TMA;
+  }
+  const long long ktot = static_cast<long long>(a->ntaps) * (a->c0 + a->c1);
+  uint64_t wdims[2] = {static_cast<uint64_t>(ktot), static_cast<uint64_t>(a->n)};
+  uint64_t wstr[1] = {static_cast<uint64_t>(ktot) * 2};
+  uint32_t wbox[2] = {64, static_cast<uint32_t>(bn)};
+  const CUtensorMap* tmb = get_tmap_bf16(a->w, 2, wdims, wstr, wbox);
+  if (!tmb) return SA_ERR_TMA;
+
+  const int mt = static_cast<int>(m_tiles);
+  switch (bn) {
+    case 32: return launch<32, 4>(tma[0], tma[1], tmb, p, mt, stream);
+    case 64: return launch<64, 4>(tma[0], tma[1], tmb, p, mt, stream);
+    case 128: return launch<128, 3>(tma[0], tma[1], tmb, p, mt, stream);
+    case 160: return launch<160, 3>(tma[0], tma[1], tmb, p, mt, stream);
+    case 256: return launch<256, 2>(tma[0], tma[1], tmb, p, mt, stream);
+    default: return fail(SA_ERR_INVALID, "sa_gemm_tap: unsupported tile_n=%d", bn);
+  }
+}

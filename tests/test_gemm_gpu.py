@@ -1,0 +1,131 @@
+"""GPU parity of the tapped tcgen05 GEMM (sa_gemm_tap) against fp32 torch ops on the same
+bf16-rounded inputs.  Tolerance: max |err| / max |ref| <= 2e-3 (north_star per-kernel bound)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-3
+
+
+def relerr(a, b):
+    return ((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-12)).item()
+
+
+def rnd(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(*shape, generator=g, device="cuda") * scale).to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("m,k,n,tile", [
+    (128, 64, 64, 64), (256, 128, 128, 128), (1000, 320, 320, 160), (4096, 1280, 1280, 256),
+    (384, 192, 64, 32), (777, 640, 640, 0), (65536, 320, 960, 0), (1024, 1280, 1280, 0),
+    (130, 1024, 8, 32),
+])
+def test_plain_linear(m, k, n, tile):
+    from stableanimator_b200 import ops
+    a, w = rnd(m, k, seed=1), rnd(n, k, scale=k ** -0.5, seed=2)
+    bias = torch.randn(n, device="cuda")
+    out = ops.gemm_tap(a, w, bias=bias, tile_n=tile)
+    ref = a.float() @ w.float().t() + bias
+    torch.cuda.synchronize()
+    assert out.shape == (m, n)
+    assert relerr(out, ref) <= TOL
+
+
+def test_epilogue_all():
+    from stableanimator_b200 import ops
+    m, k, n, rpg = 2048, 320, 320, 512
+    a, w = rnd(m, k, seed=3), rnd(n, k, scale=k ** -0.5, seed=4)
+    bias = torch.randn(n, device="cuda")
+    rb = torch.randn(m // rpg, n, device="cuda")
+    rs = torch.rand(m // rpg, device="cuda") + 0.5
+    res, bx = rnd(m, n, seed=5), rnd(m, n, seed=6)
+    alpha = 0.62
+    out = ops.gemm_tap(a, w, bias=bias, row_bias=rb, row_scale=rs, rows_per_group=rpg,
+                       residual=res, blend_x=bx, alpha=alpha)
+    acc = a.float() @ w.float().t()
+    g = torch.arange(m, device="cuda") // rpg
+    v = acc * rs[g][:, None] + bias + rb[g] + res.float()
+    ref = alpha * bx.float() + (1 - alpha) * v
+    assert relerr(out, ref) <= TOL
+
+
+@pytest.mark.parametrize("c,tile", [(64, 128), (320, 0), (320, 256)])
+def test_geglu(c, tile):
+    from stableanimator_b200 import ops
+    m = 1536
+    a = rnd(m, c, seed=7)
+    w, b = rnd(8 * c, c, scale=c ** -0.5, seed=8), torch.randn(8 * c, device="cuda")
+    wi, bi = ops.interleave_geglu(w, b)
+    out = ops.gemm_tap(a, wi, bias=bi, geglu=True, tile_n=tile)
+    proj = a.float() @ w.float().t() + b
+    val, gate = proj.chunk(2, dim=-1)
+    ref = val * F.gelu(gate)
+    assert out.shape == (m, 4 * c)
+    assert relerr(out, ref) <= TOL
+
+
+def test_strided_a_and_out():
+    from stableanimator_b200 import ops
+    m, c = 512, 128
+    qkv = rnd(m, 3 * c, seed=9)
+    w = rnd(c, c, scale=c ** -0.5, seed=10)
+    big = torch.zeros(m, 2 * c, device="cuda", dtype=torch.bfloat16)
+    ops.gemm_tap(qkv[:, c:2 * c], w, out=big[:, c:])
+    ref = qkv[:, c:2 * c].float() @ w.float().t()
+    assert relerr(big[:, c:], ref) <= TOL
+    assert big[:, :c].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("f,h,w_,cin,cout", [
+    (2, 8, 8, 64, 64), (3, 16, 16, 128, 64), (2, 32, 32, 64, 128), (16, 64, 64, 320, 320),
+    (4, 4, 4, 256, 256), (1, 18, 9, 64, 64), (2, 72, 36, 64, 64),
+])
+def test_conv3x3(f, h, w_, cin, cout):
+    from stableanimator_b200 import ops
+    x = rnd(f, h, w_, cin, seed=11)                       # NHWC
+    wt = rnd(cout, cin, 3, 3, scale=(9 * cin) ** -0.5, seed=12)  # OIHW like nn.Conv2d
+    bias = torch.randn(cout, device="cuda")
+    wp = wt.permute(0, 2, 3, 1).reshape(cout, 9 * cin).contiguous()  # [O, (ky,kx,ci)]
+    out = ops.gemm_tap(x, wp, grid=(w_, h, f), taps=ops.TAPS_3X3, bias=bias)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, padding=1).permute(0, 2, 3, 1)
+    assert relerr(out.reshape(f, h, w_, cout), ref) <= TOL
+
+
+def test_conv3x3_concat_sources():
+    from stableanimator_b200 import ops
+    f, h, w_, c0, c1, cout = 2, 16, 16, 128, 64, 128
+    x0, x1 = rnd(f, h, w_, c0, seed=13), rnd(f, h, w_, c1, seed=14)
+    wt = rnd(cout, c0 + c1, 3, 3, scale=(9 * (c0 + c1)) ** -0.5, seed=15)
+    wp = wt.permute(0, 2, 3, 1).reshape(cout, -1).contiguous()
+    out = ops.gemm_tap(x0, wp, a1=x1, grid=(w_, h, f), taps=ops.TAPS_3X3)
+    xin = torch.cat([x0, x1], dim=-1).float().permute(0, 3, 1, 2)
+    ref = F.conv2d(xin, wt.float(), None, padding=1).permute(0, 2, 3, 1)
+    assert relerr(out.reshape(f, h, w_, cout), ref) <= TOL
+
+
+@pytest.mark.parametrize("b,f,s,c", [(1, 8, 64, 64), (2, 16, 256, 128), (1, 16, 4096, 320), (1, 4, 16, 64)])
+def test_temporal_conv(b, f, s, c):
+    from stableanimator_b200 import ops
+    x = rnd(b, f, s, c, seed=16)
+    wt = rnd(c, c, 3, 1, 1, scale=(3 * c) ** -0.5, seed=17)  # OIDHW like nn.Conv3d
+    bias = torch.randn(c, device="cuda")
+    wp = wt[:, :, :, 0, 0].permute(0, 2, 1).reshape(c, 3 * c).contiguous()  # [O, (kt, ci)]
+    out = ops.gemm_tap(x, wp, grid=(s, f, b), taps=ops.TAPS_T3, bias=bias)
+    xin = x.float().permute(0, 3, 1, 2)[..., None]  # [B, C, F, S, 1]
+    ref = F.conv3d(xin, wt.float(), bias, padding=(1, 0, 0))[..., 0].permute(0, 2, 3, 1)
+    assert relerr(out.reshape(b, f, s, c), ref) <= TOL
+
+
+def test_fp32_out_small_n():
+    from stableanimator_b200 import ops
+    f, h, w_, cin = 2, 16, 16, 64
+    x = rnd(f, h, w_, cin, seed=18)
+    wt = rnd(4, cin, 3, 3, scale=(9 * cin) ** -0.5, seed=19)
+    wp = torch.zeros(8, 9 * cin, device="cuda", dtype=torch.bfloat16)
+    wp[:4] = wt.permute(0, 2, 3, 1).reshape(4, -1)
+    out = ops.gemm_tap(x, wp, grid=(w_, h, f), taps=ops.TAPS_3X3, out_f32=True)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), None, padding=1).permute(0, 2, 3, 1)
+    assert out.dtype == torch.float32
+    assert relerr(out.reshape(f, h, w_, 8)[..., :4], ref) <= 1e-4
