@@ -1,0 +1,85 @@
+"""Generate tests/golden/*.pt from the UNMODIFIED reference (build container only).
+
+    python oracle/make_golden.py
+
+Imports /root/reference/animation/modules/{unet,pose_net}.py through oracle/stubs, loads the
+deterministic synthetic weights (stableanimator_b200/synth.py) with ``strict=True``, runs the
+reference in fp32 on synthetic inputs and stores inputs' recipe + outputs.  While doing so it asserts
+that oracle/unet_oracle.py reproduces the reference to fp32 round-off (the oracle pin).
+Fixtures are small (tiny config outputs and a few taps); weights are regenerated from the seed.
+"""
+from __future__ import annotations
+
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+from oracle import ref_loader, unet_oracle  # noqa: E402
+from stableanimator_b200.arch import UNetConfig  # noqa: E402
+from stableanimator_b200.synth import (synth_inputs, synth_posenet_state_dict,  # noqa: E402
+                                       synth_unet_state_dict)
+
+GOLD = ROOT / "tests" / "golden"
+SEED = 23123134
+
+
+def rel(a, b):
+    return ((a - b).abs().max() / b.abs().max()).item()
+
+
+def unet_case(cfg: UNetConfig, name: str, frames: int, h: int, w: int, t: float, cond: bool):
+    sd = synth_unet_state_dict(cfg, SEED)
+    ref = ref_loader.build_reference_unet(cfg, sd)
+    inp = synth_inputs(cfg, frames, h, w, SEED)
+    row = 1 if cond else 0
+    sample = torch.cat([inp["latents"].expand(1, frames, 4, h, w) * 3.0,
+                        inp["image_latents"][row:row + 1]], dim=2)
+    ehs = inp["encoder_hidden_states"][row:row + 1]
+    ati = inp["added_time_ids"][row:row + 1]
+    pose_latents = None
+    if cond:
+        _, rp, _ = ref_loader.import_reference()
+        pn = rp.PoseNet(noise_latent_channels=cfg.block_out_channels[0]).eval()
+        psd = synth_posenet_state_dict(cfg.block_out_channels[0], SEED)
+        pn.load_state_dict(psd, strict=True)
+        with torch.no_grad():
+            pose_latents = pn(inp["pose"])
+        mine_pose = unet_oracle.pose_net(psd, inp["pose"])
+        e = rel(mine_pose, pose_latents)
+        print(f"[{name}] pose_net oracle vs reference: {e:.2e}")
+        assert e < 1e-5
+    tt = torch.tensor(t)
+    with torch.no_grad():
+        out_ref = ref(sample, tt, ehs, ati, pose_latents=pose_latents)[0]
+    taps = {}
+    out_mine = unet_oracle.unet_forward(sd, cfg, sample, tt, ehs, ati, pose_latents, taps=taps)
+    e = rel(out_mine, out_ref)
+    print(f"[{name}] unet oracle vs reference: max rel err {e:.2e}; out std {out_ref.std():.4f}")
+    assert e < 2e-5, "oracle restatement diverges from the reference"
+    keep = {k: v.clone() for k, v in taps.items()
+            if k in ("conv_in", "down_blocks.0.resnets.0", "down_blocks.0.attentions.0", "mid_block")}
+    torch.save({"config": name, "frames": frames, "h": h, "w": w, "t": t, "cond": cond, "seed": SEED,
+                "out": out_ref.clone(), "taps": keep,
+                "pose_latents": None if pose_latents is None else pose_latents.clone()},
+               GOLD / f"unet_{name}.pt")
+
+
+def main():
+    GOLD.mkdir(parents=True, exist_ok=True)
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    tiny = UNetConfig.tiny()
+    unet_case(tiny, "tiny_cond_f4_16x16", 4, 16, 16, 1.637770, True)
+    unet_case(tiny, "tiny_uncond_f4_16x16", 4, 16, 16, 0.338294, False)
+    unet_case(tiny, "tiny_cond_f2_8x24", 2, 8, 24, -0.462234, True)
+    if "--full" in sys.argv:
+        unet_case(UNetConfig.full(), "full_cond_f2_8x8", 2, 8, 8, 1.064048, True)
+    print("golden written to", GOLD)
+
+
+if __name__ == "__main__":
+    main()
