@@ -61,7 +61,8 @@ typedef struct sa_gemm_args {
   const void* w;         /* bf16 [N (padded to >= tile), ntaps*(c0+c1)] */
   int32_t n;             /* output columns produced by the MMA (before GEGLU halving); n % 8 == 0 */
   const float* bias;     /* [n] or NULL */
-  const float* row_bias; /* [groups, n_out] or NULL */
+  const float* row_bias; /* [groups, ldrb] (first n_out columns) or NULL */
+  int32_t ldrb;          /* row stride of row_bias in floats (0 -> n_out) */
   const float* row_scale;/* [groups] or NULL */
   int32_t rows_per_group;
   const void* residual;  /* bf16 [M, ldr] or NULL */
@@ -79,6 +80,100 @@ typedef struct sa_gemm_args {
 int sa_gemm_tap(const sa_gemm_args* args, void* stream);
 /* tile_n the heuristic would pick (weights for GEGLU must be interleaved with this tile) */
 int sa_gemm_pick_tile(int32_t m, int32_t n, int32_t geglu);
+
+/* ------------------------------------------------------------------------------------------
+ * Spatial self-attention, head_dim 64 (tcgen05 flash attention).
+ * Replaces xformers.ops.memory_efficient_attention in AnimationAttnProcessor.__call__
+ * (unet.py:1893-1905).  qkv: bf16 [frames*S, ld], column blocks q | k | v of width C = heads*64
+ * (the fused to_q/to_k/to_v projection output); out: bf16 [frames*S, ldo].
+ * ------------------------------------------------------------------------------------------ */
+int sa_attn_spatial(const void* qkv, int32_t ld, int32_t frames, int32_t S, int32_t C,
+                    int32_t heads, void* out, int32_t ldo, void* stream);
+
+/* Temporal self-attention over the F <= 16 frames of a tile, per (pixel, head).
+ * Replaces XFormersAttnProcessor.__call__ self-attention case (unet.py:1830-1848) together with the
+ * [B*F,S,C] <-> [B*S,F,C] permutes of TemporalBasicTransformerBlock.forward (:931-933,:954-956).
+ * qkv: bf16 [B*F*S, ld] (row = (b*F + f)*S + s), out: bf16 [B*F*S, ldo]. */
+int sa_attn_temporal(const void* qkv, int32_t ld, int32_t B, int32_t F, int32_t S, int32_t C,
+                     int32_t heads, void* out, int32_t ldo, void* stream);
+
+/* ID cross-attention against the num_tokens (=4) face tokens + per-frame Sum/Sum^2 of the result.
+ * Replaces AnimationIDAttnNormalizedProcessor.__call__ lines unet.py:1999-2019 (id_to_k / id_to_v
+ * come from sa_small_linear).  q: bf16 [B*F*S, ldq]; ik, iv: fp32, token t of batch b at
+ * ik + b*kv_batch_stride + t*kv_tok_stride (C contiguous floats); out: bf16
+ * [B*F*S, ldo]; stats: fp64 [B*F, 2] workspace (zeroed by the call). */
+int sa_attn_id(const void* q, int32_t ldq, const float* ik, const float* iv, int64_t kv_tok_stride,
+               int64_t kv_batch_stride, int32_t B, int32_t F, int32_t S, int32_t C, int32_t heads,
+               int32_t num_tokens, void* out, int32_t ldo, void* stats, void* stream);
+
+/* Distribution alignment folded through to_out (unet.py:2018-2024): per frame
+ *   row_scale[f]   = std_lat / (std_ip + 1e-5)          (torch.std: unbiased, N = S*C)
+ *   row_bias[f, n] = (W.v_clip)[b, n] + bias[n] + (mean_lat - row_scale[f]*mean_ip) * rowsum(W)[n]
+ * so that to_out(h + aligned(ip)) == row_scale * (ip @ W^T) + row_bias, with h == v_clip broadcast
+ * (softmax over the single CLIP key).  vclip, wv: fp32 [B, C]; w_rowsum, bias: fp32 [C]. */
+int sa_attn_id_finalize(const void* stats, const float* vclip, int64_t vclip_batch_stride,
+                        const float* wv, const float* w_rowsum, const float* bias, int32_t B,
+                        int32_t F, int32_t S, int32_t C, float* row_scale, float* row_bias,
+                        void* stream);
+
+/* GroupNorm(32 groups) (+SiLU): statistics over rows_per_stat rows x (C/32) channels, fp64 sums.
+ * nn.GroupNorm + nn.SiLU at unet.py:171-173,575,1632,1640,1643 (rows_per_stat = h*w: per frame)
+ * and :1709,1722,1731 (rows_per_stat = F*h*w: TemporalResnetBlock, whole tile).  x0 (+ optional x1,
+ * channel concat = torch.cat skip input :1347,1433) bf16 [ns*rows_per_stat, ld*]; out bf16
+ * [.., c0+c1]; stats_ws: fp64 [ns, 32, 2]. */
+int sa_groupnorm(const void* x0, const void* x1, int32_t c0, int32_t c1, int32_t ld0, int32_t ld1,
+                 int64_t rows_per_stat, int32_t ns, const float* gamma, const float* beta, float eps,
+                 int32_t do_silu, void* stats_ws, void* out, int32_t ldo, void* stream);
+
+/* LayerNorm over C (unet.py:499,510,521,892,898,907,916), eps 1e-5:
+ *   y = LN(x + addv[row / rows_per_group]); if x_out: x_out = x + addv (the new residual stream).
+ * addv fp32 [groups, C] or NULL (frame position embedding :686, temporal attn2 constant :946-947). */
+int sa_layernorm(const void* x, int32_t ldx, int64_t rows, int32_t c, const float* addv,
+                 int32_t rows_per_group, void* x_out, int32_t ldxo, const float* gamma,
+                 const float* beta, float eps, void* y, int32_t ldy, void* stream);
+
+/* Skinny linear (m <= a few dozen rows), fp32 activations, bf16 weights [n, k], fp32 out:
+ *   out (+)= act_out(act_in(x) @ W^T + b).  TimestepEmbedding (unet.py:429-436), time_emb_proj(silu(.))
+ *   (:1669-1670,:1754-1755), context K/V projections (:1974-1975,:1999-2000,:1834-1835). */
+int sa_small_linear(const float* x, int32_t ldx, int32_t m, const void* w, int32_t k, int32_t n,
+                    const float* bias, int32_t silu_in, int32_t silu_out, int32_t accumulate,
+                    float* out, int32_t ldo, void* stream);
+
+/* get_timestep_embedding (unet.py:365-390): out[i] = [cos(t_i f) | sin(t_i f)], fp32 [n, dim]. */
+int sa_sinusoid(const float* t, int32_t n, int32_t dim, float* out, void* stream);
+
+/* Direct NHWC convolution for tiny channel counts: conv_in (unet.py:69,283) with the PoseNet
+ * residual add (:284-286; `add` applies to images n >= add_from) and the PoseNet conv stack
+ * (pose_net.py:14-37).  wt: bf16 [k*k*cin, cout_pad]; out = (act(conv + bias)) * scale (+ add). */
+int sa_conv_direct(const void* x, int32_t n, int32_t h, int32_t w, int32_t cin, const void* wt,
+                   const float* bias, int32_t cout, int32_t cout_pad, int32_t ksz, int32_t stride,
+                   int32_t pad, int32_t silu_out, float scale, const void* add, int32_t add_from,
+                   void* out, void* stream);
+
+/* F.interpolate(scale_factor=2, mode="nearest") on NHWC bf16 (unet.py:1799). */
+int sa_upsample2x(const void* in, int32_t n, int32_t h, int32_t w, int32_t c, void* out, void* stream);
+/* im2col of the 3x3 stride-2 pad-1 Downsample2D conv (unet.py:1474): out bf16 [n*h/2*w/2, 9*c]. */
+int sa_im2col_s2(const void* in, int32_t n, int32_t h, int32_t w, int32_t c, void* out, void* stream);
+
+/* Boundary layout conversion: reference tensors are NCHW, the kernels are NHWC. */
+int sa_nchw_to_nhwc(const void* src, int32_t src_is_bf16, int32_t n, int32_t c, int32_t hw, void* dst,
+                    void* stream);
+int sa_nhwc_to_nchw_f32(const float* src, int32_t lds, int32_t n, int32_t c, int32_t hw, float* dst,
+                        void* stream);
+
+/* Sampler (InferenceAnimationPipeline.__call__ loop body, inference_pipeline_animation.py:644-699):
+ *  prepare   : sample[b,t] = [latents[idx[t]] / sqrt(sigma^2+1) | image_latents[b0+b, idx[t]]]  (:644-650)
+ *  accumulate: noise[b0+b, idx[t]] += unet_out[b,t] * weight[t]                                 (:673,685)
+ *  step      : eps = (n_u + g_f (n_c - n_u)) / cnt_f ; Euler v-prediction update in fp32         (:689-699)
+ * latents fp32 [F,4,h,w]; image_latents fp32 [2,F,4,h,w]; noise fp32 [2,F,4,h,w]. */
+int sa_sampler_prepare(const float* latents, const float* image_latents, const int32_t* idx,
+                       int32_t nb, int32_t b0, int32_t t, int32_t f, int32_t hw, float sigma, void* out,
+                       void* stream);
+int sa_sampler_accumulate(const float* unet_out, int32_t ldo, const int32_t* idx, const float* weight,
+                          int32_t nb, int32_t b0, int32_t t, int32_t f, int32_t hw, float* noise,
+                          void* stream);
+int sa_sampler_step(const float* noise, const float* cnt, const float* guidance, int32_t f, int32_t chw,
+                    float sigma, float sigma_next, float* latents, void* stream);
 
 #ifdef __cplusplus
 }

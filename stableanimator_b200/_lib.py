@@ -32,7 +32,7 @@ class GemmArgs(C.Structure):
         ("tap_off", C.c_int32 * 27),
         ("w", C.c_void_p),
         ("n", C.c_int32),
-        ("bias", C.c_void_p), ("row_bias", C.c_void_p), ("row_scale", C.c_void_p),
+        ("bias", C.c_void_p), ("row_bias", C.c_void_p), ("ldrb", C.c_int32), ("row_scale", C.c_void_p),
         ("rows_per_group", C.c_int32),
         ("residual", C.c_void_p), ("ldr", C.c_int32),
         ("blend_x", C.c_void_p), ("ldx", C.c_int32),
@@ -72,6 +72,22 @@ _P, _I, _F, _L = C.c_void_p, C.c_int32, C.c_float, C.c_int64
 SIGNATURES: dict[str, list] = {
     "sa_gemm_tap": [C.POINTER(GemmArgs), _P],
     "sa_gemm_pick_tile": [_I, _I, _I],
+    "sa_attn_spatial": [_P, _I, _I, _I, _I, _I, _P, _I, _P],
+    "sa_attn_temporal": [_P, _I, _I, _I, _I, _I, _I, _P, _I, _P],
+    "sa_attn_id": [_P, _I, _P, _P, _L, _L, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P],
+    "sa_attn_id_finalize": [_P, _P, _L, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P],
+    "sa_groupnorm": [_P, _P, _I, _I, _I, _I, _L, _I, _P, _P, _F, _I, _P, _P, _I, _P],
+    "sa_layernorm": [_P, _I, _L, _I, _P, _I, _P, _I, _P, _P, _F, _P, _I, _P],
+    "sa_small_linear": [_P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _P, _I, _P],
+    "sa_sinusoid": [_P, _I, _I, _P, _P],
+    "sa_conv_direct": [_P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _I, _P, _P],
+    "sa_upsample2x": [_P, _I, _I, _I, _I, _P, _P],
+    "sa_im2col_s2": [_P, _I, _I, _I, _I, _P, _P],
+    "sa_nchw_to_nhwc": [_P, _I, _I, _I, _I, _P, _P],
+    "sa_nhwc_to_nchw_f32": [_P, _I, _I, _I, _I, _P, _P],
+    "sa_sampler_prepare": [_P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P],
+    "sa_sampler_accumulate": [_P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P],
+    "sa_sampler_step": [_P, _P, _P, _I, _I, _F, _F, _P, _P],
 }
 
 

@@ -29,6 +29,7 @@ struct GemmKParams {
   int tap_off[27];
   const float* bias;
   const float* row_bias;
+  int ldrb;
   const float* row_scale;
   int rows_per_group;
   const __nv_bfloat16* residual;
@@ -197,7 +198,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     const int ncol = nout0 + c;  // first output column of this chunk
     if (p.row_bias) {
       const float4* b4 =
-          reinterpret_cast<const float4*>(p.row_bias + static_cast<long long>(grp) * n_out_total + ncol);
+          reinterpret_cast<const float4*>(p.row_bias + static_cast<long long>(grp) * p.ldrb + ncol);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         if (ncol + 4 * j < n_out_total) {
@@ -349,6 +350,7 @@ extern "C" int sa_gemm_tap(const sa_gemm_args* a, void* stream_) {
   if (a->ldc < n_out || a->ldc % (a->out_f32 ? 4 : 8)) return fail(SA_ERR_INVALID, "sa_gemm_tap: bad ldc");
   if (a->residual && (a->ldr < n_out || a->ldr % 8)) return fail(SA_ERR_INVALID, "sa_gemm_tap: bad ldr");
   if (a->blend_x && (a->ldx < n_out || a->ldx % 8)) return fail(SA_ERR_INVALID, "sa_gemm_tap: bad ldx");
+  if (a->row_bias && a->ldrb % 4) return fail(SA_ERR_INVALID, "sa_gemm_tap: ldrb must be a multiple of 4");
   const long long M = static_cast<long long>(a->d1) * a->d2 * a->d3;
   if (M > 0x7fffffffLL) return fail(SA_ERR_INVALID, "sa_gemm_tap: M too large");
 
@@ -371,6 +373,7 @@ extern "C" int sa_gemm_tap(const sa_gemm_args* a, void* stream_) {
   for (int i = 0; i < a->ntaps * 3; ++i) p.tap_off[i] = a->tap_off[i];
   p.bias = a->bias;
   p.row_bias = a->row_bias;
+  p.ldrb = a->ldrb > 0 ? a->ldrb : (a->geglu ? a->n / 2 : a->n);
   p.row_scale = a->row_scale;
   p.rows_per_group = a->rows_per_group > 0 ? a->rows_per_group : 1;
   p.residual = static_cast<const __nv_bfloat16*>(a->residual);

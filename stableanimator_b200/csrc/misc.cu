@@ -1,0 +1,413 @@
+// Small / memory-bound kernels around the tensor-core path: skinny linears (time / context
+// embeddings), sinusoidal embeddings, direct convolution for tiny channel counts (conv_in,
+// PoseNet), nearest x2 upsample, stride-2 im2col, layout conversion at the drop-in boundary and
+// the fused sampler kernels (input assembly, tile blend, CFG + Euler step).
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace sa {
+
+// ------------------------------------------------------------------ skinny linear (M <= 16)
+// out[m, n] = act_out( sum_k act_in(x[m, k]) * W[n, k] + b[n] ).  One warp per output column.
+// TimestepEmbedding (unet.py:429-436), time_emb_proj(silu(temb)) (:1669-1670, :1754-1755), the
+// K/V projections of the 5 context tokens (:1974-1975, :1999-2000, :1834-1835).
+template <int MT>
+__global__ void __launch_bounds__(256)
+small_linear_kernel(const float* __restrict__ x, int ldx, int M, const __nv_bfloat16* __restrict__ w,
+                    int K, int N, const float* __restrict__ bias, int silu_in, int silu_out,
+                    int accumulate, float* __restrict__ out, int ldo) {
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int m0 = blockIdx.y * MT;
+  if (n >= N) return;
+  float acc[MT];
+#pragma unroll
+  for (int m = 0; m < MT; ++m) acc[m] = 0.f;
+  const __nv_bfloat16* wr = w + static_cast<long long>(n) * K;
+  for (int k = lane * 8; k < K; k += 256) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(wr + k));
+    const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
+    float wf[8];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 f = unpack_bf16x2(ww[t]);
+      wf[2 * t] = f.x;
+      wf[2 * t + 1] = f.y;
+    }
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      if (m0 + m < M) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(x + static_cast<long long>(m0 + m) * ldx + k));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(x + static_cast<long long>(m0 + m) * ldx + k + 4));
+        float xv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        if (silu_in) {
+#pragma unroll
+          for (int t = 0; t < 8; ++t) xv[t] = xv[t] / (1.0f + expf(-xv[t]));
+        }
+#pragma unroll
+        for (int t = 0; t < 8; ++t) acc[m] += xv[t] * wf[t];
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < MT; ++m) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], d);
+  }
+  if (lane == 0) {
+    const float b = bias ? bias[n] : 0.f;
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      if (m0 + m < M) {
+        float v = acc[m] + b;
+        if (silu_out) v = v / (1.0f + expf(-v));
+        float* dst = out + static_cast<long long>(m0 + m) * ldo + n;
+        *dst = accumulate ? *dst + v : v;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ sinusoidal embedding
+// get_timestep_embedding (unet.py:365-390): out[i] = [cos(t_i f_k) | sin(t_i f_k)], f_k = 1e4^(-k/half)
+__global__ void sinusoid_kernel(const float* __restrict__ t, int n, int dim, float* __restrict__ out) {
+  const int half = dim >> 1;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * half) return;
+  const int i = idx / half, k = idx % half;
+  const float freq = expf(-9.210340371976184f * static_cast<float>(k) / static_cast<float>(half));
+  const float arg = t[i] * freq;
+  out[static_cast<long long>(i) * dim + k] = cosf(arg);
+  out[static_cast<long long>(i) * dim + half + k] = sinf(arg);
+}
+
+// ------------------------------------------------------------------ direct convolution
+// NHWC bf16 in, [k*k*Cin, CoutPad] bf16 weights, one thread = one output pixel x 8 out channels.
+// conv_in (unet.py:69,283 + pose add :284-286) and the PoseNet stack (pose_net.py:14-37).
+__global__ void __launch_bounds__(256)
+conv_direct_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int Cin,
+                   const __nv_bfloat16* __restrict__ w, const float* __restrict__ bias, int Cout,
+                   int CoutPad, int ksz, int stride, int pad, int Ho, int Wo, int silu_out,
+                   float scale, const __nv_bfloat16* __restrict__ add, int add_from,
+                   __nv_bfloat16* __restrict__ out) {
+  const int octs = CoutPad >> 3;
+  const long long total = static_cast<long long>(N) * Ho * Wo * octs;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int oc = static_cast<int>(idx % octs) * 8;
+    long long pix = idx / octs;
+    const int xo = static_cast<int>(pix % Wo);
+    pix /= Wo;
+    const int yo = static_cast<int>(pix % Ho);
+    const int n = static_cast<int>(pix / Ho);
+    float acc[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) acc[t] = 0.f;
+    for (int ky = 0; ky < ksz; ++ky) {
+      const int yi = yo * stride + ky - pad;
+      if (yi < 0 || yi >= H) continue;
+      for (int kx = 0; kx < ksz; ++kx) {
+        const int xi = xo * stride + kx - pad;
+        if (xi < 0 || xi >= W) continue;
+        const __nv_bfloat16* xp = x + ((static_cast<long long>(n) * H + yi) * W + xi) * Cin;
+        const __nv_bfloat16* wp = w + static_cast<long long>((ky * ksz + kx) * Cin) * CoutPad + oc;
+        for (int ci = 0; ci < Cin; ++ci) {
+          const float xv = __bfloat162float(xp[ci]);
+          const uint4 u = __ldg(reinterpret_cast<const uint4*>(wp + static_cast<long long>(ci) * CoutPad));
+          const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float2 f = unpack_bf16x2(ww[t]);
+            acc[2 * t] += xv * f.x;
+            acc[2 * t + 1] += xv * f.y;
+          }
+        }
+      }
+    }
+    const long long orow = (static_cast<long long>(n) * Ho + yo) * Wo + xo;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      if (oc + t < Cout) {
+        float v = acc[t] + (bias ? bias[oc + t] : 0.f);
+        if (silu_out) v = silu(v);
+        v *= scale;
+        if (add && n >= add_from)
+          v += __bfloat162float(add[((static_cast<long long>(n - add_from) * Ho + yo) * Wo + xo) * Cout + oc + t]);
+        out[orow * Cout + oc + t] = __float2bfloat16_rn(v);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ nearest x2 upsample (NHWC)
+// F.interpolate(scale_factor=2, mode="nearest"), unet.py:1799: out[y, x] = in[y / 2, x / 2]
+__global__ void upsample2x_kernel(const uint4* __restrict__ in, int N, int H, int W, int C8,
+                                  uint4* __restrict__ out) {
+  const long long total = static_cast<long long>(N) * 4 * H * W * C8;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(idx % C8);
+    long long p = idx / C8;
+    const int xo = static_cast<int>(p % (2 * W));
+    p /= 2 * W;
+    const int yo = static_cast<int>(p % (2 * H));
+    const long long n = p / (2 * H);
+    out[idx] = __ldg(in + ((n * H + (yo >> 1)) * W + (xo >> 1)) * C8 + c);
+  }
+}
+
+// ------------------------------------------------------------------ im2col for 3x3 stride 2 pad 1
+// Downsample2D conv (unet.py:1474): out[(n, yo, xo), tap*C + c] = in[n, 2yo+ky-1, 2xo+kx-1, c] | 0
+__global__ void im2col_s2_kernel(const uint4* __restrict__ in, int N, int H, int W, int C8,
+                                 uint4* __restrict__ out) {
+  const int Ho = H >> 1, Wo = W >> 1;
+  const long long total = static_cast<long long>(N) * Ho * Wo * 9 * C8;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(idx % C8);
+    long long p = idx / C8;
+    const int tap = static_cast<int>(p % 9);
+    p /= 9;
+    const int xo = static_cast<int>(p % Wo);
+    p /= Wo;
+    const int yo = static_cast<int>(p % Ho);
+    const long long n = p / Ho;
+    const int yi = 2 * yo + tap / 3 - 1, xi = 2 * xo + tap % 3 - 1;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (yi >= 0 && yi < H && xi >= 0 && xi < W) v = __ldg(in + ((n * H + yi) * W + xi) * C8 + c);
+    out[idx] = v;
+  }
+}
+
+// ------------------------------------------------------------------ layout conversion (boundary)
+// src [N, C, HW] (fp32 or bf16) -> dst bf16 [N, HW, C]
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const T* __restrict__ src, int C, int HW,
+                                    __nv_bfloat16* __restrict__ dst) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, p = p0 + threadIdx.x;
+    if (c < C && p < HW) tile[j][threadIdx.x] = static_cast<float>(src[(static_cast<long long>(n) * C + c) * HW + p]);
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int p = p0 + j, c = c0 + threadIdx.x;
+    if (c < C && p < HW)
+      dst[(static_cast<long long>(n) * HW + p) * C + c] = __float2bfloat16_rn(tile[threadIdx.x][j]);
+  }
+}
+// src fp32 [N, HW, lds] (first C columns) -> dst [N, C, HW] fp32, dst = dst*keep + scale*src
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, int lds, int C, int HW,
+                                    float* __restrict__ dst) {
+  const long long total = static_cast<long long>(gridDim.y) * C * HW;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int n = blockIdx.y;
+  if (idx >= static_cast<long long>(C) * HW) return;
+  (void)total;
+  const int c = static_cast<int>(idx / HW), p = static_cast<int>(idx % HW);
+  dst[(static_cast<long long>(n) * C + c) * HW + p] = src[(static_cast<long long>(n) * HW + p) * lds + c];
+}
+
+// ------------------------------------------------------------------ sampler kernels
+// inference_pipeline_animation.py:644-650 for one frame tile: sample[b, t, y, x, 0:4] =
+// latents[idx[t]] / sqrt(sigma^2+1), [4:8] = image_latents[b, idx[t]]  (NHWC bf16, C = 8)
+__global__ void sampler_prepare_kernel(const float* __restrict__ latents,
+                                       const float* __restrict__ image_latents,
+                                       const int* __restrict__ idx, int nb, int b0, int T, int F, int HW,
+                                       float inv_scale, __nv_bfloat16* __restrict__ out) {
+  const long long total = static_cast<long long>(nb) * T * HW;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int p = static_cast<int>(i % HW);
+  const int t = static_cast<int>((i / HW) % T);
+  const int b = static_cast<int>(i / (static_cast<long long>(HW) * T));
+  const int f = idx[t];
+  float v[8];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    v[c] = latents[(static_cast<long long>(f) * 4 + c) * HW + p] * inv_scale;
+    v[4 + c] = image_latents[((static_cast<long long>(b0 + b) * F + f) * 4 + c) * HW + p];
+  }
+  *reinterpret_cast<uint4*>(out + i * 8) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                                      pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
+
+// :673,685: noise[b0 + b, idx[t]] += unet_out[b, t] * weight[t]   (unet_out: fp32 NHWC, ld = ldo)
+__global__ void sampler_accumulate_kernel(const float* __restrict__ unet_out, int ldo,
+                                          const int* __restrict__ idx, const float* __restrict__ weight,
+                                          int nb, int b0, int T, int F, int HW, float* __restrict__ noise) {
+  const long long total = static_cast<long long>(nb) * T * HW;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int p = static_cast<int>(i % HW);
+  const int t = static_cast<int>((i / HW) % T);
+  const int b = static_cast<int>(i / (static_cast<long long>(HW) * T));
+  const int f = idx[t];
+  const float w = weight[t];
+  const float4 o = *reinterpret_cast<const float4*>(unet_out + i * ldo);
+  float* dst = noise + ((static_cast<long long>(b0 + b) * F + f) * 4) * HW + p;
+  dst[0] += o.x * w;
+  dst[static_cast<long long>(HW)] += o.y * w;
+  dst[2LL * HW] += o.z * w;
+  dst[3LL * HW] += o.w * w;
+}
+
+// :689-699: eps = (n_u + g_f (n_c - n_u)) / cnt_f ; Euler v-prediction step in fp32:
+//   x0 = eps * (-sigma / sqrt(sigma^2+1)) + x / (sigma^2+1);  x += (x - x0) / sigma * (sigma_next - sigma)
+__global__ void sampler_step_kernel(const float* __restrict__ noise, const float* __restrict__ cnt,
+                                    const float* __restrict__ guidance, int F, int CHW, float sigma,
+                                    float sigma_next, float* __restrict__ latents) {
+  const long long total = static_cast<long long>(F) * CHW;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int f = static_cast<int>(i / CHW);
+  const float inv = 1.0f / cnt[f];
+  const float nu = noise[i] * inv, nc = noise[total + i] * inv;
+  const float eps = nu + guidance[f] * (nc - nu);
+  const float s2 = sigma * sigma + 1.0f;
+  const float x = latents[i];
+  const float x0 = eps * (-sigma / sqrtf(s2)) + x / s2;
+  const float d = (x - x0) / sigma;
+  latents[i] = x + d * (sigma_next - sigma);
+}
+
+}  // namespace sa
+
+using namespace sa;
+
+static inline unsigned grid_for(long long total, int block, int max_blocks = 148 * 16) {
+  long long g = (total + block - 1) / block;
+  if (g > max_blocks) g = max_blocks;
+  if (g < 1) g = 1;
+  return static_cast<unsigned>(g);
+}
+
+extern "C" int sa_small_linear(const float* x, int32_t ldx, int32_t m, const void* w, int32_t k,
+                               int32_t n, const float* bias, int32_t silu_in, int32_t silu_out,
+                               int32_t accumulate, float* out, int32_t ldo, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!x || !w || !out) return fail(SA_ERR_INVALID, "sa_small_linear: null pointer");
+  if (k % 8 || ldx % 4 || m < 1) return fail(SA_ERR_INVALID, "sa_small_linear: k %% 8, ldx %% 4 required");
+  const __nv_bfloat16* wp = static_cast<const __nv_bfloat16*>(w);
+  const unsigned gx = (n + 7) / 8;
+  if (m <= 2) {
+    small_linear_kernel<2><<<dim3(gx, (m + 1) / 2), 256, 0, stream>>>(x, ldx, m, wp, k, n, bias, silu_in, silu_out, accumulate, out, ldo);
+  } else if (m <= 4) {
+    small_linear_kernel<4><<<dim3(gx, (m + 3) / 4), 256, 0, stream>>>(x, ldx, m, wp, k, n, bias, silu_in, silu_out, accumulate, out, ldo);
+  } else {
+    small_linear_kernel<8><<<dim3(gx, (m + 7) / 8), 256, 0, stream>>>(x, ldx, m, wp, k, n, bias, silu_in, silu_out, accumulate, out, ldo);
+  }
+  SA_CUDA_CHECK(cudaGetLastError());
+  return SA_OK;
+}
+
+extern "C" int sa_sinusoid(const float* t, int32_t n, int32_t dim, float* out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!t || !out || dim % 2) return fail(SA_ERR_INVALID, "sa_sinusoid: bad arguments");
+  const int total = n * (dim / 2);
+  sinusoid_kernel<<<(total + 255) / 256, 256, 0, stream>>>(t, n, dim, out);
+  SA_CUDA_CHECK(cudaGetLastError());
+  return SA_OK;
+}
+
+extern "C" int sa_conv_direct(const void* x, int32_t n, int32_t h, int32_t w, int32_t cin,
+                              const void* wt, const float* bias, int32_t cout, int32_t cout_pad,
+                              int32_t ksz, int32_t stride, int32_t pad, int32_t silu_out, float scale,
+                              const void* add, int32_t add_from, void* out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!x || !wt || !out) return fail(SA_ERR_INVALID, "sa_conv_direct: null pointer");
+  if (cout_pad % 8 || cout_pad < cout) return fail(SA_ERR_INVALID, "sa_conv_direct: cout_pad must be a multiple of 8");
+  const int ho = (h + 2 * pad - ksz) / stride + 1, wo = (w + 2 * pad - ksz) / stride + 1;
+  const long long total = static_cast<long long>(n) * ho * wo * (cout_pad / 8);
+  conv_direct_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(x), n, h, w, cin, static_cast<const __nv_bfloat16*>(wt), bias, cout,
+      cout_pad, ksz, stride, pad, ho, wo, silu_out, scale, static_cast<const __nv_bfloat16*>(add), add_from,
+      static_cast<__nv_bfloat16*>(out));
+  SA_CUDA_CHECK(cudaGetLastError());
+  return SA_OK;
+}
+
+extern "C" int sa_upsample2x(const void* in, int32_t n, int32_t h, int32_t w, int32_t c, void* out,
+                             void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!in || !out || c % 8) return fail(SA_ERR_INVALID, "sa_upsample2x: bad arguments");
+  const long long total = static_cast<long long>(n) * 4 * h * w * (c / 8);
+  upsample2x_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const uint4*>(in), n, h, w, c / 8,
+                                                             static_cast<uint4*>(out));
+  SA_CUDA_CHECK(cudaGetLastError());
+  return SA_OK;
+}
+
+extern "C" int sa_im2col_s2(const void* in, int32_t n, int32_t h, int32_t w, int32_t c, void* out,
+                            void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!in || !out || c % 8 || h % 2 || w % 2) return fail(SA_ERR_INVALID, "sa_im2col_s2: bad arguments");
+  const long long total = static_cast<long long>(n) * (h / 2) * (w / 2) * 9 * (c / 8);
+  im2col_s2_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const uint4*>(in), n, h, w, c / 8,
+                                                            static_cast<uint4*>(out));
+  SA_CUDA_CHECK(cudaGetLastError());
+  return SA_OK;
+}
+
+extern "C" int sa_nchw_to_nhwc(const void* src, int32_t src_is_bf16, int32_t n, int32_t c, int32_t hw,
+                               void* dst, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!src || !dst) return fail(SA_ERR_INVALID, "sa_nchw_to_nhwc: null pointer");
+  dim3 grid((hw + 31) / 32, (c + 31) / 32, n), block(32, 8);
+  if (src_is_bf16)
+    nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(src), c, hw,
+                                                                   static_cast<__nv_bfloat16*>(dst));
+  else
+    nchw_to_nhwc_kernel<float><<<grid, block, 0, stream>>>(static_cast<const float*>(src), c, hw,
+                                                           static_cast<__nv_bfloat16*>(dst));
+  SA_CUDA_CHECK(cudaGetLastError());
+  return SA_OK;
+}
+
+extern "C" int sa_nhwc_to_nchw_f32(const float* src, int32_t lds, int32_t n, int32_t c, int32_t hw,
+                                   float* dst, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!src || !dst) return fail(SA_ERR_INVALID, "sa_nhwc_to_nchw_f32: null pointer");
+  dim3 grid((static_cast<long long>(c) * hw + 255) / 256, n);
+  nhwc_to_nchw_kernel<<<grid, 256, 0, stream>>>(src, lds, c, hw, dst);
+  SA_CUDA_CHECK(cudaGetLastError());
+  return SA_OK;
+}
+
+extern "C" int sa_sampler_prepare(const float* latents, const float* image_latents, const int32_t* idx,
+                                  int32_t nb, int32_t b0, int32_t t, int32_t f, int32_t hw, float sigma,
+                                  void* out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!latents || !image_latents || !idx || !out) return fail(SA_ERR_INVALID, "sa_sampler_prepare: null pointer");
+  const long long total = static_cast<long long>(nb) * t * hw;
+  const float inv = 1.0f / sqrtf(sigma * sigma + 1.0f);
+  sampler_prepare_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      latents, image_latents, idx, nb, b0, t, f, hw, inv, static_cast<__nv_bfloat16*>(out));
+  SA_CUDA_CHECK(cudaGetLastError());
+  return SA_OK;
+}
+
+extern "C" int sa_sampler_accumulate(const float* unet_out, int32_t ldo, const int32_t* idx,
+                                     const float* weight, int32_t nb, int32_t b0, int32_t t, int32_t f,
+                                     int32_t hw, float* noise, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!unet_out || !idx || !weight || !noise || ldo % 4) return fail(SA_ERR_INVALID, "sa_sampler_accumulate: bad arguments");
+  const long long total = static_cast<long long>(nb) * t * hw;
+  sampler_accumulate_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      unet_out, ldo, idx, weight, nb, b0, t, f, hw, noise);
+  SA_CUDA_CHECK(cudaGetLastError());
+  return SA_OK;
+}
+
+extern "C" int sa_sampler_step(const float* noise, const float* cnt, const float* guidance, int32_t f,
+                               int32_t chw, float sigma, float sigma_next, float* latents, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!noise || !cnt || !guidance || !latents) return fail(SA_ERR_INVALID, "sa_sampler_step: null pointer");
+  const long long total = static_cast<long long>(f) * chw;
+  sampler_step_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(noise, cnt, guidance, f, chw,
+                                                                                    sigma, sigma_next, latents);
+  SA_CUDA_CHECK(cudaGetLastError());
+  return SA_OK;
+}

@@ -99,7 +99,6 @@ def gemm_tap(
         out = torch.empty((rows, n_out), device=a0.device,
                           dtype=torch.float32 if out_f32 else torch.bfloat16)
     _chk_f32(bias, "bias")
-    _chk_f32(row_bias, "row_bias")
     _chk_f32(row_scale, "row_scale")
     args = GemmArgs()
     args.a0, args.a1 = a0.data_ptr(), _ptr(a1)
@@ -109,7 +108,11 @@ def gemm_tap(
     for i, t in enumerate(taps):
         args.tap_off[3 * i], args.tap_off[3 * i + 1], args.tap_off[3 * i + 2] = t
     args.w, args.n = w.data_ptr(), n_mma
-    args.bias, args.row_bias, args.row_scale = _ptr(bias), _ptr(row_bias), _ptr(row_scale)
+    args.bias, args.row_scale = _ptr(bias), _ptr(row_scale)
+    if row_bias is not None:
+        if row_bias.dtype != torch.float32 or row_bias.stride(-1) != 1:
+            raise ValueError("row_bias must be fp32 with unit inner stride")
+        args.row_bias, args.ldrb = row_bias.data_ptr(), row_bias.stride(0)
     args.rows_per_group = rows_per_group
     if residual is not None:
         _chk_bf16(residual, "residual")
@@ -134,3 +137,201 @@ def interleave_geglu(w: torch.Tensor, b: Optional[torch.Tensor]):
     assert h % 64 == 0
     idx = torch.arange(n2, device=w.device).reshape(2, h // 64, 64).permute(1, 0, 2).reshape(-1)
     return w[idx].contiguous(), (None if b is None else b[idx].contiguous())
+
+
+# ----------------------------------------------------------------------------- attention
+def attn_spatial(qkv: torch.Tensor, frames: int, s: int, heads: int,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """softmax(q k^T / 8) v per (frame, head); qkv bf16 [frames*s, 3C] -> bf16 [frames*s, C]."""
+    _chk_bf16(qkv, "qkv")
+    c = heads * 64
+    if out is None:
+        out = torch.empty((frames * s, c), device=qkv.device, dtype=torch.bfloat16)
+    check(lib().sa_attn_spatial(qkv.data_ptr(), qkv.stride(-2), frames, s, c, heads, out.data_ptr(),
+                                out.stride(-2), _stream()), "sa_attn_spatial")
+    return out
+
+
+def attn_temporal(qkv: torch.Tensor, b: int, f: int, s: int, heads: int,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _chk_bf16(qkv, "qkv")
+    c = heads * 64
+    if out is None:
+        out = torch.empty((b * f * s, c), device=qkv.device, dtype=torch.bfloat16)
+    check(lib().sa_attn_temporal(qkv.data_ptr(), qkv.stride(-2), b, f, s, c, heads, out.data_ptr(),
+                                 out.stride(-2), _stream()), "sa_attn_temporal")
+    return out
+
+
+def attn_id(q: torch.Tensor, ik: torch.Tensor, iv: torch.Tensor, b: int, f: int, s: int, heads: int,
+            stats: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """ip = softmax(q ik^T / 8) iv over the 4 face tokens; stats (fp64 [b*f, 2]) gets Sum, Sum^2.
+    ik / iv: fp32 views [b, 4, C] (any batch/token strides, unit channel stride)."""
+    _chk_bf16(q, "q")
+    c = heads * 64
+    for t in (ik, iv):
+        if t.dtype != torch.float32 or t.shape != (b, 4, c) or t.stride(2) != 1:
+            raise ValueError("ik/iv must be fp32 [b, 4, C] with unit channel stride")
+    if ik.stride() != iv.stride():
+        raise ValueError("ik and iv must share strides")
+    if out is None:
+        out = torch.empty((b * f * s, c), device=q.device, dtype=torch.bfloat16)
+    check(lib().sa_attn_id(q.data_ptr(), q.stride(-2), ik.data_ptr(), iv.data_ptr(), ik.stride(1), ik.stride(0),
+                           b, f, s, c, heads, 4, out.data_ptr(), out.stride(-2), stats.data_ptr(), _stream()),
+          "sa_attn_id")
+    return out
+
+
+def attn_id_finalize(stats, vclip, wv, w_rowsum, bias, b, f, s, c, row_scale, row_bias) -> None:
+    """vclip: fp32 view [b, C] (any batch stride); the rest contiguous fp32."""
+    for t, nm in ((wv, "wv"), (w_rowsum, "w_rowsum"), (bias, "bias"),
+                  (row_scale, "row_scale"), (row_bias, "row_bias")):
+        _chk_f32(t, nm)
+    if vclip.dtype != torch.float32 or vclip.stride(1) != 1:
+        raise ValueError("vclip must be fp32 with unit channel stride")
+    check(lib().sa_attn_id_finalize(stats.data_ptr(), vclip.data_ptr(), vclip.stride(0), wv.data_ptr(),
+                                    w_rowsum.data_ptr(), bias.data_ptr(), b, f, s, c, row_scale.data_ptr(),
+                                    row_bias.data_ptr(), _stream()), "sa_attn_id_finalize")
+
+
+# ----------------------------------------------------------------------------- normalisation
+def groupnorm(x0: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, rows_per_stat: int,
+              *, x1: Optional[torch.Tensor] = None, silu: bool = True, stats_ws: Optional[torch.Tensor] = None,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _chk_bf16(x0, "x0")
+    c0 = x0.shape[-1]
+    rows = x0.numel() // c0
+    c1, ld1 = 0, 0
+    if x1 is not None:
+        _chk_bf16(x1, "x1")
+        c1, ld1 = x1.shape[-1], x1.stride(-2)
+    ns = rows // rows_per_stat
+    if ns * rows_per_stat != rows:
+        raise ValueError("rows must be a multiple of rows_per_stat")
+    if stats_ws is None:
+        stats_ws = torch.empty((ns, 32, 2), device=x0.device, dtype=torch.float64)
+    if out is None:
+        out = torch.empty((rows, c0 + c1), device=x0.device, dtype=torch.bfloat16)
+    _chk_f32(gamma, "gamma")
+    _chk_f32(beta, "beta")
+    check(lib().sa_groupnorm(x0.data_ptr(), _ptr(x1), c0, c1, x0.stride(-2), ld1, rows_per_stat, ns,
+                             gamma.data_ptr(), beta.data_ptr(), float(eps), int(silu), stats_ws.data_ptr(),
+                             out.data_ptr(), out.stride(-2), _stream()), "sa_groupnorm")
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, addv: Optional[torch.Tensor] = None,
+              rows_per_group: int = 1, x_out: Optional[torch.Tensor] = None,
+              out: Optional[torch.Tensor] = None, eps: float = 1e-5) -> torch.Tensor:
+    _chk_bf16(x, "x")
+    c = x.shape[-1]
+    rows = x.numel() // c
+    if out is None:
+        out = torch.empty((rows, c), device=x.device, dtype=torch.bfloat16)
+    _chk_f32(addv, "addv")
+    check(lib().sa_layernorm(x.data_ptr(), x.stride(-2), rows, c, _ptr(addv), rows_per_group, _ptr(x_out),
+                             0 if x_out is None else x_out.stride(-2), gamma.data_ptr(), beta.data_ptr(),
+                             float(eps), out.data_ptr(), out.stride(-2), _stream()), "sa_layernorm")
+    return out
+
+
+# ----------------------------------------------------------------------------- small / memory-bound ops
+def small_linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
+                 silu_in: bool = False, silu_out: bool = False, accumulate: bool = False,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 x [m, k] (row stride arbitrary), bf16 w [n, k] -> fp32 [m, n] (``accumulate``: out += ...)."""
+    if x.dtype != torch.float32 or x.stride(-1) != 1:
+        raise ValueError("x must be fp32 with unit inner stride")
+    _chk_bf16(w, "w")
+    m, k = x.shape
+    n = w.shape[0]
+    if out is None:
+        out = torch.empty((m, n), device=x.device, dtype=torch.float32)
+    check(lib().sa_small_linear(x.data_ptr(), x.stride(0), m, w.data_ptr(), k, n, _ptr(bias), int(silu_in),
+                                int(silu_out), int(accumulate), out.data_ptr(), out.stride(0), _stream()),
+          "sa_small_linear")
+    return out
+
+
+def sinusoid(t: torch.Tensor, dim: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _chk_f32(t, "t")
+    n = t.numel()
+    if out is None:
+        out = torch.empty((n, dim), device=t.device, dtype=torch.float32)
+    check(lib().sa_sinusoid(t.data_ptr(), n, dim, out.data_ptr(), _stream()), "sa_sinusoid")
+    return out
+
+
+def conv_direct(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor], cout: int, ksz: int,
+                stride: int, pad: int, *, silu: bool = False, scale: float = 1.0,
+                add: Optional[torch.Tensor] = None, add_from: int = 0,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x bf16 [n, h, w, cin] (NHWC); wt bf16 [k*k*cin, cout_pad] -> bf16 [n, ho, wo, cout]."""
+    _chk_bf16(x, "x")
+    _chk_bf16(wt, "wt")
+    n, h, w, cin = x.shape
+    ho, wo = (h + 2 * pad - ksz) // stride + 1, (w + 2 * pad - ksz) // stride + 1
+    if out is None:
+        out = torch.empty((n, ho, wo, cout), device=x.device, dtype=torch.bfloat16)
+    check(lib().sa_conv_direct(x.data_ptr(), n, h, w, cin, wt.data_ptr(), _ptr(bias), cout, wt.shape[1], ksz,
+                               stride, pad, int(silu), float(scale), _ptr(add), add_from, out.data_ptr(),
+                               _stream()), "sa_conv_direct")
+    return out
+
+
+def upsample2x(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _chk_bf16(x, "x")
+    n, h, w, c = x.shape
+    if out is None:
+        out = torch.empty((n, 2 * h, 2 * w, c), device=x.device, dtype=torch.bfloat16)
+    check(lib().sa_upsample2x(x.data_ptr(), n, h, w, c, out.data_ptr(), _stream()), "sa_upsample2x")
+    return out
+
+
+def im2col_s2(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _chk_bf16(x, "x")
+    n, h, w, c = x.shape
+    if out is None:
+        out = torch.empty((n * (h // 2) * (w // 2), 9 * c), device=x.device, dtype=torch.bfloat16)
+    check(lib().sa_im2col_s2(x.data_ptr(), n, h, w, c, out.data_ptr(), _stream()), "sa_im2col_s2")
+    return out
+
+
+def nchw_to_nhwc(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[n, c, h, w] fp32/bf16 contiguous -> bf16 [n, h, w, c]."""
+    if not x.is_contiguous() or x.dtype not in (torch.float32, torch.bfloat16):
+        raise ValueError("x must be contiguous fp32/bf16 NCHW")
+    n, c, h, w = x.shape
+    if out is None:
+        out = torch.empty((n, h, w, c), device=x.device, dtype=torch.bfloat16)
+    check(lib().sa_nchw_to_nhwc(x.data_ptr(), int(x.dtype == torch.bfloat16), n, c, h * w, out.data_ptr(),
+                                _stream()), "sa_nchw_to_nhwc")
+    return out
+
+
+def nhwc_to_nchw_f32(x: torch.Tensor, n: int, c: int, hw: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 [n*hw, ld] (first c columns) -> fp32 [n, c, hw]."""
+    if x.dtype != torch.float32:
+        raise ValueError("x must be fp32")
+    if out is None:
+        out = torch.empty((n, c, hw), device=x.device, dtype=torch.float32)
+    check(lib().sa_nhwc_to_nchw_f32(x.data_ptr(), x.stride(-2), n, c, hw, out.data_ptr(), _stream()),
+          "sa_nhwc_to_nchw_f32")
+    return out
+
+
+def sampler_prepare(latents, image_latents, idx, nb, b0, f, hw, sigma, out) -> None:
+    check(lib().sa_sampler_prepare(latents.data_ptr(), image_latents.data_ptr(), idx.data_ptr(), nb, b0,
+                                   idx.numel(), f, hw, float(sigma), out.data_ptr(), _stream()),
+          "sa_sampler_prepare")
+
+
+def sampler_accumulate(unet_out, idx, weight, nb, b0, f, hw, noise) -> None:
+    check(lib().sa_sampler_accumulate(unet_out.data_ptr(), unet_out.stride(-2), idx.data_ptr(),
+                                      weight.data_ptr(), nb, b0, idx.numel(), f, hw, noise.data_ptr(),
+                                      _stream()), "sa_sampler_accumulate")
+
+
+def sampler_step(noise, cnt, guidance, f, chw, sigma, sigma_next, latents) -> None:
+    check(lib().sa_sampler_step(noise.data_ptr(), cnt.data_ptr(), guidance.data_ptr(), f, chw, float(sigma),
+                                float(sigma_next), latents.data_ptr(), _stream()), "sa_sampler_step")
