@@ -98,7 +98,14 @@ def _declare(l: C.CDLL) -> None:
         fn.restype = C.c_int
 
 
+# kernels launched by one successful call of each entry point (for bench.py's gpu_launches claim)
+KERNELS_PER_CALL = {"sa_groupnorm": 2}
+launch_count = 0
+
+
 def check(rc: int, what: str) -> None:
+    global launch_count
+    launch_count += KERNELS_PER_CALL.get(what, 1)
     if rc != 0:
         msg = lib().sa_last_error().decode("utf-8", "replace")
         raise SaKernelError(f"{what} failed with code {rc}: {msg}")
