@@ -56,13 +56,13 @@ struct TmapHash {
 };
 
 const CUtensorMap* get_tmap_bf16(const void* base, int rank, const uint64_t* dims,
-                                 const uint64_t* strides_bytes, const uint32_t* box) {
+                                 const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
   static std::mutex mu;
   static std::unordered_map<TmapKey, CUtensorMap*, TmapHash> cache;
   TmapKey key;
   memset(&key, 0, sizeof(key));
   key.w[0] = reinterpret_cast<uint64_t>(base);
-  key.w[1] = static_cast<uint64_t>(rank);
+  key.w[1] = static_cast<uint64_t>(rank) | (static_cast<uint64_t>(swizzle_bytes) << 8);
   for (int i = 0; i < rank; ++i) {
     key.w[2 + i] = dims[i];
     key.w[7 + i] = (i == 0) ? 0 : strides_bytes[i - 1];
@@ -86,7 +86,8 @@ const CUtensorMap* get_tmap_bf16(const void* base, int rank, const uint64_t* dim
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank),
                   const_cast<void*>(base), dims, strides_bytes, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     fail(SA_ERR_TMA,

@@ -41,6 +41,9 @@ struct GemmKParams {
   void* out;
   int ldc;
   int out_f32;
+  // persistent kernel (v2) only
+  int n_tiles_n, total_tiles;
+  float out_scale;  // v = (acc*rs + bias + row_bias [geglu]) * out_scale + residual ...
 };
 
 template <int BN>
@@ -258,6 +261,316 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                              pack_bf16x2(v[8 * j + 4], v[8 * j + 5]),
                              pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
     }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<TCOLS>(tmem_base);
+}
+
+// =====================================================================================================
+// v2: persistent, warp-specialised variant (bf16 output).  One CTA per SM loops over output tiles:
+//   warp 0      : TMA producer (A boxes + W boxes into a STAGES-deep ring that runs across tiles)
+//   warp 1      : MMA issuer; accumulators double-buffered in TMEM (2 x BN columns) so the epilogue
+//                 of tile i overlaps the main loop of tile i+1
+//   warps 2..5  : epilogue, thread = row.  Per 32-column chunk: tcgen05.ld -> fp32 math -> bf16 into a
+//                 SWIZZLE_64B staging tile [128 rows x 64 B] -> one TMA store (clips ragged tiles).
+//                 residual / blend_x chunks are TMA-loaded two chunks ahead into the same staging
+//                 slots (each thread reads and then overwrites only its own row), so every global
+//                 access of the epilogue is a coalesced bulk copy.
+// =====================================================================================================
+constexpr int EPI_CHUNK = 32;              // output columns per staging chunk
+constexpr int EPI_TILE_BYTES = 128 * 64;   // [128 rows][32 bf16]
+constexpr int EPI_RO_SLOTS = 3, EPI_X_SLOTS = 2;
+
+template <int BN, int STAGES>
+struct Gemm2Smem {
+  static constexpr int STAGE_BYTES = 128 * 128 + BN * 128;
+  static constexpr int RO_OFF = STAGES * STAGE_BYTES;
+  static constexpr int X_OFF = RO_OFF + EPI_RO_SLOTS * EPI_TILE_BYTES;
+  static constexpr int BAR_OFF = X_OFF + EPI_X_SLOTS * EPI_TILE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;  // + barriers + alignment slack
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                        const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
+                        const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmBld,
+                        const GemmKParams p) {
+  using L = Gemm2Smem<BN, STAGES>;
+  constexpr int A_BYTES = 128 * 128;
+  constexpr int STAGE_BYTES = L::STAGE_BYTES;
+  constexpr int TCOLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  constexpr int ACC_STRIDE = TCOLS / 2;  // column offset of the second accumulator
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sRO = smem + L::RO_OFF;
+  uint8_t* sX = smem + L::X_OFF;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* acc_full = empty_bar + STAGES;   // [2]
+  uint64_t* acc_empty = acc_full + 2;        // [2]
+  uint64_t* ro_ready = acc_empty + 2;        // [3]
+  uint64_t* x_ready = ro_ready + EPI_RO_SLOTS;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_ready + EPI_X_SLOTS);
+
+  const int warp = threadIdx.x >> 5;
+  const int KB = p.ntaps * p.kcpt;
+  const int out_cols_tile = p.geglu ? BN / 2 : BN;
+  const int CPT = out_cols_tile / EPI_CHUNK;  // chunks per tile
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmA1);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmOut);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 128);
+    }
+    for (int i = 0; i < EPI_RO_SLOTS; ++i) mbar_init(&ro_ready[i], 1);
+    for (int i = 0; i < EPI_X_SLOTS; ++i) mbar_init(&x_ready[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<TCOLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto tile_origin = [&](int tile, int& n0, int& q1, int& q2, int& q3) {
+    const int nt = tile % p.n_tiles_n, mt = tile / p.n_tiles_n;
+    n0 = nt * BN;
+    q1 = (mt % p.t1) * p.b1;
+    q2 = ((mt / p.t1) % p.t2) * p.b2;
+    q3 = (mt / (p.t1 * p.t2)) * p.b3;
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int n0, q1, q2, q3;
+        tile_origin(tile, n0, q1, q2, q3);
+        int tap = 0, ch = 0;
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+          mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+          uint8_t* sa_ = smem + s * STAGE_BYTES;
+          const int o1 = p.tap_off[tap * 3 + 0], o2 = p.tap_off[tap * 3 + 1], o3 = p.tap_off[tap * 3 + 2];
+          if (ch < p.kc0)
+            tma_load_4d(sa_, &tmA0, &full_bar[s], ch * 64, q1 + o1, q2 + o2, q3 + o3);
+          else
+            tma_load_4d(sa_, &tmA1, &full_bar[s], (ch - p.kc0) * 64, q1 + o1, q2 + o2, q3 + o3);
+          tma_load_2d(sa_ + A_BYTES, &tmB, &full_bar[s], kb * 64, n0);
+          if (++ch == p.kcpt) {
+            ch = 0;
+            ++tap;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+      int it = 0, ti = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
+        const int ab = ti & 1;
+        mbar_wait(&acc_empty[ab], ((ti >> 1) & 1) ^ 1);  // epilogue drained this accumulator
+        tc_fence_after();
+        const uint32_t acc = tmem_base + ab * ACC_STRIDE;
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&full_bar[s], (it / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+          const uint64_t da = umma_desc_sw128(a_addr);
+          const uint64_t db = umma_desc_sw128(a_addr + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16(acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&acc_full[ab]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue (128 threads)
+    const int quad = warp & 3;
+    const int r = quad * 32 + (threadIdx.x & 31);  // tile row == TMEM lane
+    const bool leader = (threadIdx.x == 64);
+    const int i1 = r % p.b1, i2 = (r / p.b1) % p.b2, i3 = r / (p.b1 * p.b2);
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const float alpha = p.alpha, beta = 1.0f - p.alpha, gs = p.out_scale;
+    const int my_tiles = (p.total_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                         static_cast<int>(gridDim.x);
+    const int total_chunks = my_tiles * CPT;
+    uint8_t* my_ro = sRO + r * 64;
+    uint8_t* my_x = sX + r * 64;
+    const int sw = (r >> 1) & 3;  // SWIZZLE_64B: 16-byte chunk index ^= (row >> 1) & 3
+
+    // make staging slot `slot` ready for global chunk g: TMA-load the residual chunk, or just mark free
+    auto issue_ready = [&](int g) {
+      if (g >= total_chunks) return;
+      const int slot = g % EPI_RO_SLOTS;
+      if (p.residual) {
+        int n0, q1, q2, q3;
+        tile_origin(static_cast<int>(blockIdx.x) + (g / CPT) * static_cast<int>(gridDim.x), n0, q1, q2, q3);
+        const int col = (p.geglu ? n0 / 2 : n0) + (g % CPT) * EPI_CHUNK;
+        mbar_expect_tx(&ro_ready[slot], EPI_TILE_BYTES);
+        tma_load_4d(sRO + slot * EPI_TILE_BYTES, &tmRes, &ro_ready[slot], col, q1, q2, q3);
+      } else {
+        mbar_arrive(&ro_ready[slot]);
+      }
+    };
+    auto issue_x = [&](int g) {
+      if (!p.blend_x || g >= total_chunks) return;
+      const int slot = g % EPI_X_SLOTS;
+      int n0, q1, q2, q3;
+      tile_origin(static_cast<int>(blockIdx.x) + (g / CPT) * static_cast<int>(gridDim.x), n0, q1, q2, q3);
+      const int col = (p.geglu ? n0 / 2 : n0) + (g % CPT) * EPI_CHUNK;
+      mbar_expect_tx(&x_ready[slot], EPI_TILE_BYTES);
+      tma_load_4d(sX + slot * EPI_TILE_BYTES, &tmBld, &x_ready[slot], col, q1, q2, q3);
+    };
+    if (leader) {
+      issue_ready(0);
+      issue_ready(1);
+      issue_x(0);
+      issue_x(1);
+    }
+
+    int gc = 0, ti = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
+      int n0, q1, q2, q3;
+      tile_origin(tile, n0, q1, q2, q3);
+      const int p1 = q1 + i1, p2 = q2 + i2, p3 = q3 + i3;
+      const bool valid = (p1 < p.d1) && (p2 < p.d2) && (p3 < p.d3);
+      const long long row = (static_cast<long long>(p3) * p.d2 + p2) * p.d1 + p1;
+      const int grp = valid ? static_cast<int>(row / p.rows_per_group) : 0;
+      const float rs = p.row_scale ? p.row_scale[grp] : 1.0f;
+      const int nout0 = p.geglu ? n0 / 2 : n0;
+      const int ab = ti & 1;
+      mbar_wait(&acc_full[ab], (ti >> 1) & 1);
+      tc_fence_after();
+      const uint32_t acc = lane_addr + ab * ACC_STRIDE;
+
+      for (int c = 0; c < CPT; ++c, ++gc) {
+        const int mc = p.geglu ? ((c >> 1) * 128 + (c & 1) * 32) : c * EPI_CHUNK;  // MMA column of the chunk
+        float v[32];
+        {
+          uint32_t u[32];
+          tmem_ld_32x32(acc + mc, u);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(u[j]) * rs;
+        }
+        if (p.bias) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + mc);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = __ldg(b4 + j);
+            v[4 * j + 0] += b.x;
+            v[4 * j + 1] += b.y;
+            v[4 * j + 2] += b.z;
+            v[4 * j + 3] += b.w;
+          }
+        }
+        if (p.geglu) {
+          uint32_t g[32];
+          tmem_ld_32x32(acc + mc + 64, g);
+          tmem_ld_wait();
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + mc + 64);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias) b = __ldg(b4 + j);
+            v[4 * j + 0] *= gelu_fast(__uint_as_float(g[4 * j + 0]) * rs + b.x);
+            v[4 * j + 1] *= gelu_fast(__uint_as_float(g[4 * j + 1]) * rs + b.y);
+            v[4 * j + 2] *= gelu_fast(__uint_as_float(g[4 * j + 2]) * rs + b.z);
+            v[4 * j + 3] *= gelu_fast(__uint_as_float(g[4 * j + 3]) * rs + b.w);
+          }
+        }
+        if (c == CPT - 1) {  // accumulator fully read: hand it back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(&acc_empty[ab]);
+        }
+        const int ncol = nout0 + c * EPI_CHUNK;
+        if (p.row_bias) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.row_bias + static_cast<long long>(grp) * p.ldrb + ncol);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = __ldg(b4 + j);
+            v[4 * j + 0] += b.x;
+            v[4 * j + 1] += b.y;
+            v[4 * j + 2] += b.z;
+            v[4 * j + 3] += b.w;
+          }
+        }
+        if (gs != 1.0f) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= gs;
+        }
+        // staging slot of this chunk: holds the residual chunk (if any) and is free for our output
+        const int slot = gc % EPI_RO_SLOTS;
+        mbar_wait(&ro_ready[slot], (gc / EPI_RO_SLOTS) & 1);
+        uint8_t* ro = my_ro + slot * EPI_TILE_BYTES;
+        if (p.residual) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 q = *reinterpret_cast<const uint4*>(ro + ((j ^ sw) << 4));
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 f = unpack_bf16x2(w[t]);
+              v[8 * j + 2 * t] += f.x;
+              v[8 * j + 2 * t + 1] += f.y;
+            }
+          }
+        }
+        if (p.blend_x) {
+          const int xs = gc % EPI_X_SLOTS;
+          mbar_wait(&x_ready[xs], (gc / EPI_X_SLOTS) & 1);
+          const uint8_t* xr = my_x + xs * EPI_TILE_BYTES;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 q = *reinterpret_cast<const uint4*>(xr + ((j ^ sw) << 4));
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 f = unpack_bf16x2(w[t]);
+              v[8 * j + 2 * t] = alpha * f.x + beta * v[8 * j + 2 * t];
+              v[8 * j + 2 * t + 1] = alpha * f.y + beta * v[8 * j + 2 * t + 1];
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<uint4*>(ro + ((j ^ sw) << 4)) =
+              make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                         pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+        fence_proxy_async();       // staging tile visible to the TMA store
+        named_bar_sync(1, 128);    // all 128 rows written (and all reads of the X slot done)
+        if (leader) {
+          tma_store_4d(&tmOut, sRO + slot * EPI_TILE_BYTES, ncol, q1, q2, q3);
+          tma_store_commit();
+          // the slot of chunk gc-1 (== slot of chunk gc+2) is reusable once its store has read smem
+          tma_store_wait_read<1>();
+          issue_ready(gc + 2);
+          issue_x(gc + 2);
+        }
+      }
+    }
+    if (leader) tma_store_wait_all();
   }
 
   tc_fence_before();
