@@ -45,9 +45,9 @@ const char* sa_last_error(void);
  *   - temporal conv  (nn.Conv3d k=(3,1,1), unet.py:1711,1725): ntaps = 3, grid = (S, F, B)
  * Epilogue, in this order (every piece optional):
  *   v = acc * row_scale[g] + bias[n] + row_bias[g, n]          g = m / rows_per_group
- *   if geglu: v = v_value * gelu_erf(v_gate)   (GEGLU, unet.py:868-870; W rows interleaved by
- *                                               tile_n/2 blocks: [value block | gate block])
- *   v += residual[m, n]
+ *   if geglu: v = v_value * gelu_erf(v_gate)   (GEGLU, unet.py:868-870; W rows interleaved in
+ *                                               64-row blocks: [value block | gate block])
+ *   v = v * out_scale + residual[m, n]
  *   if blend_x: v = alpha * blend_x[m, n] + (1 - alpha) * v    (AlphaBlender, unet.py:473)
  * ------------------------------------------------------------------------------------------ */
 typedef struct sa_gemm_args {
@@ -75,6 +75,7 @@ typedef struct sa_gemm_args {
   int32_t ldc;
   int32_t out_f32;
   int32_t tile_n;        /* 0 = auto; else one of 32, 64, 128, 160, 256 */
+  float out_scale;       /* 0 = 1.0; scales (acc*row_scale + bias + row_bias [geglu]) before residual */
 } sa_gemm_args;
 
 int sa_gemm_tap(const sa_gemm_args* args, void* stream);

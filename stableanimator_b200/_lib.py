@@ -41,6 +41,7 @@ class GemmArgs(C.Structure):
         ("out", C.c_void_p), ("ldc", C.c_int32),
         ("out_f32", C.c_int32),
         ("tile_n", C.c_int32),
+        ("out_scale", C.c_float),
     ]
 
 

@@ -14,6 +14,8 @@
 //
 // Replaces: nn.Linear / nn.Conv2d 3x3 & 1x1 / nn.Conv3d (3,1,1) call sites of
 // animation/modules/unet.py (see include/sa_b200.h for the per-site citations).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -198,6 +200,10 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       }
     }
     if (!valid) continue;
+    if (p.out_scale != 1.0f) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] *= p.out_scale;
+    }
     const int ncol = nout0 + c;  // first output column of this chunk
     if (p.row_bias) {
       const float4* b4 =
@@ -273,27 +279,32 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
 //   warp 0      : TMA producer (A boxes + W boxes into a STAGES-deep ring that runs across tiles)
 //   warp 1      : MMA issuer; accumulators double-buffered in TMEM (2 x BN columns) so the epilogue
 //                 of tile i overlaps the main loop of tile i+1
-//   warps 2..5  : epilogue, thread = row.  Per 32-column chunk: tcgen05.ld -> fp32 math -> bf16 into a
-//                 SWIZZLE_64B staging tile [128 rows x 64 B] -> one TMA store (clips ragged tiles).
-//                 residual / blend_x chunks are TMA-loaded two chunks ahead into the same staging
-//                 slots (each thread reads and then overwrites only its own row), so every global
-//                 access of the epilogue is a coalesced bulk copy.
+//   warps 2..9  : epilogue.  Warp w owns the 32 tile rows of TMEM quadrant (w % 4) and every second
+//                 32-column chunk ((w - 2) / 4 selects even / odd chunks); the eight warps run fully
+//                 decoupled pipelines (no CTA-level barrier).  Per chunk: tcgen05.ld (prefetched one
+//                 chunk ahead) -> fp32 math -> bf16 into the warp's SWIZZLE_64B staging tile
+//                 [32 rows x 64 B] -> one TMA store of the (32 cols, s1, s2, s3) sub-box, which also
+//                 clips ragged tiles.  residual / blend_x sub-boxes are TMA-loaded two chunks ahead
+//                 into the same staging slots (a thread reads, then overwrites, only its own row), so
+//                 every global access of the epilogue is a bulk copy.
 // =====================================================================================================
-constexpr int EPI_CHUNK = 32;              // output columns per staging chunk
-constexpr int EPI_TILE_BYTES = 128 * 64;   // [128 rows][32 bf16]
+constexpr int EPI_CHUNK = 32;             // output columns per chunk
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_TILE_BYTES = 32 * 64;   // per-warp staging tile: [32 rows][32 bf16]
 constexpr int EPI_RO_SLOTS = 3, EPI_X_SLOTS = 2;
+constexpr int EPI_WARP_BYTES = (EPI_RO_SLOTS + EPI_X_SLOTS) * EPI_TILE_BYTES;
 
 template <int BN, int STAGES>
 struct Gemm2Smem {
   static constexpr int STAGE_BYTES = 128 * 128 + BN * 128;
-  static constexpr int RO_OFF = STAGES * STAGE_BYTES;
-  static constexpr int X_OFF = RO_OFF + EPI_RO_SLOTS * EPI_TILE_BYTES;
-  static constexpr int BAR_OFF = X_OFF + EPI_X_SLOTS * EPI_TILE_BYTES;
-  static constexpr int TOTAL = BAR_OFF + 256 + 1024;  // + barriers + alignment slack
+  static constexpr int EPI_OFF = STAGES * STAGE_BYTES;
+  static constexpr int BAR_OFF = EPI_OFF + EPI_WARPS * EPI_WARP_BYTES;
+  static constexpr int NBARS = 2 * STAGES + 4 + EPI_WARPS * (EPI_RO_SLOTS + EPI_X_SLOTS);
+  static constexpr int TOTAL = BAR_OFF + NBARS * 8 + 16 + 1024;  // + tmem slot + alignment slack
 };
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(192, 1)
+template <int BN, int STAGES, bool GEGLU>
+__global__ void __launch_bounds__(320, 1)
 gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                         const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
                         const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmBld,
@@ -306,19 +317,16 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sRO = smem + L::RO_OFF;
-  uint8_t* sX = smem + L::X_OFF;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* acc_full = empty_bar + STAGES;   // [2]
   uint64_t* acc_empty = acc_full + 2;        // [2]
-  uint64_t* ro_ready = acc_empty + 2;        // [3]
-  uint64_t* x_ready = ro_ready + EPI_RO_SLOTS;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_ready + EPI_X_SLOTS);
+  uint64_t* epi_bar = acc_empty + 2;         // [EPI_WARPS][RO_SLOTS + X_SLOTS]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_bar + EPI_WARPS * (EPI_RO_SLOTS + EPI_X_SLOTS));
 
   const int warp = threadIdx.x >> 5;
   const int KB = p.ntaps * p.kcpt;
-  const int out_cols_tile = p.geglu ? BN / 2 : BN;
+  const int out_cols_tile = GEGLU ? BN / 2 : BN;
   const int CPT = out_cols_tile / EPI_CHUNK;  // chunks per tile
 
   if (warp == 0 && elect_one()) {
@@ -332,10 +340,9 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 128);
+      mbar_init(&acc_empty[i], EPI_WARPS * 32);
     }
-    for (int i = 0; i < EPI_RO_SLOTS; ++i) mbar_init(&ro_ready[i], 1);
-    for (int i = 0; i < EPI_X_SLOTS; ++i) mbar_init(&x_ready[i], 1);
+    for (int i = 0; i < EPI_WARPS * (EPI_RO_SLOTS + EPI_X_SLOTS); ++i) mbar_init(&epi_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<TCOLS>(tmem_slot);
@@ -405,30 +412,49 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------------ epilogue (128 threads)
-    const int quad = warp & 3;
-    const int r = quad * 32 + (threadIdx.x & 31);  // tile row == TMEM lane
-    const bool leader = (threadIdx.x == 64);
+    // ------------------------------------------------------------------ epilogue (8 decoupled warps)
+    const int ew = warp - 2;              // 0..7
+    const int quad = warp & 3;            // TMEM lane quadrant this warp may access
+    const int half = ew >> 2;             // 0: even chunks, 1: odd chunks
+    const int lane = threadIdx.x & 31;
+    const int r = quad * 32 + lane;       // tile row == TMEM lane
     const int i1 = r % p.b1, i2 = (r / p.b1) % p.b2, i3 = r / (p.b1 * p.b2);
+    // origin of this warp's 32-row sub-box inside the tile box (rows quad*32 .. quad*32+31)
+    const int r0 = quad * 32;
+    const int w1 = r0 % p.b1, w2 = (r0 / p.b1) % p.b2, w3 = r0 / (p.b1 * p.b2);
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     const float alpha = p.alpha, beta = 1.0f - p.alpha, gs = p.out_scale;
     const int my_tiles = (p.total_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
                          static_cast<int>(gridDim.x);
-    const int total_chunks = my_tiles * CPT;
-    uint8_t* my_ro = sRO + r * 64;
-    uint8_t* my_x = sX + r * 64;
-    const int sw = (r >> 1) & 3;  // SWIZZLE_64B: 16-byte chunk index ^= (row >> 1) & 3
+    const int cpw = (CPT - half + 1) / 2;           // chunks of a tile handled by this warp
+    const int total_chunks = my_tiles * cpw;
+    uint8_t* wbase = smem + L::EPI_OFF + ew * EPI_WARP_BYTES;
+    uint8_t* sRO = wbase;
+    uint8_t* sX = wbase + EPI_RO_SLOTS * EPI_TILE_BYTES;
+    uint64_t* ro_ready = epi_bar + ew * (EPI_RO_SLOTS + EPI_X_SLOTS);
+    uint64_t* x_ready = ro_ready + EPI_RO_SLOTS;
+    const int sw = (lane >> 1) & 3;  // SWIZZLE_64B: 16-byte chunk index ^= (row >> 1) & 3
+    uint8_t* my_ro = sRO + lane * 64;
+    const uint8_t* my_x = sX + lane * 64;
 
-    // make staging slot `slot` ready for global chunk g: TMA-load the residual chunk, or just mark free
+    // coordinates of this warp's g-th chunk (its own sequence across tiles)
+    auto chunk_coords = [&](int g, int& col, int& c1, int& c2, int& c3) {
+      int n0, q1, q2, q3;
+      tile_origin(static_cast<int>(blockIdx.x) + (g / cpw) * static_cast<int>(gridDim.x), n0, q1, q2, q3);
+      col = (GEGLU ? n0 / 2 : n0) + (half + 2 * (g % cpw)) * EPI_CHUNK;
+      c1 = q1 + w1;
+      c2 = q2 + w2;
+      c3 = q3 + w3;
+    };
+    // make the staging slot of chunk g ready: TMA-load the residual sub-box, or just mark it free
     auto issue_ready = [&](int g) {
       if (g >= total_chunks) return;
       const int slot = g % EPI_RO_SLOTS;
       if (p.residual) {
-        int n0, q1, q2, q3;
-        tile_origin(static_cast<int>(blockIdx.x) + (g / CPT) * static_cast<int>(gridDim.x), n0, q1, q2, q3);
-        const int col = (p.geglu ? n0 / 2 : n0) + (g % CPT) * EPI_CHUNK;
+        int col, c1, c2, c3;
+        chunk_coords(g, col, c1, c2, c3);
         mbar_expect_tx(&ro_ready[slot], EPI_TILE_BYTES);
-        tma_load_4d(sRO + slot * EPI_TILE_BYTES, &tmRes, &ro_ready[slot], col, q1, q2, q3);
+        tma_load_4d(sRO + slot * EPI_TILE_BYTES, &tmRes, &ro_ready[slot], col, c1, c2, c3);
       } else {
         mbar_arrive(&ro_ready[slot]);
       }
@@ -436,13 +462,12 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
     auto issue_x = [&](int g) {
       if (!p.blend_x || g >= total_chunks) return;
       const int slot = g % EPI_X_SLOTS;
-      int n0, q1, q2, q3;
-      tile_origin(static_cast<int>(blockIdx.x) + (g / CPT) * static_cast<int>(gridDim.x), n0, q1, q2, q3);
-      const int col = (p.geglu ? n0 / 2 : n0) + (g % CPT) * EPI_CHUNK;
+      int col, c1, c2, c3;
+      chunk_coords(g, col, c1, c2, c3);
       mbar_expect_tx(&x_ready[slot], EPI_TILE_BYTES);
-      tma_load_4d(sX + slot * EPI_TILE_BYTES, &tmBld, &x_ready[slot], col, q1, q2, q3);
+      tma_load_4d(sX + slot * EPI_TILE_BYTES, &tmBld, &x_ready[slot], col, c1, c2, c3);
     };
-    if (leader) {
+    if (lane == 0) {
       issue_ready(0);
       issue_ready(1);
       issue_x(0);
@@ -458,21 +483,34 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
       const long long row = (static_cast<long long>(p3) * p.d2 + p2) * p.d1 + p1;
       const int grp = valid ? static_cast<int>(row / p.rows_per_group) : 0;
       const float rs = p.row_scale ? p.row_scale[grp] : 1.0f;
-      const int nout0 = p.geglu ? n0 / 2 : n0;
+      const int nout0 = GEGLU ? n0 / 2 : n0;
       const int ab = ti & 1;
       mbar_wait(&acc_full[ab], (ti >> 1) & 1);
       tc_fence_after();
       const uint32_t acc = lane_addr + ab * ACC_STRIDE;
+      auto mma_col = [&](int c) { return GEGLU ? ((c >> 1) * 128 + (c & 1) * 32) : c * EPI_CHUNK; };
 
-      for (int c = 0; c < CPT; ++c, ++gc) {
-        const int mc = p.geglu ? ((c >> 1) * 128 + (c & 1) * 32) : c * EPI_CHUNK;  // MMA column of the chunk
-        float v[32];
-        {
-          uint32_t u[32];
-          tmem_ld_32x32(acc + mc, u);
-          tmem_ld_wait();
+      uint32_t u[32], g[GEGLU ? 32 : 1];
+      if (half < CPT) {
+        tmem_ld_32x32(acc + mma_col(half), u);
+        if constexpr (GEGLU) tmem_ld_32x32(acc + mma_col(half) + 64, reinterpret_cast<uint32_t(&)[32]>(g));
+      }
+      for (int c = half; c < CPT; c += 2, ++gc) {
+        const int mc = mma_col(c);
+        float v[32], gt[GEGLU ? 32 : 1];
+        tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(u[j]) * rs;
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(u[j]) * rs;
+        if constexpr (GEGLU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) gt[j] = __uint_as_float(g[j]) * rs;
+        }
+        if (c + 2 < CPT) {  // prefetch the next chunk's accumulator columns
+          tmem_ld_32x32(acc + mma_col(c + 2), u);
+          if constexpr (GEGLU) tmem_ld_32x32(acc + mma_col(c + 2) + 64, reinterpret_cast<uint32_t(&)[32]>(g));
+        } else {            // accumulator fully read by this thread: hand it back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(&acc_empty[ab]);
         }
         if (p.bias) {
           const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + mc);
@@ -485,24 +523,17 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
             v[4 * j + 3] += b.w;
           }
         }
-        if (p.geglu) {
-          uint32_t g[32];
-          tmem_ld_32x32(acc + mc + 64, g);
-          tmem_ld_wait();
+        if constexpr (GEGLU) {
           const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + mc + 64);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
             if (p.bias) b = __ldg(b4 + j);
-            v[4 * j + 0] *= gelu_fast(__uint_as_float(g[4 * j + 0]) * rs + b.x);
-            v[4 * j + 1] *= gelu_fast(__uint_as_float(g[4 * j + 1]) * rs + b.y);
-            v[4 * j + 2] *= gelu_fast(__uint_as_float(g[4 * j + 2]) * rs + b.z);
-            v[4 * j + 3] *= gelu_fast(__uint_as_float(g[4 * j + 3]) * rs + b.w);
+            v[4 * j + 0] *= gelu_fast(gt[4 * j + 0] + b.x);
+            v[4 * j + 1] *= gelu_fast(gt[4 * j + 1] + b.y);
+            v[4 * j + 2] *= gelu_fast(gt[4 * j + 2] + b.z);
+            v[4 * j + 3] *= gelu_fast(gt[4 * j + 3] + b.w);
           }
-        }
-        if (c == CPT - 1) {  // accumulator fully read: hand it back to the MMA warp
-          tc_fence_before();
-          mbar_arrive(&acc_empty[ab]);
         }
         const int ncol = nout0 + c * EPI_CHUNK;
         if (p.row_bias) {
@@ -520,7 +551,7 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] *= gs;
         }
-        // staging slot of this chunk: holds the residual chunk (if any) and is free for our output
+        // staging slot of this chunk: holds the residual sub-box (if any) and is free for our output
         const int slot = gc % EPI_RO_SLOTS;
         mbar_wait(&ro_ready[slot], (gc / EPI_RO_SLOTS) & 1);
         uint8_t* ro = my_ro + slot * EPI_TILE_BYTES;
@@ -558,19 +589,20 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
           *reinterpret_cast<uint4*>(ro + ((j ^ sw) << 4)) =
               make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
                          pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
-        fence_proxy_async();       // staging tile visible to the TMA store
-        named_bar_sync(1, 128);    // all 128 rows written (and all reads of the X slot done)
-        if (leader) {
-          tma_store_4d(&tmOut, sRO + slot * EPI_TILE_BYTES, ncol, q1, q2, q3);
+        fence_proxy_async();  // staging rows visible to the TMA store
+        __syncwarp();         // all 32 rows written (and this warp's reads of the X slot done)
+        if (lane == 0) {
+          tma_store_4d(&tmOut, sRO + slot * EPI_TILE_BYTES, ncol, q1 + w1, q2 + w2, q3 + w3);
           tma_store_commit();
           // the slot of chunk gc-1 (== slot of chunk gc+2) is reusable once its store has read smem
           tma_store_wait_read<1>();
           issue_ready(gc + 2);
           issue_x(gc + 2);
         }
+        __syncwarp();
       }
     }
-    if (leader) tma_store_wait_all();
+    if (lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -595,6 +627,26 @@ static int launch(const CUtensorMap* a0, const CUtensorMap* a1, const CUtensorMa
   return SA_OK;
 }
 
+template <int BN, int STAGES, bool GEGLU>
+static int launch_persist(const CUtensorMap* a0, const CUtensorMap* a1, const CUtensorMap* b,
+                          const CUtensorMap* o, const CUtensorMap* r, const CUtensorMap* x, GemmKParams p,
+                          int m_tiles, cudaStream_t stream) {
+  using L = Gemm2Smem<BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    SA_CUDA_CHECK(cudaFuncSetAttribute(gemm_tap_persist_kernel<BN, STAGES, GEGLU>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    configured = true;
+  }
+  p.n_tiles_n = p.N / BN;
+  p.total_tiles = m_tiles * p.n_tiles_n;
+  int grid = num_sms();
+  if (grid > p.total_tiles) grid = p.total_tiles;
+  gemm_tap_persist_kernel<BN, STAGES, GEGLU><<<grid, 320, L::TOTAL, stream>>>(*a0, *a1, *b, *o, *r, *x, p);
+  SA_CUDA_CHECK(cudaGetLastError());
+  return SA_OK;
+}
+
 static int pick_tile(int m, int n, int geglu) {
   // cost model: an SM works through ceil(ctas / sms) tiles, each costing ~ (bn + overhead) columns
   // of MMA time; pick the exact divisor of n that minimises it (ties -> larger tile).
@@ -607,8 +659,9 @@ static int pick_tile(int m, int n, int geglu) {
     const int bn = cand[i];
     if (n % bn != 0) continue;
     if (geglu && bn != 256 && bn != 128) continue;
+    if (bn == 32 && n >= 64) continue;
     const long long ctas = m_tiles * (n / bn);
-    const long long cost = ((ctas + sms - 1) / sms) * (bn + 32);
+    const long long cost = ((ctas + sms - 1) / sms) * (bn + 16);
     if (best == 0 || cost < best_cost) {
       best = bn;
       best_cost = cost;
@@ -729,6 +782,42 @@ extern "C" int sa_gemm_tap(const sa_gemm_args* a, void* stream_) {
   if (!tmb) return SA_ERR_TMA;
 
   const int mt = static_cast<int>(m_tiles);
+  p.out_scale = a->out_scale != 0.0f ? a->out_scale : 1.0f;
+  static const bool force_v1 = getenv("SA_GEMM_V1") != nullptr;
+  const bool v2_ok = !force_v1 && !a->out_f32 && (a->n % bn == 0) && bn >= 64;
+  if (v2_ok) {
+    // epilogue tensor maps: [n_out cols, d1, d2, d3]; box = (32 columns) x the 32-row sub-box
+    // (s1, s2, s3) of the tile box that one epilogue warp owns, SWIZZLE_64B
+    const int s1 = p.b1 < 32 ? p.b1 : 32;
+    const int s2 = p.b2 < 32 / s1 ? p.b2 : 32 / s1;
+    const int s3 = 32 / (s1 * s2);
+    auto epi_map = [&](const void* base, long long ld) -> const CUtensorMap* {
+      uint64_t dims[4] = {static_cast<uint64_t>(n_out), static_cast<uint64_t>(a->d1),
+                          static_cast<uint64_t>(a->d2), static_cast<uint64_t>(a->d3)};
+      uint64_t strides[3] = {static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(ld) * 2 * a->d1,
+                             static_cast<uint64_t>(ld) * 2 * a->d1 * a->d2};
+      uint32_t box[4] = {32, static_cast<uint32_t>(s1), static_cast<uint32_t>(s2), static_cast<uint32_t>(s3)};
+      return get_tmap_bf16(base, 4, dims, strides, box, 64);
+    };
+    const CUtensorMap* tmo = epi_map(a->out, a->ldc);
+    const CUtensorMap* tmr = a->residual ? epi_map(a->residual, a->ldr) : tmo;
+    const CUtensorMap* tmx = a->blend_x ? epi_map(a->blend_x, a->ldx) : tmo;
+    if (!tmo || !tmr || !tmx) return SA_ERR_TMA;
+    if (p.geglu) {
+      switch (bn) {
+        case 128: return launch_persist<128, 4, true>(tma[0], tma[1], tmb, tmo, tmr, tmx, p, mt, stream);
+        case 256: return launch_persist<256, 3, true>(tma[0], tma[1], tmb, tmo, tmr, tmx, p, mt, stream);
+        default: break;
+      }
+    } else
+    switch (bn) {
+      case 64: return launch_persist<64, 6, false>(tma[0], tma[1], tmb, tmo, tmr, tmx, p, mt, stream);
+      case 128: return launch_persist<128, 4, false>(tma[0], tma[1], tmb, tmo, tmr, tmx, p, mt, stream);
+      case 160: return launch_persist<160, 4, false>(tma[0], tma[1], tmb, tmo, tmr, tmx, p, mt, stream);
+      case 256: return launch_persist<256, 3, false>(tma[0], tma[1], tmb, tmo, tmr, tmx, p, mt, stream);
+      default: break;
+    }
+  }
   switch (bn) {
     case 32: return launch<32, 4>(tma[0], tma[1], tmb, p, mt, stream);
     case 64: return launch<64, 4>(tma[0], tma[1], tmb, p, mt, stream);

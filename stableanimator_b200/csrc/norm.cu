@@ -52,13 +52,30 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x0,
   float s[8], q[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) s[k] = q[k] = 0.f;
-  for (long long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
-    float v[8];
-    load8(src + (ns * P + r) * ld, v);
+  {
+    // 4 independent 128-bit loads in flight per thread
+    const long long step = blockDim.y;
+    long long r = r0 + threadIdx.y;
+    for (; r + 3 * step < r1; r += 4 * step) {
+      float v[4][8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      s[k] += v[k];
-      q[k] += v[k] * v[k];
+      for (int u = 0; u < 4; ++u) load8(src + (ns * P + r + u * step) * ld, v[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          s[k] += v[u][k];
+          q[k] += v[u][k] * v[u][k];
+        }
+    }
+    for (; r < r1; r += step) {
+      float v[8];
+      load8(src + (ns * P + r) * ld, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        s[k] += v[k];
+        q[k] += v[k] * v[k];
+      }
     }
   }
   // fold the 8 channels into their groups (an octet may straddle two groups)
@@ -116,7 +133,23 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0,
   const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
   long long r1 = r0 + rows_per_cta;
   if (r1 > P) r1 = P;
-  for (long long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+  const long long step = blockDim.y;
+  long long r = r0 + threadIdx.y;
+  for (; r + 3 * step < r1; r += 4 * step) {
+    float v[4][8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) load8(src + (ns * P + r + u * step) * ld, v[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float y = v[u][k] * a[k] + b[k];
+        v[u][k] = do_silu ? silu(y) : y;
+      }
+      store8(out + (ns * P + r + u * step) * ldo + c, v[u]);
+    }
+  }
+  for (; r < r1; r += step) {
     float v[8];
     load8(src + (ns * P + r) * ld, v);
 #pragma unroll
@@ -215,7 +248,7 @@ static int gn_geometry(int C, long long P, int ns, dim3* block, dim3* grid, int*
   long long chunks = (target_ctas + ns - 1) / ns;
   if (chunks < 1) chunks = 1;
   long long rpc = (P + chunks - 1) / chunks;
-  const long long min_rows = static_cast<long long>(ty) * 4;
+  const long long min_rows = static_cast<long long>(ty) * 8;
   if (rpc < min_rows) rpc = min_rows;
   *rows_per_cta = static_cast<int>(rpc);
   *grid = dim3(static_cast<unsigned>((P + rpc - 1) / rpc), ns, 1);

@@ -66,6 +66,7 @@ def gemm_tap(
     out: Optional[torch.Tensor] = None,
     out_f32: bool = False,
     tile_n: int = 0,
+    out_scale: float = 1.0,
 ) -> torch.Tensor:
     """``out = epilogue(sum_taps A(shifted) @ W^T)`` -- see ``sa_gemm_tap`` in include/sa_b200.h.
 
@@ -125,6 +126,7 @@ def gemm_tap(
     args.out, args.ldc = out.data_ptr(), out.stride(-2)
     args.out_f32 = int(out.dtype == torch.float32)
     args.tile_n = tile_n
+    args.out_scale = float(out_scale)
     check(lib().sa_gemm_tap(C.byref(args), _stream()), "sa_gemm_tap")
     return out
 

@@ -232,9 +232,10 @@ class UNetB200:
         h2 = ops.gemm_tap(n3, w[f"{t_}.conv1.w"], grid=gridt, taps=ops.TAPS_T3, bias=w[f"{t_}.conv1.b"],
                           row_bias=temb[:, o_t:o_t + r.cout], rows_per_group=F * S)
         n4 = ops.groupnorm(h2, w[f"{t_}.norm2.g"], w[f"{t_}.norm2.b"], r.eps, F * S, silu=True)
-        # conv2 + residual (xs), then AlphaBlender(alpha*xs + (1-alpha)*temporal) in the same epilogue
+        # conv2 + residual (xs), then AlphaBlender: alpha*xs + (1-alpha)*(xs + conv2) == xs + (1-alpha)*conv2,
+        # one epilogue with a single residual read
         return ops.gemm_tap(n4, w[f"{t_}.conv2.w"], grid=gridt, taps=ops.TAPS_T3, bias=w[f"{t_}.conv2.b"],
-                            residual=xs, blend_x=xs, alpha=w[f"{r.name}.alpha"])
+                            residual=xs, out_scale=1.0 - w[f"{r.name}.alpha"])
 
     def _tst(self, t: TstSpec, x, ctx: _Ctx, B, F, h, wd):
         """TransformerSpatioTemporalModel.forward (unet.py:623-708) on NHWC tokens x [M, C]."""

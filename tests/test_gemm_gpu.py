@@ -126,3 +126,36 @@ def test_fp32_out_small_n():
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), None, padding=1).permute(0, 2, 3, 1)
     assert out.dtype == torch.float32
     assert_close(out.reshape(f, h, w_, 8)[..., :4], ref, tol=1e-4)
+
+
+def test_out_scale_residual_is_alpha_blend():
+    """res-block time mixer: alpha*x + (1-alpha)*(x + conv) == x + (1-alpha)*conv (unet.py:1601-1605)."""
+    from stableanimator_b200 import ops
+    m, k, n, alpha = 4096, 640, 640, 0.57
+    a, w = rnd(m, k, seed=21), rnd(n, k, scale=k ** -0.5, seed=22)
+    bias, x = torch.randn(n, device="cuda"), rnd(m, n, seed=23)
+    out = ops.gemm_tap(a, w, bias=bias, residual=x, out_scale=1.0 - alpha)
+    conv = a.float() @ w.float().t() + bias
+    ref = alpha * x.float() + (1 - alpha) * (x.float() + conv)
+    assert_close(out, ref)
+
+
+@pytest.mark.parametrize("m,k,n", [(148 * 128 * 3 + 77, 320, 320), (300, 64, 1280), (128 * 149, 128, 256)])
+def test_persistent_many_tiles_and_ragged_rows(m, k, n):
+    from stableanimator_b200 import ops
+    a, w = rnd(m, k, seed=24), rnd(n, k, scale=k ** -0.5, seed=25)
+    res = rnd(m, n, seed=26)
+    out = ops.gemm_tap(a, w, residual=res)
+    assert_close(out, a.float() @ w.float().t() + res.float())
+
+
+def test_geglu_matches_exact_erf_gelu_on_wide_range():
+    from stableanimator_b200 import ops
+    m, c = 512, 64
+    a = rnd(m, c, scale=3.0, seed=27)
+    w, b = rnd(8 * c, c, scale=1.0, seed=28), torch.randn(8 * c, device="cuda") * 2
+    wi, bi = ops.interleave_geglu(w, b)
+    out = ops.gemm_tap(a, wi, bias=bi, geglu=True)
+    proj = a.float() @ w.float().t() + b
+    val, gate = proj.chunk(2, dim=-1)
+    assert_close(out, val * F.gelu(gate))
