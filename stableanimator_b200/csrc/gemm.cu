@@ -46,6 +46,7 @@ struct GemmKParams {
   // persistent kernel (v2) only
   int n_tiles_n, total_tiles;
   float out_scale;  // v = (acc*rs + bias + row_bias [geglu]) * out_scale + residual ...
+  FastDiv fd_ntn, fd_t1, fd_t2, fd_rpg;
 };
 
 template <int BN>
@@ -352,11 +353,14 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
   const uint32_t tmem_base = *tmem_slot;
 
   auto tile_origin = [&](int tile, int& n0, int& q1, int& q2, int& q3) {
-    const int nt = tile % p.n_tiles_n, mt = tile / p.n_tiles_n;
-    n0 = nt * BN;
-    q1 = (mt % p.t1) * p.b1;
-    q2 = ((mt / p.t1) % p.t2) * p.b2;
-    q3 = (mt / (p.t1 * p.t2)) * p.b3;
+    uint32_t mt, nt, a, b, c;
+    p.fd_ntn.divmod(static_cast<uint32_t>(tile), mt, nt);
+    p.fd_t1.divmod(mt, a, b);   // b = mt % t1
+    p.fd_t2.divmod(a, c, a);    // a = (mt / t1) % t2, c = mt / (t1*t2)
+    n0 = static_cast<int>(nt) * BN;
+    q1 = static_cast<int>(b) * p.b1;
+    q2 = static_cast<int>(a) * p.b2;
+    q3 = static_cast<int>(c) * p.b3;
   };
 
   if (warp == 0) {
@@ -369,7 +373,7 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
         int tap = 0, ch = 0;
         for (int kb = 0; kb < KB; ++kb, ++it) {
           const int s = it % STAGES;
-          mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+          mbar_wait_relaxed(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
           mbar_expect_tx(&full_bar[s], STAGE_BYTES);
           uint8_t* sa_ = smem + s * STAGE_BYTES;
           const int o1 = p.tap_off[tap * 3 + 0], o2 = p.tap_off[tap * 3 + 1], o3 = p.tap_off[tap * 3 + 2];
@@ -437,55 +441,53 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
     uint8_t* my_ro = sRO + lane * 64;
     const uint8_t* my_x = sX + lane * 64;
 
-    // coordinates of this warp's g-th chunk (its own sequence across tiles)
-    auto chunk_coords = [&](int g, int& col, int& c1, int& c2, int& c3) {
+    // lane 0 prepares the staging slots of this warp's chunks strictly in order (chunk 0, 1, 2, ...),
+    // two chunks ahead of their use: TMA-load the residual / blend sub-boxes, or just mark the slot free
+    int nx_g = 0, nx_tile = blockIdx.x, nx_c = half;
+    auto issue_next = [&]() {
+      if (nx_g >= total_chunks) return;
       int n0, q1, q2, q3;
-      tile_origin(static_cast<int>(blockIdx.x) + (g / cpw) * static_cast<int>(gridDim.x), n0, q1, q2, q3);
-      col = (GEGLU ? n0 / 2 : n0) + (half + 2 * (g % cpw)) * EPI_CHUNK;
-      c1 = q1 + w1;
-      c2 = q2 + w2;
-      c3 = q3 + w3;
-    };
-    // make the staging slot of chunk g ready: TMA-load the residual sub-box, or just mark it free
-    auto issue_ready = [&](int g) {
-      if (g >= total_chunks) return;
-      const int slot = g % EPI_RO_SLOTS;
+      tile_origin(nx_tile, n0, q1, q2, q3);
+      const int col = (GEGLU ? n0 / 2 : n0) + nx_c * EPI_CHUNK;
+      const int slot = nx_g % EPI_RO_SLOTS;
       if (p.residual) {
-        int col, c1, c2, c3;
-        chunk_coords(g, col, c1, c2, c3);
         mbar_expect_tx(&ro_ready[slot], EPI_TILE_BYTES);
-        tma_load_4d(sRO + slot * EPI_TILE_BYTES, &tmRes, &ro_ready[slot], col, c1, c2, c3);
+        tma_load_4d(sRO + slot * EPI_TILE_BYTES, &tmRes, &ro_ready[slot], col, q1 + w1, q2 + w2, q3 + w3);
       } else {
         mbar_arrive(&ro_ready[slot]);
       }
-    };
-    auto issue_x = [&](int g) {
-      if (!p.blend_x || g >= total_chunks) return;
-      const int slot = g % EPI_X_SLOTS;
-      int col, c1, c2, c3;
-      chunk_coords(g, col, c1, c2, c3);
-      mbar_expect_tx(&x_ready[slot], EPI_TILE_BYTES);
-      tma_load_4d(sX + slot * EPI_TILE_BYTES, &tmBld, &x_ready[slot], col, c1, c2, c3);
+      if (p.blend_x) {
+        const int xs = nx_g % EPI_X_SLOTS;
+        mbar_expect_tx(&x_ready[xs], EPI_TILE_BYTES);
+        tma_load_4d(sX + xs * EPI_TILE_BYTES, &tmBld, &x_ready[xs], col, q1 + w1, q2 + w2, q3 + w3);
+      }
+      ++nx_g;
+      nx_c += 2;
+      if (nx_c >= CPT) {
+        nx_c = half;
+        nx_tile += gridDim.x;
+      }
     };
     if (lane == 0) {
-      issue_ready(0);
-      issue_ready(1);
-      issue_x(0);
-      issue_x(1);
+      issue_next();
+      issue_next();
     }
+    const bool need_grp = (p.row_scale != nullptr) || (p.row_bias != nullptr);
 
     int gc = 0, ti = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
       int n0, q1, q2, q3;
       tile_origin(tile, n0, q1, q2, q3);
-      const int p1 = q1 + i1, p2 = q2 + i2, p3 = q3 + i3;
-      const bool valid = (p1 < p.d1) && (p2 < p.d2) && (p3 < p.d3);
-      const long long row = (static_cast<long long>(p3) * p.d2 + p2) * p.d1 + p1;
-      const int grp = valid ? static_cast<int>(row / p.rows_per_group) : 0;
+      int grp = 0;
+      if (need_grp) {
+        const int p1 = q1 + i1, p2 = q2 + i2, p3 = q3 + i3;
+        if ((p1 < p.d1) && (p2 < p.d2) && (p3 < p.d3))
+          grp = static_cast<int>(p.fd_rpg.div(static_cast<uint32_t>((p3 * p.d2 + p2) * p.d1 + p1)));
+      }
       const float rs = p.row_scale ? p.row_scale[grp] : 1.0f;
       const int nout0 = GEGLU ? n0 / 2 : n0;
       const int ab = ti & 1;
-      mbar_wait(&acc_full[ab], (ti >> 1) & 1);
+      mbar_wait_relaxed(&acc_full[ab], (ti >> 1) & 1);
       tc_fence_after();
       const uint32_t acc = lane_addr + ab * ACC_STRIDE;
       auto mma_col = [&](int c) { return GEGLU ? ((c >> 1) * 128 + (c & 1) * 32) : c * EPI_CHUNK; };
@@ -499,11 +501,31 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
         const int mc = mma_col(c);
         float v[32], gt[GEGLU ? 32 : 1];
         tmem_ld_wait();
+        if (p.bias) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + mc);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(u[j]) * rs;
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = __ldg(b4 + j);
+            v[4 * j + 0] = fmaf(__uint_as_float(u[4 * j + 0]), rs, b.x);
+            v[4 * j + 1] = fmaf(__uint_as_float(u[4 * j + 1]), rs, b.y);
+            v[4 * j + 2] = fmaf(__uint_as_float(u[4 * j + 2]), rs, b.z);
+            v[4 * j + 3] = fmaf(__uint_as_float(u[4 * j + 3]), rs, b.w);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(u[j]) * rs;
+        }
         if constexpr (GEGLU) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + mc + 64);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) gt[j] = __uint_as_float(g[j]) * rs;
+          for (int j = 0; j < 8; ++j) {
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias) b = __ldg(b4 + j);
+            gt[4 * j + 0] = fmaf(__uint_as_float(g[4 * j + 0]), rs, b.x);
+            gt[4 * j + 1] = fmaf(__uint_as_float(g[4 * j + 1]), rs, b.y);
+            gt[4 * j + 2] = fmaf(__uint_as_float(g[4 * j + 2]), rs, b.z);
+            gt[4 * j + 3] = fmaf(__uint_as_float(g[4 * j + 3]), rs, b.w);
+          }
         }
         if (c + 2 < CPT) {  // prefetch the next chunk's accumulator columns
           tmem_ld_32x32(acc + mma_col(c + 2), u);
@@ -512,28 +534,9 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
           tc_fence_before();
           mbar_arrive(&acc_empty[ab]);
         }
-        if (p.bias) {
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + mc);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b = __ldg(b4 + j);
-            v[4 * j + 0] += b.x;
-            v[4 * j + 1] += b.y;
-            v[4 * j + 2] += b.z;
-            v[4 * j + 3] += b.w;
-          }
-        }
         if constexpr (GEGLU) {
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + mc + 64);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.bias) b = __ldg(b4 + j);
-            v[4 * j + 0] *= gelu_fast(gt[4 * j + 0] + b.x);
-            v[4 * j + 1] *= gelu_fast(gt[4 * j + 1] + b.y);
-            v[4 * j + 2] *= gelu_fast(gt[4 * j + 2] + b.z);
-            v[4 * j + 3] *= gelu_fast(gt[4 * j + 3] + b.w);
-          }
+          for (int j = 0; j < 32; ++j) v[j] *= gelu_fast(gt[j]);
         }
         const int ncol = nout0 + c * EPI_CHUNK;
         if (p.row_bias) {
@@ -596,8 +599,7 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
           tma_store_commit();
           // the slot of chunk gc-1 (== slot of chunk gc+2) is reusable once its store has read smem
           tma_store_wait_read<1>();
-          issue_ready(gc + 2);
-          issue_x(gc + 2);
+          issue_next();
         }
         __syncwarp();
       }
@@ -640,6 +642,10 @@ static int launch_persist(const CUtensorMap* a0, const CUtensorMap* a1, const CU
   }
   p.n_tiles_n = p.N / BN;
   p.total_tiles = m_tiles * p.n_tiles_n;
+  p.fd_ntn.init(p.n_tiles_n);
+  p.fd_t1.init(p.t1);
+  p.fd_t2.init(p.t2);
+  p.fd_rpg.init(p.rows_per_group);
   int grid = num_sms();
   if (grid > p.total_tiles) grid = p.total_tiles;
   gemm_tap_persist_kernel<BN, STAGES, GEGLU><<<grid, 320, L::TOTAL, stream>>>(*a0, *a1, *b, *o, *r, *x, p);
@@ -658,7 +664,7 @@ static int pick_tile(int m, int n, int geglu) {
   for (int i = 0; i < 5; ++i) {
     const int bn = cand[i];
     if (n % bn != 0) continue;
-    if (geglu && bn != 256 && bn != 128) continue;
+    if (geglu && bn != 128) continue;  // measured: 128 beats 256 (3 stages) at every level
     if (bn == 32 && n >= 64) continue;
     const long long ctas = m_tiles * (n / bn);
     const long long cost = ((ctas + sms - 1) / sms) * (bn + 16);

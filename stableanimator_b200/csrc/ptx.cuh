@@ -56,6 +56,35 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// same, for waiters that are not on the critical path: back off between polls so the spinning warp
+// does not steal issue slots from the warps doing the work
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(64);
+}
+
+// unsigned division by a runtime constant without the ~20-instruction hardware sequence
+// (q = umulhi(x, mul) >> shr, valid for 0 <= x < 2^31; CUTLASS FastDivmod construction)
+struct FastDiv {
+  uint32_t d, mul, shr;
+  __host__ void init(uint32_t div) {
+    d = div;
+    if (div <= 1) {
+      mul = 0;
+      shr = 0;
+      return;
+    }
+    uint32_t lg = 0;
+    while ((1u << lg) < div) ++lg;
+    const uint32_t p = 31 + lg;
+    mul = static_cast<uint32_t>(((1ull << p) + div - 1) / div);
+    shr = p - 32;
+  }
+  __device__ __forceinline__ uint32_t div(uint32_t x) const { return d <= 1 ? x : (__umulhi(x, mul) >> shr); }
+  __device__ __forceinline__ void divmod(uint32_t x, uint32_t& q, uint32_t& r) const {
+    q = div(x);
+    r = x - q * d;
+  }
+};
 
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
@@ -209,17 +238,23 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
-// exact-GELU x * Phi(x) with erf from Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far below bf16
-// resolution), evaluated on the tail side so negative inputs do not cancel: ~12 instructions
+// exact-GELU x * Phi(x), Phi from erfc by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7 + approx-unit
+// error, far below bf16 resolution), evaluated on the tail side so negative inputs do not cancel.
+// Branch-free, 2 MUFU (rcp, ex2) + ~12 FMA-pipe instructions.
 __device__ __forceinline__ float gelu_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float e = 0.5f * p * t * __expf(-z * z);  // 0.5 * erfc(z)
-  return x * (x >= 0.f ? 1.0f - e : e);
+  const float ax = fabsf(x);
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(ax, 0.3275911f * 0.70710678118654752440f, 1.0f)));
+  // 0.5 * (a1 t + a2 t^2 + ... + a5 t^5), Horner, 0.5 folded into the coefficients
+  float p = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  p = fmaf(p, t, 0.5f * 1.421413741f);
+  p = fmaf(p, t, 0.5f * -0.284496736f);
+  p = fmaf(p, t, 0.5f * 0.254829592f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.72134752044448170368f));  // exp(-x^2/2)
+  const float h = p * t * e;                       // 0.5 * erfc(|x| / sqrt 2) = Phi(-|x|)
+  const float cdf = x >= 0.f ? 1.0f - h : h;
+  return x * cdf;
 }
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
