@@ -29,74 +29,170 @@ __device__ __forceinline__ void ld32(const __nv_bfloat16* p, float (&v)[32]) {
   }
 }
 
-// One warp per (batch b, pixel s, head h).  lane = (half << 4) | frame: each lane owns query frame
-// i and 32 of the 64 head dims.
-__global__ void __launch_bounds__(256)
+// One warp per (batch b, pixel s, head h): the 16x16 attention over frames maps exactly onto
+// mma.sync m16n8k16 tiles (bf16 in, fp32 accumulate) -- the problem is far too small for tcgen05 and is
+// HBM-bound; the legacy warp-level MMA just removes the ~2000 FMA instructions per task that made the
+// first version instruction-bound.  Per task: cp.async the three [F x 64] tiles (128-byte rows, XOR
+// swizzled) -> S = Q K^T (8 MMAs) -> softmax in the accumulator fragments -> P as the A fragment of
+// O = P V (8 MMAs, V via ldmatrix.trans) -> O staged through smem -> 16-byte coalesced stores.
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                               uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
+constexpr int AT_WARPS = 8;
+constexpr int AT_TILE = 16 * 128;  // one [16 frames x 64 dims] bf16 tile
+
+__global__ void __launch_bounds__(AT_WARPS * 32)
 attn_temporal_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, int B, int F, int S, int C,
                      int heads, __nv_bfloat16* __restrict__ out, int ldo) {
-  const int lane = threadIdx.x & 31;
-  const long long task = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  __shared__ __align__(128) uint8_t sm[AT_WARPS][3][AT_TILE];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long task = static_cast<long long>(blockIdx.x) * AT_WARPS + warp;
   const long long ntasks = static_cast<long long>(B) * S * heads;
   if (task >= ntasks) return;
   const int h = static_cast<int>(task % heads);
   const long long bs = task / heads;
   const int s = static_cast<int>(bs % S);
   const int b = static_cast<int>(bs / S);
-  const int i = lane & 15, half = lane >> 4;
-  const int iq = i < F ? i : F - 1;
-  const long long row0 = static_cast<long long>(b) * F * S + s;  // row of frame 0
-  const int col = h * 64 + half * 32;
+  const long long row0 = static_cast<long long>(b) * F * S + s;  // global row of frame 0
+  uint8_t* sq = sm[warp][0];
+  uint8_t* sk = sm[warp][1];
+  uint8_t* sv = sm[warp][2];
 
-  float q[32];
-  ld32(qkv + (row0 + static_cast<long long>(iq) * S) * ld + col, q);
+  // ---- load: chunk id = lane + 32*i -> (frame = id / 8, 16-byte chunk = id % 8); rows >= F are zeroed
 #pragma unroll
-  for (int d = 0; d < 32; ++d) q[d] *= 0.125f;  // attn.scale = 64^-0.5 (unet.py:737)
+  for (int i = 0; i < 4; ++i) {
+    const int id = lane + 32 * i;
+    const int f = id >> 3, ch = id & 7;
+    const uint32_t off = f * 128 + ((ch ^ (f & 7)) << 4);
+    if (f < F) {
+      const __nv_bfloat16* g = qkv + (row0 + static_cast<long long>(f) * S) * ld + h * 64 + ch * 8;
+      cp_async16(smem_u32(sq + off), g);
+      cp_async16(smem_u32(sk + off), g + C);
+      cp_async16(smem_u32(sv + off), g + 2 * C);
+    } else {
+      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(sq + off) = z;
+      *reinterpret_cast<uint4*>(sk + off) = z;
+      *reinterpret_cast<uint4*>(sv + off) = z;
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
 
-  float sc[16];
-  float mx = -INFINITY;
+  // ---- S = Q K^T : two n-tiles (keys 0-7, 8-15), 4 k-steps over the 64 dims
+  float sc[2][4];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    sc[j] = -INFINITY;
-    if (j < F) {
-      float k[32];
-      ld32(qkv + (row0 + static_cast<long long>(j) * S) * ld + C + col, k);
-      float p = 0.f;
+  for (int n = 0; n < 2; ++n)
 #pragma unroll
-      for (int d = 0; d < 32; ++d) p += q[d] * k[d];
-      p += __shfl_xor_sync(0xffffffffu, p, 16);
-      sc[j] = p;
-      mx = fmaxf(mx, p);
+    for (int e = 0; e < 4; ++e) sc[n][e] = 0.f;
+  {
+    const int ar = (lane & 7) + 8 * ((lane >> 3) & 1);   // A: row, k-half = lane >> 4
+    const int br = (lane & 7) + 8 * (lane >> 4);          // B (K rows = keys): key row, k-half = (lane >> 3) & 1
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
+      ldsm_x4(smem_u32(sq + ar * 128 + (((2 * ks + (lane >> 4)) ^ (ar & 7)) << 4)), a0, a1, a2, a3);
+      ldsm_x4(smem_u32(sk + br * 128 + (((2 * ks + ((lane >> 3) & 1)) ^ (br & 7)) << 4)), b0, b1, b2, b3);
+      mma_bf16_16816(sc[0], a0, a1, a2, a3, b0, b1);
+      mma_bf16_16816(sc[1], a0, a1, a2, a3, b2, b3);
     }
   }
-  float l = 0.f;
+  // ---- softmax over keys (columns); fragment: e0,e1 -> row lane/4, cols 8n + 2(lane%4) + {0,1};
+  //      e2,e3 -> row lane/4 + 8.  attn.scale = 64^-0.5 folded into the exp2 argument.
+  const float sl2 = 0.125f * 1.4426950408889634f;
+  float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    if (j < F) {
-      sc[j] = __expf(sc[j] - mx);
-      l += sc[j];
+  for (int n = 0; n < 2; ++n)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int col = 8 * n + 2 * (lane & 3) + (e & 1);
+      if (col >= F) sc[n][e] = -INFINITY;
+      mx[e >> 1] = fmaxf(mx[e >> 1], sc[n][e]);
+    }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+    mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+  }
+  float sum[2] = {0.f, 0.f};
+#pragma unroll
+  for (int n = 0; n < 2; ++n)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      sc[n][e] = ex2_approx((sc[n][e] - mx[e >> 1]) * sl2);
+      sum[e >> 1] += sc[n][e];
+    }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 1);
+    sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 2);
+  }
+  const float inv0 = 1.0f / sum[0], inv1 = 1.0f / sum[1];
+  // P as the A fragment of the PV MMA (k = keys): the two S n-tiles are exactly the k-halves.
+  // P is split into bf16 hi + lo parts (two MMAs per tile, free here: the kernel is HBM-bound) so the
+  // probabilities carry ~16 significant bits instead of 8.
+  float pn[8] = {sc[0][0] * inv0, sc[0][1] * inv0, sc[0][2] * inv1, sc[0][3] * inv1,
+                 sc[1][0] * inv0, sc[1][1] * inv0, sc[1][2] * inv1, sc[1][3] * inv1};
+  uint32_t ph[4], pl[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    ph[i] = pack_bf16x2(pn[2 * i], pn[2 * i + 1]);
+    const float2 hf = unpack_bf16x2(ph[i]);
+    pl[i] = pack_bf16x2(pn[2 * i] - hf.x, pn[2 * i + 1] - hf.y);
+  }
+
+  // ---- O = P V : 8 n-tiles of 8 dims, one k-step (16 keys); V^T fragments via ldmatrix.trans
+  float o[8][4];
+#pragma unroll
+  for (int n = 0; n < 8; ++n)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[n][e] = 0.f;
+  {
+    const int vr = (lane & 7) + 8 * ((lane >> 3) & 1);  // key row; n-tile pair member = lane >> 4
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      uint32_t b0, b1, b2, b3;
+      ldsm_x4_t(smem_u32(sv + vr * 128 + (((2 * np + (lane >> 4)) ^ (vr & 7)) << 4)), b0, b1, b2, b3);
+      mma_bf16_16816(o[2 * np], ph[0], ph[1], ph[2], ph[3], b0, b1);
+      mma_bf16_16816(o[2 * np], pl[0], pl[1], pl[2], pl[3], b0, b1);
+      mma_bf16_16816(o[2 * np + 1], ph[0], ph[1], ph[2], ph[3], b2, b3);
+      mma_bf16_16816(o[2 * np + 1], pl[0], pl[1], pl[2], pl[3], b2, b3);
     }
   }
-  const float inv = 1.0f / l;
-  float o[32];
+  // ---- stage O (bf16) in the Q tile, then coalesced 16-byte stores
+  __syncwarp();
 #pragma unroll
-  for (int d = 0; d < 32; ++d) o[d] = 0.f;
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    if (j < F) {
-      float v[32];
-      ld32(qkv + (row0 + static_cast<long long>(j) * S) * ld + 2 * C + col, v);
-      const float p = sc[j] * inv;
-#pragma unroll
-      for (int d = 0; d < 32; ++d) o[d] += p * v[d];
-    }
+  for (int n = 0; n < 8; ++n) {
+    const int r = lane >> 2;
+    *reinterpret_cast<uint32_t*>(sq + r * 128 + ((n ^ (r & 7)) << 4) + (lane & 3) * 4) = pack_bf16x2(o[n][0], o[n][1]);
+    *reinterpret_cast<uint32_t*>(sq + (r + 8) * 128 + ((n ^ ((r + 8) & 7)) << 4) + (lane & 3) * 4) =
+        pack_bf16x2(o[n][2], o[n][3]);
   }
-  if (i < F) {
-    uint4* dst = reinterpret_cast<uint4*>(out + (row0 + static_cast<long long>(i) * S) * ldo + col);
+  __syncwarp();
 #pragma unroll
-    for (int t = 0; t < 4; ++t)
-      dst[t] = make_uint4(pack_bf16x2(o[8 * t], o[8 * t + 1]), pack_bf16x2(o[8 * t + 2], o[8 * t + 3]),
-                          pack_bf16x2(o[8 * t + 4], o[8 * t + 5]),
-                          pack_bf16x2(o[8 * t + 6], o[8 * t + 7]));
+  for (int i = 0; i < 4; ++i) {
+    const int id = lane + 32 * i;
+    const int f = id >> 3, ch = id & 7;
+    if (f < F) {
+      const uint4 v = *reinterpret_cast<const uint4*>(sq + f * 128 + ((ch ^ (f & 7)) << 4));
+      *reinterpret_cast<uint4*>(out + (row0 + static_cast<long long>(f) * S) * ldo + h * 64 + ch * 8) = v;
+    }
   }
 }
 
@@ -282,8 +378,8 @@ extern "C" int sa_attn_temporal(const void* qkv, int32_t ld, int32_t B, int32_t 
   if (F < 1 || F > 16) return fail(SA_ERR_INVALID, "sa_attn_temporal: F=%d must be in [1,16]", F);
   if (C != heads * 64 || ld % 8 || ldo % 8) return fail(SA_ERR_INVALID, "sa_attn_temporal: head_dim must be 64");
   const long long ntasks = static_cast<long long>(B) * S * heads;
-  const unsigned grid = static_cast<unsigned>((ntasks + 7) / 8);
-  attn_temporal_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(qkv), ld, B, F, S, C,
+  const unsigned grid = static_cast<unsigned>((ntasks + AT_WARPS - 1) / AT_WARPS);
+  attn_temporal_kernel<<<grid, AT_WARPS * 32, 0, stream>>>(static_cast<const __nv_bfloat16*>(qkv), ld, B, F, S, C,
                                                  heads, static_cast<__nv_bfloat16*>(out), ldo);
   SA_CUDA_CHECK(cudaGetLastError());
   return SA_OK;

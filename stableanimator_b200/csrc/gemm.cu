@@ -290,27 +290,30 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
 //                 every global access of the epilogue is a bulk copy.
 // =====================================================================================================
 constexpr int EPI_CHUNK = 32;             // output columns per chunk
-constexpr int EPI_WARPS = 8;
 constexpr int EPI_TILE_BYTES = 32 * 64;   // per-warp staging tile: [32 rows][32 bf16]
 constexpr int EPI_RO_SLOTS = 3, EPI_X_SLOTS = 2;
 constexpr int EPI_WARP_BYTES = (EPI_RO_SLOTS + EPI_X_SLOTS) * EPI_TILE_BYTES;
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EW>
 struct Gemm2Smem {
   static constexpr int STAGE_BYTES = 128 * 128 + BN * 128;
   static constexpr int EPI_OFF = STAGES * STAGE_BYTES;
-  static constexpr int BAR_OFF = EPI_OFF + EPI_WARPS * EPI_WARP_BYTES;
-  static constexpr int NBARS = 2 * STAGES + 4 + EPI_WARPS * (EPI_RO_SLOTS + EPI_X_SLOTS);
+  static constexpr int BAR_OFF = EPI_OFF + EW * EPI_WARP_BYTES;
+  static constexpr int NBARS = 2 * STAGES + 4 + EW * (EPI_RO_SLOTS + EPI_X_SLOTS);
   static constexpr int TOTAL = BAR_OFF + NBARS * 8 + 16 + 1024;  // + tmem slot + alignment slack
 };
 
-template <int BN, int STAGES, bool GEGLU>
-__global__ void __launch_bounds__(320, 1)
+// EW = number of epilogue warps: 8 (two per TMEM quadrant, alternating chunks) for short-K problems
+// whose epilogue must keep up with a short main loop, 4 (less staging smem -> one more pipeline stage)
+// for long-K problems.
+template <int BN, int STAGES, bool GEGLU, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                         const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
                         const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmBld,
                         const GemmKParams p) {
-  using L = Gemm2Smem<BN, STAGES>;
+  using L = Gemm2Smem<BN, STAGES, EW>;
+  constexpr int CSTRIDE = EW / 4;  // chunk stride of one epilogue warp
   constexpr int A_BYTES = 128 * 128;
   constexpr int STAGE_BYTES = L::STAGE_BYTES;
   constexpr int TCOLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
@@ -323,7 +326,7 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
   uint64_t* acc_full = empty_bar + STAGES;   // [2]
   uint64_t* acc_empty = acc_full + 2;        // [2]
   uint64_t* epi_bar = acc_empty + 2;         // [EPI_WARPS][RO_SLOTS + X_SLOTS]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_bar + EPI_WARPS * (EPI_RO_SLOTS + EPI_X_SLOTS));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_bar + EW * (EPI_RO_SLOTS + EPI_X_SLOTS));
 
   const int warp = threadIdx.x >> 5;
   const int KB = p.ntaps * p.kcpt;
@@ -341,9 +344,9 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], EPI_WARPS * 32);
+      mbar_init(&acc_empty[i], EW * 32);
     }
-    for (int i = 0; i < EPI_WARPS * (EPI_RO_SLOTS + EPI_X_SLOTS); ++i) mbar_init(&epi_bar[i], 1);
+    for (int i = 0; i < EW * (EPI_RO_SLOTS + EPI_X_SLOTS); ++i) mbar_init(&epi_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<TCOLS>(tmem_slot);
@@ -416,10 +419,10 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------------ epilogue (8 decoupled warps)
-    const int ew = warp - 2;              // 0..7
+    // ------------------------------------------------------------------ epilogue (EW decoupled warps)
+    const int ew = warp - 2;              // 0..EW-1
     const int quad = warp & 3;            // TMEM lane quadrant this warp may access
-    const int half = ew >> 2;             // 0: even chunks, 1: odd chunks
+    const int half = ew >> 2;             // first chunk of this warp (chunks half, half+CSTRIDE, ...)
     const int lane = threadIdx.x & 31;
     const int r = quad * 32 + lane;       // tile row == TMEM lane
     const int i1 = r % p.b1, i2 = (r / p.b1) % p.b2, i3 = r / (p.b1 * p.b2);
@@ -430,7 +433,7 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
     const float alpha = p.alpha, beta = 1.0f - p.alpha, gs = p.out_scale;
     const int my_tiles = (p.total_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
                          static_cast<int>(gridDim.x);
-    const int cpw = (CPT - half + 1) / 2;           // chunks of a tile handled by this warp
+    const int cpw = (CPT - half + CSTRIDE - 1) / CSTRIDE;  // chunks of a tile handled by this warp
     const int total_chunks = my_tiles * cpw;
     uint8_t* wbase = smem + L::EPI_OFF + ew * EPI_WARP_BYTES;
     uint8_t* sRO = wbase;
@@ -462,7 +465,7 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
         tma_load_4d(sX + xs * EPI_TILE_BYTES, &tmBld, &x_ready[xs], col, q1 + w1, q2 + w2, q3 + w3);
       }
       ++nx_g;
-      nx_c += 2;
+      nx_c += CSTRIDE;
       if (nx_c >= CPT) {
         nx_c = half;
         nx_tile += gridDim.x;
@@ -497,7 +500,7 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
         tmem_ld_32x32(acc + mma_col(half), u);
         if constexpr (GEGLU) tmem_ld_32x32(acc + mma_col(half) + 64, reinterpret_cast<uint32_t(&)[32]>(g));
       }
-      for (int c = half; c < CPT; c += 2, ++gc) {
+      for (int c = half; c < CPT; c += CSTRIDE, ++gc) {
         const int mc = mma_col(c);
         float v[32], gt[GEGLU ? 32 : 1];
         tmem_ld_wait();
@@ -527,9 +530,9 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
             gt[4 * j + 3] = fmaf(__uint_as_float(g[4 * j + 3]), rs, b.w);
           }
         }
-        if (c + 2 < CPT) {  // prefetch the next chunk's accumulator columns
-          tmem_ld_32x32(acc + mma_col(c + 2), u);
-          if constexpr (GEGLU) tmem_ld_32x32(acc + mma_col(c + 2) + 64, reinterpret_cast<uint32_t(&)[32]>(g));
+        if (c + CSTRIDE < CPT) {  // prefetch the next chunk's accumulator columns
+          tmem_ld_32x32(acc + mma_col(c + CSTRIDE), u);
+          if constexpr (GEGLU) tmem_ld_32x32(acc + mma_col(c + CSTRIDE) + 64, reinterpret_cast<uint32_t(&)[32]>(g));
         } else {            // accumulator fully read by this thread: hand it back to the MMA warp
           tc_fence_before();
           mbar_arrive(&acc_empty[ab]);
@@ -629,14 +632,14 @@ static int launch(const CUtensorMap* a0, const CUtensorMap* a1, const CUtensorMa
   return SA_OK;
 }
 
-template <int BN, int STAGES, bool GEGLU>
+template <int BN, int STAGES, bool GEGLU, int EW>
 static int launch_persist(const CUtensorMap* a0, const CUtensorMap* a1, const CUtensorMap* b,
                           const CUtensorMap* o, const CUtensorMap* r, const CUtensorMap* x, GemmKParams p,
                           int m_tiles, cudaStream_t stream) {
-  using L = Gemm2Smem<BN, STAGES>;
+  using L = Gemm2Smem<BN, STAGES, EW>;
   static bool configured = false;
   if (!configured) {
-    SA_CUDA_CHECK(cudaFuncSetAttribute(gemm_tap_persist_kernel<BN, STAGES, GEGLU>,
+    SA_CUDA_CHECK(cudaFuncSetAttribute(gemm_tap_persist_kernel<BN, STAGES, GEGLU, EW>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
   }
@@ -648,12 +651,12 @@ static int launch_persist(const CUtensorMap* a0, const CUtensorMap* a1, const CU
   p.fd_rpg.init(p.rows_per_group);
   int grid = num_sms();
   if (grid > p.total_tiles) grid = p.total_tiles;
-  gemm_tap_persist_kernel<BN, STAGES, GEGLU><<<grid, 320, L::TOTAL, stream>>>(*a0, *a1, *b, *o, *r, *x, p);
+  gemm_tap_persist_kernel<BN, STAGES, GEGLU, EW><<<grid, 64 + 32 * EW, L::TOTAL, stream>>>(*a0, *a1, *b, *o, *r, *x, p);
   SA_CUDA_CHECK(cudaGetLastError());
   return SA_OK;
 }
 
-static int pick_tile(int m, int n, int geglu) {
+static int pick_tile(int m, int n, int geglu, long long k = 0) {
   // cost model: an SM works through ceil(ctas / sms) tiles, each costing ~ (bn + overhead) columns
   // of MMA time; pick the exact divisor of n that minimises it (ties -> larger tile).
   const long long m_tiles = (m + 127) / 128;
@@ -664,7 +667,7 @@ static int pick_tile(int m, int n, int geglu) {
   for (int i = 0; i < 5; ++i) {
     const int bn = cand[i];
     if (n % bn != 0) continue;
-    if (geglu && bn != 128) continue;  // measured: 128 beats 256 (3 stages) at every level
+    if (geglu && bn != (k >= 1280 ? 256 : 128)) continue;  // measured: 256 wins from K = 1280 up
     if (bn == 32 && n >= 64) continue;
     const long long ctas = m_tiles * (n / bn);
     const long long cost = ((ctas + sms - 1) / sms) * (bn + 16);
@@ -758,7 +761,8 @@ extern "C" int sa_gemm_tap(const sa_gemm_args* a, void* stream_) {
   p.ldc = a->ldc;
   p.out_f32 = a->out_f32;
 
-  int bn = a->tile_n ? a->tile_n : pick_tile(p.M, p.N, p.geglu);
+  const long long ktot_pick = static_cast<long long>(a->ntaps) * (a->c0 + a->c1);
+  int bn = a->tile_n ? a->tile_n : pick_tile(p.M, p.N, p.geglu, ktot_pick);
   if (p.geglu && bn != 128 && bn != 256) return fail(SA_ERR_INVALID, "sa_gemm_tap: geglu tile must be 128/256");
 
   // tensor maps: A sources as rank-4 (C, d1, d2, d3); W as rank-2 (K, N)
@@ -809,20 +813,23 @@ extern "C" int sa_gemm_tap(const sa_gemm_args* a, void* stream_) {
     const CUtensorMap* tmr = a->residual ? epi_map(a->residual, a->ldr) : tmo;
     const CUtensorMap* tmx = a->blend_x ? epi_map(a->blend_x, a->ldx) : tmo;
     if (!tmo || !tmr || !tmx) return SA_ERR_TMA;
+    const bool long_k = ktot >= 1280;  // long main loop: 4 epilogue warps, one more pipeline stage
+#define SA_LP(BN_, ST_, G_, EW_) return launch_persist<BN_, ST_, G_, EW_>(tma[0], tma[1], tmb, tmo, tmr, tmx, p, mt, stream)
     if (p.geglu) {
       switch (bn) {
-        case 128: return launch_persist<128, 4, true>(tma[0], tma[1], tmb, tmo, tmr, tmx, p, mt, stream);
-        case 256: return launch_persist<256, 3, true>(tma[0], tma[1], tmb, tmo, tmr, tmx, p, mt, stream);
+        case 128: if (long_k) SA_LP(128, 5, true, 4); else SA_LP(128, 4, true, 8);
+        case 256: SA_LP(256, 3, true, 8);
         default: break;
       }
     } else
     switch (bn) {
-      case 64: return launch_persist<64, 6, false>(tma[0], tma[1], tmb, tmo, tmr, tmx, p, mt, stream);
-      case 128: return launch_persist<128, 4, false>(tma[0], tma[1], tmb, tmo, tmr, tmx, p, mt, stream);
-      case 160: return launch_persist<160, 4, false>(tma[0], tma[1], tmb, tmo, tmr, tmx, p, mt, stream);
-      case 256: return launch_persist<256, 3, false>(tma[0], tma[1], tmb, tmo, tmr, tmx, p, mt, stream);
+      case 64: SA_LP(64, 6, false, 8);
+      case 128: if (long_k) SA_LP(128, 5, false, 4); else SA_LP(128, 4, false, 8);
+      case 160: if (long_k) SA_LP(160, 5, false, 4); else SA_LP(160, 4, false, 8);
+      case 256: SA_LP(256, 3, false, 8);
       default: break;
     }
+#undef SA_LP
   }
   switch (bn) {
     case 32: return launch<32, 4>(tma[0], tma[1], tmb, p, mt, stream);

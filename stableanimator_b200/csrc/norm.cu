@@ -162,74 +162,74 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0,
 }
 
 // ------------------------------------------------------------------ LayerNorm
-// One warp per row.  y = LN(x + addv[row / rows_per_group]) * gamma + beta; optionally stores the
-// pre-norm sum (the new residual stream) to x_out.
-template <int MAXO>
+// LPR lanes per row (8, 16 or 32), OPL octets (8 channels, 16 B) per lane, LPR * OPL == C / 8, so a
+// warp normalises 32 / LPR rows at once with every lane busy (C = 320 -> 8 lanes x 5 octets, 4 rows
+// per warp).  y = LN(x + addv[row / rows_per_group]) * gamma + beta; optionally stores the pre-norm sum
+// (the new residual stream) to x_out.  Two-pass variance in registers.
+template <int LPR, int OPL>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const __nv_bfloat16* __restrict__ x, int ldx, long long M, int C,
                  const float* __restrict__ addv, int rows_per_group,
                  __nv_bfloat16* __restrict__ x_out, int ldxo, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y, int ldy) {
+  constexpr int RPW = 32 / LPR;  // rows per warp
   const int lane = threadIdx.x & 31;
-  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= M) return;
-  const int noct = C >> 3;
-  float v[MAXO][8];
+  const int sub = lane / LPR, l = lane % LPR;
+  const long long warp_id = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long row = warp_id * RPW + sub;
+  const bool active = row < M;
+  const long long rr = active ? row : 0;
+  float v[OPL][8];
   float sum = 0.f;
-  const float* av = addv ? addv + (row / rows_per_group) * C : nullptr;
+  const float* av = addv ? addv + (rr / rows_per_group) * C : nullptr;
 #pragma unroll
-  for (int o = 0; o < MAXO; ++o) {
-    const int oc = lane + 32 * o;
-    if (oc < noct) {
-      load8(x + row * ldx + oc * 8, v[o]);
-      if (av) {
-        const float4 a0 = __ldg(reinterpret_cast<const float4*>(av + oc * 8));
-        const float4 a1 = __ldg(reinterpret_cast<const float4*>(av + oc * 8 + 4));
-        v[o][0] += a0.x; v[o][1] += a0.y; v[o][2] += a0.z; v[o][3] += a0.w;
-        v[o][4] += a1.x; v[o][5] += a1.y; v[o][6] += a1.z; v[o][7] += a1.w;
-        if (x_out) {
-          store8(x_out + row * ldxo + oc * 8, v[o]);
-          // keep the bf16-rounded value: it is what every later consumer of the stream reads
+  for (int o = 0; o < OPL; ++o) {
+    const int oc = l + LPR * o;
+    load8(x + rr * ldx + oc * 8, v[o]);
+    if (av) {
+      const float4 a0 = __ldg(reinterpret_cast<const float4*>(av + oc * 8));
+      const float4 a1 = __ldg(reinterpret_cast<const float4*>(av + oc * 8 + 4));
+      v[o][0] += a0.x; v[o][1] += a0.y; v[o][2] += a0.z; v[o][3] += a0.w;
+      v[o][4] += a1.x; v[o][5] += a1.y; v[o][6] += a1.z; v[o][7] += a1.w;
+      if (x_out) {
+        if (active) store8(x_out + rr * ldxo + oc * 8, v[o]);
+        // keep the bf16-rounded value: it is what every later consumer of the stream reads
 #pragma unroll
-          for (int k = 0; k < 8; ++k) v[o][k] = __bfloat162float(__float2bfloat16_rn(v[o][k]));
-        }
+        for (int k = 0; k < 8; ++k) v[o][k] = __bfloat162float(__float2bfloat16_rn(v[o][k]));
       }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) sum += v[o][k];
     }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sum += v[o][k];
   }
 #pragma unroll
-  for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+  for (int d = LPR / 2; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
   const float mean = sum / static_cast<float>(C);
   float var = 0.f;
 #pragma unroll
-  for (int o = 0; o < MAXO; ++o) {
-    if (lane + 32 * o < noct) {
+  for (int o = 0; o < OPL; ++o) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float d = v[o][k] - mean;
-        var += d * d;
-      }
+    for (int k = 0; k < 8; ++k) {
+      const float d = v[o][k] - mean;
+      var += d * d;
     }
   }
 #pragma unroll
-  for (int d = 16; d > 0; d >>= 1) var += __shfl_xor_sync(0xffffffffu, var, d);
+  for (int d = LPR / 2; d > 0; d >>= 1) var += __shfl_xor_sync(0xffffffffu, var, d);
   const float rstd = rsqrtf(var / static_cast<float>(C) + eps);
+  if (!active) return;
 #pragma unroll
-  for (int o = 0; o < MAXO; ++o) {
-    const int oc = lane + 32 * o;
-    if (oc < noct) {
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + oc * 8));
-      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + oc * 8 + 4));
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + oc * 8));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + oc * 8 + 4));
-      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-      float o8[8];
+  for (int o = 0; o < OPL; ++o) {
+    const int oc = l + LPR * o;
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + oc * 8));
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + oc * 8 + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + oc * 8));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + oc * 8 + 4));
+    const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    float o8[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) o8[k] = (v[o][k] - mean) * rstd * g[k] + b[k];
-      store8(y + row * ldy + oc * 8, o8);
-    }
+    for (int k = 0; k < 8; ++k) o8[k] = fmaf((v[o][k] - mean) * rstd, g[k], bb[k]);
+    store8(y + rr * ldy + oc * 8, o8);
   }
 }
 
@@ -288,23 +288,40 @@ extern "C" int sa_layernorm(const void* x, int32_t ldx, int64_t rows, int32_t c,
                             const float* beta, float eps, void* y, int32_t ldy, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!x || !y || !gamma || !beta) return fail(SA_ERR_INVALID, "sa_layernorm: null pointer");
-  if (c % 8 || c > 2048 || c <= 0) return fail(SA_ERR_INVALID, "sa_layernorm: C=%d unsupported", c);
+  if (c % 64 || c > 2048 || c <= 0) return fail(SA_ERR_INVALID, "sa_layernorm: C=%d unsupported (multiple of 64, <= 2048)", c);
   if (rows <= 0) return SA_OK;
-  const int warps = 8;
-  const unsigned grid = static_cast<unsigned>((rows + warps - 1) / warps);
   const int rpg = rows_per_group > 0 ? rows_per_group : 1;
   const int noct = c / 8;
+  // lanes per row: the largest of 32/16/8 that divides C/8 with at most 8 octets per lane
+  int lpr = 0;
+  for (int cand = 32; cand >= 8; cand >>= 1)
+    if (noct % cand == 0 && noct / cand <= 8) {
+      lpr = cand;
+      break;
+    }
+  if (!lpr) return fail(SA_ERR_INVALID, "sa_layernorm: C=%d unsupported", c);
+  const int opl = noct / lpr;
+  const int warps = 8, rpw = 32 / lpr;
+  const unsigned grid = static_cast<unsigned>((rows + static_cast<long long>(warps) * rpw - 1) / (warps * rpw));
   const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x);
   __nv_bfloat16* xo = static_cast<__nv_bfloat16*>(x_out);
   __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(y);
-#define SA_LN(MAXO)                                                                             \
-  layernorm_kernel<MAXO><<<grid, warps * 32, 0, stream>>>(xp, ldx, rows, c, addv, rpg, xo, ldxo, \
-                                                          gamma, beta, eps, yp, ldy)
-  if (noct <= 32) SA_LN(1);
-  else if (noct <= 64) SA_LN(2);
-  else if (noct <= 96) SA_LN(3);
-  else if (noct <= 160) SA_LN(5);
-  else SA_LN(8);
+#define SA_LN(LPR, OPL)                                                                             \
+  layernorm_kernel<LPR, OPL><<<grid, warps * 32, 0, stream>>>(xp, ldx, rows, c, addv, rpg, xo, ldxo, \
+                                                              gamma, beta, eps, yp, ldy)
+#define SA_LN_ROW(LPR)                                                         \
+  switch (opl) {                                                               \
+    case 1: SA_LN(LPR, 1); break;                                              \
+    case 2: SA_LN(LPR, 2); break;                                              \
+    case 3: SA_LN(LPR, 3); break;                                              \
+    case 4: SA_LN(LPR, 4); break;                                              \
+    case 5: SA_LN(LPR, 5); break;                                              \
+    case 6: SA_LN(LPR, 6); break;                                              \
+    case 7: SA_LN(LPR, 7); break;                                              \
+    default: SA_LN(LPR, 8); break;                                             \
+  }
+  if (lpr == 32) { SA_LN_ROW(32) } else if (lpr == 16) { SA_LN_ROW(16) } else { SA_LN_ROW(8) }
+#undef SA_LN_ROW
 #undef SA_LN
   SA_CUDA_CHECK(cudaGetLastError());
   return SA_OK;

@@ -237,7 +237,7 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_ma
 __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
-__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 // exact-GELU x * Phi(x), Phi from erfc by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7 + approx-unit
 // error, far below bf16 resolution), evaluated on the tail side so negative inputs do not cancel.
 // Branch-free, 2 MUFU (rcp, ex2) + ~12 FMA-pipe instructions.
