@@ -24,9 +24,9 @@ def accumulate(units, tiles, weights, F, h, w, step):
     return noise
 
 
-def _worker(rank, world, port, F, tile, overlap, q):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+def _worker(rank, world, store_path, F, tile, overlap, q):
+    # file rendezvous: no TCP port to collide with another test run on the same host
+    dist.init_process_group("gloo", init_method=f"file://{store_path}", rank=rank, world_size=world)
     tiles = sch.tile_indices(F, tile, overlap)
     weights = torch.tensor(sch.tile_weights(tile))
     mine = sch.partition_units(len(tiles), world)[rank]
@@ -42,14 +42,14 @@ def _worker(rank, world, port, F, tile, overlap, q):
 
 
 @pytest.mark.parametrize("F,tile,overlap", [(16, 16, 4), (64, 16, 4), (128, 16, 4)])
-def test_partitioned_blend_equals_single_process(F, tile, overlap):
+def test_partitioned_blend_equals_single_process(F, tile, overlap, tmp_path):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() + F) % 2000
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, F, tile, overlap, q)) for r in range(2)]
+    store = str(tmp_path / "rendezvous")
+    procs = [ctx.Process(target=_worker, args=(r, 2, store, F, tile, overlap, q)) for r in range(2)]
     for p in procs:
         p.start()
-    got = q.get(timeout=120)
+    got = q.get(timeout=300)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
