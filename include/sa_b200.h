@@ -76,6 +76,9 @@ typedef struct sa_gemm_args {
   int32_t out_f32;
   int32_t tile_n;        /* 0 = auto; else one of 32, 64, 128, 160, 256 */
   float out_scale;       /* 0 = 1.0; scales (acc*row_scale + bias + row_bias [geglu]) before residual */
+  int32_t f16_from_col;  /* > 0: output columns >= this (a multiple of 32) are stored as IEEE fp16 (saturating)
+                            instead of bf16 -- the V block of the spatial-attention q|k|v projection, which
+                            sa_attn_spatial consumes in half precision; 0 = all bf16 */
 } sa_gemm_args;
 
 int sa_gemm_tap(const sa_gemm_args* args, void* stream);
@@ -85,8 +88,11 @@ int sa_gemm_pick_tile(int32_t m, int32_t n, int32_t geglu);
 /* ------------------------------------------------------------------------------------------
  * Spatial self-attention, head_dim 64 (tcgen05 flash attention).
  * Replaces xformers.ops.memory_efficient_attention in AnimationAttnProcessor.__call__
- * (unet.py:1893-1905).  qkv: bf16 [frames*S, ld], column blocks q | k | v of width C = heads*64
- * (the fused to_q/to_k/to_v projection output); out: bf16 [frames*S, ldo].
+ * (unet.py:1893-1905).  qkv: 16-bit [frames*S, ld], column blocks q | k | v of width C = heads*64
+ * (the fused to_q/to_k/to_v projection output): q and k are bf16, v is IEEE fp16 (sa_gemm_tap with
+ * f16_from_col = 2C writes it that way) because the probabilities P in (0, 256] are handed to the
+ * tensor core as fp16 (11-bit significand) and kind::f16 needs A and B in the same format;
+ * out: bf16 [frames*S, ldo].
  * ------------------------------------------------------------------------------------------ */
 int sa_attn_spatial(const void* qkv, int32_t ld, int32_t frames, int32_t S, int32_t C,
                     int32_t heads, void* out, int32_t ldo, void* stream);

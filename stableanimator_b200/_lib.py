@@ -42,6 +42,7 @@ class GemmArgs(C.Structure):
         ("out_f32", C.c_int32),
         ("tile_n", C.c_int32),
         ("out_scale", C.c_float),
+        ("f16_from_col", C.c_int32),
     ]
 
 

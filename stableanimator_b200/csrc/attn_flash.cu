@@ -9,89 +9,55 @@
 //
 // CTA = 2 query tiles of 128 rows of one (frame, head); 320 threads:
 //   warps 0-3 / 4-7 : softmax warpgroup of tile A / tile B, one thread per query row (TMEM lane)
-//   warp 8          : TMA producer (Q tiles once; K/V blocks of 128 keys, 3-stage ring shared by
+//   warp 8          : TMA producer (Q tiles once; K/V blocks of 128 keys, 4-stage ring shared by
 //                     both tiles)
 //   warp 9          : MMA issuer + TMEM allocator
 // The two tiles ping-pong on the tensor core: while warpgroup A runs the softmax of S_A(j) the MMA
-// pipe computes S_B(j), P_A V(j-1), ...  Per tile and key block:
-//   S = Q K^T (128x128 fp32 in TMEM) -> softmax thread reads its row twice (max, then exp2), writes
-//   P as bf16 into 128B-swizzled smem (A operand) -> O_part = P V (128x64 fp32 in TMEM, V consumed
-//   MN-major straight from the TMA tile) -> folded into the thread's fp32 O registers with the
-//   running-max correction (O = O * alpha + O_part), so TMEM is never read-modify-written.
-// TMEM columns: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384).
-// smem: Q 2x16K | K 3x16K | V 3x16K | P 2x32K = 192 KB -> one CTA per SM.
+// pipe computes P_B V(j-1), S_B(j), ...  Per tile and key block:
+//   S = Q K^T (128x128 fp32 in TMEM) -> softmax thread: one tcgen05.ld of its row, max, exp2, P as
+//   fp16 back into TMEM -> O += P [V | 1] (TS-form MMA, accumulating in TMEM; column 64 = row sum).
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
 
 namespace sa {
 
-constexpr int FA_BM = 128, FA_BN = 128, FA_D = 64, FA_ST = 3;
-constexpr int FA_TILE = 128 * 128;  // bytes of a [128][64] bf16 tile
-constexpr int FA_SMEM = FA_TILE * (2 + 2 * FA_ST + 4) + 1024 + 256;
+constexpr int FA_BM = 128, FA_BN = 128, FA_D = 64;
+constexpr int FA_TILE = 128 * 128;  // bytes of a [128][64] 16-bit tile
 
-struct FaBars {
+// -----------------------------------------------------------------------------------------------------
+// Single-pass softmax, P and O resident in TMEM:
+//   * the softmax thread reads its whole S row (128 fp32) with ONE tcgen05.ld, takes the row max with
+//     3-input FMNMX, computes exp2 on packed fp32x2 lanes (FFMA2 / FADD2), and writes P
+//     back into TMEM over the first 64 columns of its own S row (tcgen05.st) -- as fp16 pairs: P is in
+//     (0, 256] so half precision holds it with an 11-bit significand (bf16: 8).  kind::f16 needs A and B in
+//     the same format (a mixed fp16 x bf16 descriptor traps), so the V block of qkv is fp16 too: the
+//     q|k|v projection writes it that way (sa_gemm_tap f16_from_col = 2C);
+//   * O = P V is a TS-form tcgen05.mma (A = P from TMEM, B = V MN-major from the TMA tile) that
+//     ACCUMULATES into O in TMEM over all key blocks -- no per-block fold through registers;
+//   * the running max is updated lazily: O / l are rescaled (TMEM read-modify-write by the row's own
+//     thread) only when a block's max exceeds the reference max by more than 2^8, so P <= 256 and the
+//     common case has no correction work at all.  The decision is warp-uniform (any-lane vote).
+//   * the row sum comes out of the same MMA: V is extended by 16 columns of ones (a constant 2 KB smem
+//     atom addressed through the descriptor's leading-dimension offset, N = 80), so O[:, 64] = sum of
+//     the fp16-ROUNDED probabilities -- numerator and denominator use identical weights (a row
+//     dominated by one key reproduces that key's V exactly) and the softmax threads carry no sum.
+// TMEM columns: S_A/P_A [0,128) S_B/P_B [128,256) O_A [256,336) O_B [336,416).
+// smem: Q 2x16K | K 4x16K | V 4x16K | ones 2K = 162 KB + barriers -> one CTA per SM.
+// -----------------------------------------------------------------------------------------------------
+constexpr int FA3_ST = 4;
+constexpr int FA3_ON = 80;      // P V output columns: 64 head dims + 16 ones columns (row sum)
+constexpr int FA3_SMEM = FA_TILE * (2 + 2 * FA3_ST) + 2048 + 1024 + 256;
+constexpr float FA3_TAU = 8.0f;  // lazy-rescale threshold (log2 units)
+
+struct Fa3Bars {
   uint64_t q_full;
-  uint64_t k_full[FA_ST], v_full[FA_ST], kv_empty[FA_ST];
+  uint64_t k_full[FA3_ST], v_full[FA3_ST], kv_empty[FA3_ST];
   uint64_t s_full[2], o_full[2], p_full[2];
   uint32_t tmem_slot;
 };
-
-// one key block of one query row: MASKED handles the last, partial block (keys >= kv_left are -inf)
-template <bool MASKED>
-__device__ __forceinline__ void fa_softmax_block(uint32_t s_addr, uint32_t o_addr, bool fold, uint64_t* o_full_bar,
-                                                 uint32_t o_phase, int kv_left, float sl2, float& m, float& l,
-                                                 float& alpha_prev, float (&o)[FA_D], uint8_t* prow, int sw) {
-  // pass 1: row max
-  float mx = -INFINITY;
-#pragma unroll
-  for (int c = 0; c < FA_BN; c += 64) {
-    uint32_t u[64];
-    tmem_ld_32x64(s_addr + c, u);
-    tmem_ld_wait();
-#pragma unroll
-    for (int t = 0; t < 64; ++t) {
-      if (!MASKED || c + t < kv_left) mx = fmaxf(mx, __uint_as_float(u[t]));
-    }
-  }
-  const float m_new = fmaxf(m, mx * sl2);
-  const float alpha = ex2_approx(m - m_new);  // 0 on the first block (m = -inf)
-  // fold the previous block's P V into the O registers (PV_{j-1} must have completed)
-  if (fold) {
-    mbar_wait(o_full_bar, o_phase);
-    tc_fence_after();
-    uint32_t u[64];
-    tmem_ld_32x64(o_addr, u);
-    tmem_ld_wait();
-#pragma unroll
-    for (int t = 0; t < FA_D; ++t) o[t] = o[t] * alpha_prev + __uint_as_float(u[t]);
-  }
-  alpha_prev = alpha;
-  l *= alpha;
-  m = m_new;
-  // pass 2: P = exp2(s * sl2 - m) -> bf16 -> swizzled smem (A operand of the PV MMA)
-#pragma unroll
-  for (int c = 0; c < FA_BN; c += 64) {
-    uint32_t u[64];
-    tmem_ld_32x64(s_addr + c, u);
-    tmem_ld_wait();
-    uint8_t* base = prow + (c >> 6) * FA_TILE;
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      float p[8];
-#pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        const float e = ex2_approx(fmaf(__uint_as_float(u[8 * g + t]), sl2, -m_new));
-        p[t] = (!MASKED || c + 8 * g + t < kv_left) ? e : 0.f;
-        l += p[t];
-      }
-      *reinterpret_cast<uint4*>(base + ((g ^ sw) << 4)) =
-          make_uint4(pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]), pack_bf16x2(p[4], p[5]),
-                     pack_bf16x2(p[6], p[7]));
-    }
-  }
-}
 
 __global__ void __launch_bounds__(320, 1)
 attn_flash_kernel(const __grid_constant__ CUtensorMap tm, int S, int C, __nv_bfloat16* __restrict__ out,
@@ -99,10 +65,10 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm, int S, int C, __nv_bfl
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;                          // 2 tiles
-  uint8_t* sK = smem + 2 * FA_TILE;            // FA_ST stages
-  uint8_t* sV = sK + FA_ST * FA_TILE;          // FA_ST stages
-  uint8_t* sP = sV + FA_ST * FA_TILE;          // 2 tiles x 2 halves of 64 keys
-  FaBars* bars = reinterpret_cast<FaBars*>(sP + 4 * FA_TILE);
+  uint8_t* sK = smem + 2 * FA_TILE;            // FA3_ST stages
+  uint8_t* sV = sK + FA3_ST * FA_TILE;         // FA3_ST stages
+  uint8_t* sOnes = sV + FA3_ST * FA_TILE;      // [16 keys][64] bf16 ones: second N-atom of every V operand
+  Fa3Bars* bars = reinterpret_cast<Fa3Bars*>(sOnes + 2048);
 
   const int warp = threadIdx.x >> 5;
   const int q0 = blockIdx.x * 2 * FA_BM;
@@ -114,7 +80,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm, int S, int C, __nv_bfl
   if (warp == 8 && elect_one()) {
     tma_prefetch_desc(&tm);
     mbar_init(&bars->q_full, 1);
-    for (int i = 0; i < FA_ST; ++i) {
+    for (int i = 0; i < FA3_ST; ++i) {
       mbar_init(&bars->k_full[i], 1);
       mbar_init(&bars->v_full[i], 1);
       mbar_init(&bars->kv_empty[i], 1);
@@ -127,6 +93,8 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm, int S, int C, __nv_bfl
     fence_barrier_init();
   }
   if (warp == 9) tmem_alloc<512>(&bars->tmem_slot);
+  if (threadIdx.x < 128) reinterpret_cast<uint4*>(sOnes)[threadIdx.x] = make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u)  /* fp16 1.0 */;
+  fence_proxy_async();  // the ones atom is read by the tensor core (async proxy)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -139,8 +107,8 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm, int S, int C, __nv_bfl
       for (int t = 0; t < ntiles; ++t)
         tma_load_3d(sQ + t * FA_TILE, &tm, &bars->q_full, head * FA_D, q0 + t * FA_BM, frame);
       for (int j = 0; j < nblk; ++j) {
-        const int st = j % FA_ST;
-        mbar_wait(&bars->kv_empty[st], ((j / FA_ST) & 1) ^ 1);
+        const int st = j % FA3_ST;
+        mbar_wait(&bars->kv_empty[st], ((j / FA3_ST) & 1) ^ 1);
         mbar_expect_tx(&bars->k_full[st], FA_TILE);
         tma_load_3d(sK + st * FA_TILE, &tm, &bars->k_full[st], C + head * FA_D, j * FA_BN, frame);
         mbar_expect_tx(&bars->v_full[st], FA_TILE);
@@ -152,10 +120,10 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm, int S, int C, __nv_bfl
     // ------------------------------------------------------------ MMA issuer
     if (elect_one()) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, FA_BN, 0, 0);  // S = Q K^T (both K-major)
-      constexpr uint32_t idesc_o = umma_idesc_bf16(128, FA_D, 0, 1);   // O = P V   (V is MN-major)
+      constexpr uint32_t idesc_o = umma_idesc_f16(128, FA3_ON, 0, 1);  // O += P [V | 1], fp16 x fp16 (V MN-major)
       auto issue_s = [&](int t, int j) {
         const uint64_t dq = umma_desc_sw128(smem_u32(sQ + t * FA_TILE));
-        const uint64_t dk = umma_desc_sw128(smem_u32(sK + (j % FA_ST) * FA_TILE));
+        const uint64_t dk = umma_desc_sw128(smem_u32(sK + (j % FA3_ST) * FA_TILE));
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_f16(tmem_base + t * 128, dq + 2 * k, dk + 2 * k, idesc_s, k != 0 ? 1u : 0u);
@@ -166,24 +134,26 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm, int S, int C, __nv_bfl
       tc_fence_after();
       for (int t = 0; t < ntiles; ++t) issue_s(t, 0);
       for (int j = 0; j < nblk; ++j) {
-        const int st = j % FA_ST;
+        const int st = j % FA3_ST;
         for (int t = 0; t < ntiles; ++t) {
-          mbar_wait(&bars->p_full[t], j & 1);  // P_t(j) in smem, S_t(j) and O_t(j-1) drained
-          if (t == 0) mbar_wait(&bars->v_full[st], (j / FA_ST) & 1);
+          mbar_wait(&bars->p_full[t], j & 1);  // P_t(j) in TMEM, O_t corrected if it had to be
+          if (t == 0) mbar_wait(&bars->v_full[st], (j / FA3_ST) & 1);
           tc_fence_after();
+          const uint32_t p_tmem = tmem_base + t * 128;
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk) {
-            const uint64_t dp = umma_desc_sw128(smem_u32(sP + (2 * t + (kk >> 2)) * FA_TILE)) + 2 * (kk & 3);
-            const uint64_t dv = umma_desc_sw128(smem_u32(sV + st * FA_TILE + kk * 2048));
-            umma_f16(tmem_base + 256 + t * 64, dp, dv, idesc_o, kk != 0 ? 1u : 0u);
+            // B = 16 keys x 80 columns: N-atom 0 = the V tile rows, N-atom 1 (leading-dimension offset) = ones
+            const uint32_t va = smem_u32(sV + st * FA_TILE + kk * 2048);
+            const uint64_t dv = umma_desc_sw128_lbo(va, smem_u32(sOnes) - va);
+            umma_f16_ts(tmem_base + 256 + t * FA3_ON, p_tmem + kk * 8, dv, idesc_o, (j | kk) != 0 ? 1u : 0u);
           }
           umma_commit(&bars->o_full[t]);
           if (j + 1 < nblk) {
             if (t == 0) {
-              mbar_wait(&bars->k_full[(j + 1) % FA_ST], ((j + 1) / FA_ST) & 1);
+              mbar_wait(&bars->k_full[(j + 1) % FA3_ST], ((j + 1) / FA3_ST) & 1);
               tc_fence_after();
             }
-            issue_s(t, j + 1);
+            issue_s(t, j + 1);  // in-order after P V(j): may overwrite the S/P columns
           }
         }
         umma_commit(&bars->kv_empty[st]);  // K_j (read by S(j)) and V_j (read by PV(j)) are free
@@ -197,49 +167,93 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm, int S, int C, __nv_bfl
     if (t < ntiles) {
       const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
       const uint32_t s_addr = lane_addr + t * 128;
-      const uint32_t o_addr = lane_addr + 256 + t * 64;
+      const uint32_t o_addr = lane_addr + 256 + t * FA3_ON;
       const float sl2 = 0.125f * 1.4426950408889634f;  // attn.scale * log2(e)
-      float o[FA_D];
-#pragma unroll
-      for (int d = 0; d < FA_D; ++d) o[d] = 0.f;
-      float m = -INFINITY, l = 0.f, alpha_prev = 1.f;
-      uint8_t* prow = sP + 2 * t * FA_TILE + r * 128;
-      const int sw = r & 7;
+      const uint64_t sl22 = pack2(sl2, sl2);
+      float m_ref = -INFINITY;                 // reference max the exponentials are taken against
 
       for (int j = 0; j < nblk; ++j) {
         const int kv_left = S - j * FA_BN;
         mbar_wait(&bars->s_full[t], j & 1);
         tc_fence_after();
-        if (kv_left >= FA_BN)
-          fa_softmax_block<false>(s_addr, o_addr, j >= 1, &bars->o_full[t], (j - 1) & 1, kv_left, sl2, m, l,
-                                  alpha_prev, o, prow, sw);
-        else
-          fa_softmax_block<true>(s_addr, o_addr, j >= 1, &bars->o_full[t], (j - 1) & 1, kv_left, sl2, m, l,
-                                 alpha_prev, o, prow, sw);
-        fence_proxy_async();  // P visible to the tensor core's async-proxy reads
-        tc_fence_before();    // our TMEM reads of S_t(j) / O_t(j-1) precede the MMAs that overwrite them
+        uint32_t s[128];
+        tmem_ld_32x128(s_addr, s);
+        tmem_ld_wait();
+        if (kv_left < FA_BN) {
+#pragma unroll
+          for (int c = 0; c < FA_BN; ++c)
+            if (c >= kv_left) s[c] = 0xff800000u;  // -inf
+        }
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int c = 0; c < FA_BN; c += 8) {
+          mx[0] = max3(mx[0], __uint_as_float(s[c]), __uint_as_float(s[c + 1]));
+          mx[1] = max3(mx[1], __uint_as_float(s[c + 2]), __uint_as_float(s[c + 3]));
+          mx[2] = max3(mx[2], __uint_as_float(s[c + 4]), __uint_as_float(s[c + 5]));
+          mx[3] = max3(mx[3], __uint_as_float(s[c + 6]), __uint_as_float(s[c + 7]));
+        }
+        const float bm = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * sl2;
+        const bool need = bm > m_ref + FA3_TAU;   // always true on the first block (m_ref = -inf)
+        if (__any_sync(0xffffffffu, need)) {
+          const float m_new = need ? bm : m_ref;
+          const float alpha = ex2_approx(m_ref - m_new);  // 1 for lanes that keep their max, 0 on block 0
+          m_ref = m_new;
+          const uint64_t a2 = pack2(alpha, alpha);
+          if (j > 0) {
+            // rescale O in TMEM: P V(j-1) must have completed; P V(j) is gated by our p_full arrival
+            mbar_wait(&bars->o_full[t], (j - 1) & 1);
+            tc_fence_after();
+            uint32_t o[64];
+            tmem_ld_32x64(o_addr, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int d = 0; d < FA_D; d += 2) {
+              const float2 f = unpack2(mul2(pack2u(o[d], o[d + 1]), a2));
+              o[d] = __float_as_uint(f.x);
+              o[d + 1] = __float_as_uint(f.y);
+            }
+            tmem_st_32x64(o_addr, o);
+            uint32_t ls[16];  // the row-sum columns
+            tmem_ld_32x16(o_addr + 64, ls);
+            tmem_ld_wait();
+#pragma unroll
+            for (int d = 0; d < 16; ++d) ls[d] = __float_as_uint(__uint_as_float(ls[d]) * alpha);
+            tmem_st_32x16(o_addr + 64, ls);
+          }
+        }
+        const uint64_t nm2 = pack2(-m_ref, -m_ref);
+        uint32_t pw[64];
+#pragma unroll
+        for (int c = 0; c < FA_BN; c += 4) {
+          const float2 x0 = unpack2(fma2(pack2u(s[c], s[c + 1]), sl22, nm2));
+          const float2 x1 = unpack2(fma2(pack2u(s[c + 2], s[c + 3]), sl22, nm2));
+          const float e0 = ex2_approx(x0.x), e1 = ex2_approx(x0.y);
+          const float e2 = ex2_approx(x1.x), e3 = ex2_approx(x1.y);
+          pw[c >> 1] = pack_f16x2(e0, e1);        // P <= 2^8 (lazy max): fp16 keeps 11 significant bits
+          pw[(c >> 1) + 1] = pack_f16x2(e2, e3);
+        }
+        tmem_st_32x64(s_addr, pw);   // P over the first 64 columns of this row's S
+        tmem_st_wait();              // P (and a rescaled O) are in TMEM
+        tc_fence_before();
         mbar_arrive(&bars->p_full[t]);
       }
-      // last block's P V
+      // all P V accumulated
       mbar_wait(&bars->o_full[t], (nblk - 1) & 1);
       tc_fence_after();
-      {
-        uint32_t u[64];
-        tmem_ld_32x64(o_addr, u);
-        tmem_ld_wait();
-#pragma unroll
-        for (int d = 0; d < FA_D; ++d) o[d] = o[d] * alpha_prev + __uint_as_float(u[d]);
-      }
+      uint32_t o[64], ls[16];
+      tmem_ld_32x64(o_addr, o);
+      tmem_ld_32x16(o_addr + 64, ls);
+      tmem_ld_wait();
       const int qrow = q0 + t * FA_BM + r;
       if (qrow < S) {
-        const float inv = 1.0f / l;
+        const float inv = 1.0f / __uint_as_float(ls[0]);
         uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<long long>(frame) * S + qrow) * ldo + head * FA_D);
 #pragma unroll
         for (int g = 0; g < 8; ++g)
-          dst[g] = make_uint4(pack_bf16x2(o[8 * g] * inv, o[8 * g + 1] * inv),
-                              pack_bf16x2(o[8 * g + 2] * inv, o[8 * g + 3] * inv),
-                              pack_bf16x2(o[8 * g + 4] * inv, o[8 * g + 5] * inv),
-                              pack_bf16x2(o[8 * g + 6] * inv, o[8 * g + 7] * inv));
+          dst[g] = make_uint4(pack_bf16x2(__uint_as_float(o[8 * g]) * inv, __uint_as_float(o[8 * g + 1]) * inv),
+                              pack_bf16x2(__uint_as_float(o[8 * g + 2]) * inv, __uint_as_float(o[8 * g + 3]) * inv),
+                              pack_bf16x2(__uint_as_float(o[8 * g + 4]) * inv, __uint_as_float(o[8 * g + 5]) * inv),
+                              pack_bf16x2(__uint_as_float(o[8 * g + 6]) * inv, __uint_as_float(o[8 * g + 7]) * inv));
       }
     }
   }
@@ -268,11 +282,11 @@ extern "C" int sa_attn_spatial(const void* qkv, int32_t ld, int32_t frames, int3
   if (!tm) return SA_ERR_TMA;
   static bool configured = false;
   if (!configured) {
-    SA_CUDA_CHECK(cudaFuncSetAttribute(attn_flash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+    SA_CUDA_CHECK(cudaFuncSetAttribute(attn_flash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA3_SMEM));
     configured = true;
   }
   dim3 grid((S + 2 * FA_BM - 1) / (2 * FA_BM), heads, frames);
-  attn_flash_kernel<<<grid, 320, FA_SMEM, stream>>>(*tm, S, C, static_cast<__nv_bfloat16*>(out), ldo);
+  attn_flash_kernel<<<grid, 320, FA3_SMEM, stream>>>(*tm, S, C, static_cast<__nv_bfloat16*>(out), ldo);
   SA_CUDA_CHECK(cudaGetLastError());
   return SA_OK;
 }

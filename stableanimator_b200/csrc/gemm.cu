@@ -46,6 +46,7 @@ struct GemmKParams {
   // persistent kernel (v2) only
   int n_tiles_n, total_tiles;
   float out_scale;  // v = (acc*rs + bias + row_bias [geglu]) * out_scale + residual ...
+  int f16_from;     // > 0: output columns >= f16_from are stored as fp16 instead of bf16
   FastDiv fd_ntn, fd_t1, fd_t2, fd_rpg;
 };
 
@@ -502,32 +503,34 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
       }
       for (int c = half; c < CPT; c += CSTRIDE, ++gc) {
         const int mc = mma_col(c);
-        float v[32], gt[GEGLU ? 32 : 1];
+        // all epilogue math runs on packed fp32x2 lanes (FFMA2): half the issue slots of scalar code
+        uint64_t v2[16], g2[GEGLU ? 16 : 1];
         tmem_ld_wait();
+        const uint64_t rs2 = pack2(rs, rs);
         if (p.bias) {
           const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + mc);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 b = __ldg(b4 + j);
-            v[4 * j + 0] = fmaf(__uint_as_float(u[4 * j + 0]), rs, b.x);
-            v[4 * j + 1] = fmaf(__uint_as_float(u[4 * j + 1]), rs, b.y);
-            v[4 * j + 2] = fmaf(__uint_as_float(u[4 * j + 2]), rs, b.z);
-            v[4 * j + 3] = fmaf(__uint_as_float(u[4 * j + 3]), rs, b.w);
+            v2[2 * j] = fma2(pack2u(u[4 * j], u[4 * j + 1]), rs2, pack2(b.x, b.y));
+            v2[2 * j + 1] = fma2(pack2u(u[4 * j + 2], u[4 * j + 3]), rs2, pack2(b.z, b.w));
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(u[j]) * rs;
+          for (int j = 0; j < 16; ++j) v2[j] = mul2(pack2u(u[2 * j], u[2 * j + 1]), rs2);
         }
         if constexpr (GEGLU) {
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + mc + 64);
+          if (p.bias) {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + mc + 64);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.bias) b = __ldg(b4 + j);
-            gt[4 * j + 0] = fmaf(__uint_as_float(g[4 * j + 0]), rs, b.x);
-            gt[4 * j + 1] = fmaf(__uint_as_float(g[4 * j + 1]), rs, b.y);
-            gt[4 * j + 2] = fmaf(__uint_as_float(g[4 * j + 2]), rs, b.z);
-            gt[4 * j + 3] = fmaf(__uint_as_float(g[4 * j + 3]), rs, b.w);
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = __ldg(b4 + j);
+              g2[2 * j] = fma2(pack2u(g[4 * j], g[4 * j + 1]), rs2, pack2(b.x, b.y));
+              g2[2 * j + 1] = fma2(pack2u(g[4 * j + 2], g[4 * j + 3]), rs2, pack2(b.z, b.w));
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) g2[j] = mul2(pack2u(g[2 * j], g[2 * j + 1]), rs2);
           }
         }
         if (c + CSTRIDE < CPT) {  // prefetch the next chunk's accumulator columns
@@ -539,7 +542,7 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
         }
         if constexpr (GEGLU) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] *= gelu_fast(gt[j]);
+          for (int j = 0; j < 16; ++j) v2[j] = mul2(v2[j], gelu2(g2[j]));
         }
         const int ncol = nout0 + c * EPI_CHUNK;
         if (p.row_bias) {
@@ -547,15 +550,14 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 b = __ldg(b4 + j);
-            v[4 * j + 0] += b.x;
-            v[4 * j + 1] += b.y;
-            v[4 * j + 2] += b.z;
-            v[4 * j + 3] += b.w;
+            v2[2 * j] = add2(v2[2 * j], pack2(b.x, b.y));
+            v2[2 * j + 1] = add2(v2[2 * j + 1], pack2(b.z, b.w));
           }
         }
         if (gs != 1.0f) {
+          const uint64_t gs2 = pack2(gs, gs);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] *= gs;
+          for (int j = 0; j < 16; ++j) v2[j] = mul2(v2[j], gs2);
         }
         // staging slot of this chunk: holds the residual sub-box (if any) and is free for our output
         const int slot = gc % EPI_RO_SLOTS;
@@ -565,36 +567,39 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint4 q = *reinterpret_cast<const uint4*>(ro + ((j ^ sw) << 4));
-            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const float2 f = unpack_bf16x2(w[t]);
-              v[8 * j + 2 * t] += f.x;
-              v[8 * j + 2 * t + 1] += f.y;
-            }
+            v2[4 * j + 0] = add2(v2[4 * j + 0], bf16x2_to_f32x2(q.x));
+            v2[4 * j + 1] = add2(v2[4 * j + 1], bf16x2_to_f32x2(q.y));
+            v2[4 * j + 2] = add2(v2[4 * j + 2], bf16x2_to_f32x2(q.z));
+            v2[4 * j + 3] = add2(v2[4 * j + 3], bf16x2_to_f32x2(q.w));
           }
         }
         if (p.blend_x) {
           const int xs = gc % EPI_X_SLOTS;
           mbar_wait(&x_ready[xs], (gc / EPI_X_SLOTS) & 1);
           const uint8_t* xr = my_x + xs * EPI_TILE_BYTES;
+          const uint64_t al2 = pack2(alpha, alpha), be2 = pack2(beta, beta);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint4 q = *reinterpret_cast<const uint4*>(xr + ((j ^ sw) << 4));
-            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const float2 f = unpack_bf16x2(w[t]);
-              v[8 * j + 2 * t] = alpha * f.x + beta * v[8 * j + 2 * t];
-              v[8 * j + 2 * t + 1] = alpha * f.y + beta * v[8 * j + 2 * t + 1];
-            }
+            v2[4 * j + 0] = fma2(al2, bf16x2_to_f32x2(q.x), mul2(be2, v2[4 * j + 0]));
+            v2[4 * j + 1] = fma2(al2, bf16x2_to_f32x2(q.y), mul2(be2, v2[4 * j + 1]));
+            v2[4 * j + 2] = fma2(al2, bf16x2_to_f32x2(q.z), mul2(be2, v2[4 * j + 2]));
+            v2[4 * j + 3] = fma2(al2, bf16x2_to_f32x2(q.w), mul2(be2, v2[4 * j + 3]));
           }
         }
+        if (p.f16_from > 0 && ncol >= p.f16_from) {  // chunk-uniform: half-precision block (attention V)
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          *reinterpret_cast<uint4*>(ro + ((j ^ sw) << 4)) =
-              make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                         pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(ro + ((j ^ sw) << 4)) =
+                make_uint4(pack_f16x2_sat_f2(v2[4 * j]), pack_f16x2_sat_f2(v2[4 * j + 1]),
+                           pack_f16x2_sat_f2(v2[4 * j + 2]), pack_f16x2_sat_f2(v2[4 * j + 3]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(ro + ((j ^ sw) << 4)) =
+                make_uint4(pack_bf16x2_f2(v2[4 * j]), pack_bf16x2_f2(v2[4 * j + 1]), pack_bf16x2_f2(v2[4 * j + 2]),
+                           pack_bf16x2_f2(v2[4 * j + 3]));
+        }
         fence_proxy_async();  // staging rows visible to the TMA store
         __syncwarp();         // all 32 rows written (and this warp's reads of the X slot done)
         if (lane == 0) {
@@ -793,6 +798,8 @@ extern "C" int sa_gemm_tap(const sa_gemm_args* a, void* stream_) {
 
   const int mt = static_cast<int>(m_tiles);
   p.out_scale = a->out_scale != 0.0f ? a->out_scale : 1.0f;
+  p.f16_from = a->f16_from_col;
+  if (a->f16_from_col < 0 || a->f16_from_col % 32) return fail(SA_ERR_INVALID, "sa_gemm_tap: f16_from_col must be a multiple of 32");
   static const bool force_v1 = getenv("SA_GEMM_V1") != nullptr;
   const bool v2_ok = !force_v1 && !a->out_f32 && (a->n % bn == 0) && bn >= 64;
   if (v2_ok) {
@@ -831,6 +838,8 @@ extern "C" int sa_gemm_tap(const sa_gemm_args* a, void* stream_) {
     }
 #undef SA_LP
   }
+  if (a->f16_from_col > 0)
+    return fail(SA_ERR_INVALID, "sa_gemm_tap: f16_from_col needs the persistent bf16 path (n %% tile == 0, tile >= 64)");
   switch (bn) {
     case 32: return launch<32, 4>(tma[0], tma[1], tmb, p, mt, stream);
     case 64: return launch<64, 4>(tma[0], tma[1], tmb, p, mt, stream);

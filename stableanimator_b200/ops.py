@@ -67,6 +67,7 @@ def gemm_tap(
     out_f32: bool = False,
     tile_n: int = 0,
     out_scale: float = 1.0,
+    f16_from_col: int = 0,
 ) -> torch.Tensor:
     """``out = epilogue(sum_taps A(shifted) @ W^T)`` -- see ``sa_gemm_tap`` in include/sa_b200.h.
 
@@ -127,6 +128,7 @@ def gemm_tap(
     args.out_f32 = int(out.dtype == torch.float32)
     args.tile_n = tile_n
     args.out_scale = float(out_scale)
+    args.f16_from_col = int(f16_from_col)
     check(lib().sa_gemm_tap(C.byref(args), _stream()), "sa_gemm_tap")
     return out
 
@@ -144,7 +146,9 @@ def interleave_geglu(w: torch.Tensor, b: Optional[torch.Tensor]):
 # ----------------------------------------------------------------------------- attention
 def attn_spatial(qkv: torch.Tensor, frames: int, s: int, heads: int,
                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """softmax(q k^T / 8) v per (frame, head); qkv bf16 [frames*s, 3C] -> bf16 [frames*s, C]."""
+    """softmax(q k^T / 8) v per (frame, head); qkv 16-bit [frames*s, 3C] -> bf16 [frames*s, C].
+    q | k are bf16, the v block holds IEEE fp16 bit patterns (``gemm_tap(..., f16_from_col=2C)`` or
+    :func:`v_block_to_f16_`)."""
     _chk_bf16(qkv, "qkv")
     c = heads * 64
     if out is None:
@@ -152,6 +156,13 @@ def attn_spatial(qkv: torch.Tensor, frames: int, s: int, heads: int,
     check(lib().sa_attn_spatial(qkv.data_ptr(), qkv.stride(-2), frames, s, c, heads, out.data_ptr(),
                                 out.stride(-2), _stream()), "sa_attn_spatial")
     return out
+
+
+def v_block_to_f16_(qkv: torch.Tensor, c: int) -> torch.Tensor:
+    """In place: re-encode the v block (columns >= 2C) of an all-bf16 q|k|v tensor as fp16 bit patterns."""
+    v = qkv[:, 2 * c:3 * c]
+    v.copy_(v.float().clamp(-65504.0, 65504.0).half().view(torch.bfloat16))
+    return qkv
 
 
 def attn_temporal(qkv: torch.Tensor, b: int, f: int, s: int, heads: int,

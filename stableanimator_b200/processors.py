@@ -66,7 +66,7 @@ class AnimationAttnProcessor(nn.Module):
             raise NotImplementedError("AnimationAttnProcessor is only used for self-attention (unet.py:535-538)")
         bsz, s, c = hidden_states.shape
         p = _pack(attn, None, hidden_states.device)
-        qkv = ops.gemm_tap(_tokens(hidden_states), p["qkv"])
+        qkv = ops.gemm_tap(_tokens(hidden_states), p["qkv"], f16_from_col=2 * c)  # v block in fp16
         o = ops.attn_spatial(qkv, bsz, s, attn.heads)
         out = ops.gemm_tap(o, p["o"], bias=p["ob"])
         return out.reshape(bsz, s, c).to(hidden_states.dtype)

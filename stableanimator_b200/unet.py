@@ -248,7 +248,7 @@ class UNetB200:
         y = ops.gemm_tap(n, w[f"{t.name}.proj_in.w"], bias=w[f"{t.name}.proj_in.b"])
         # --- BasicTransformerBlock (unet.py:525-556)
         a = ops.layernorm(y, w[f"{b}.norm1.g"], w[f"{b}.norm1.b"])
-        qkv = ops.gemm_tap(a, w[f"{b}.attn1.qkv"])
+        qkv = ops.gemm_tap(a, w[f"{b}.attn1.qkv"], f16_from_col=2 * c)  # v block in fp16 for the P V MMA
         o = ops.attn_spatial(qkv, BF, S, heads)
         y1 = ops.gemm_tap(o, w[f"{b}.attn1.to_out.0.w"], bias=w[f"{b}.attn1.to_out.0.b"], residual=y)
         a = ops.layernorm(y1, w[f"{b}.norm2.g"], w[f"{b}.norm2.b"])

@@ -159,3 +159,23 @@ def test_geglu_matches_exact_erf_gelu_on_wide_range():
     proj = a.float() @ w.float().t() + b
     val, gate = proj.chunk(2, dim=-1)
     assert_close(out, val * F.gelu(gate))
+
+
+def test_fp16_column_block():
+    """f16_from_col: the q|k|v projection stores its V block as IEEE fp16 (saturating) for the fp16 P V
+    MMA of sa_attn_spatial; the other columns stay bf16."""
+    from stableanimator_b200 import ops
+    m, k, c = 1000, 320, 320
+    a, w = rnd(m, k, seed=11), rnd(3 * c, k, scale=k ** -0.5, seed=12)
+    w[2 * c + 5] *= 1e6  # one V column overflows fp16: must saturate to +-65504, not inf
+    out = ops.gemm_tap(a, w, f16_from_col=2 * c)
+    ref = a.float() @ w.float().t()
+    assert out.dtype == torch.bfloat16
+    assert_close(out[:, :2 * c], ref[:, :2 * c], what="q|k (bf16)")
+    v = out[:, 2 * c:].contiguous().view(torch.float16).float()
+    assert torch.isfinite(v).all()
+    vref = ref[:, 2 * c:].clamp(-65504.0, 65504.0)
+    # fp16 output: half-ulp is 2^-11 relative; 2^-10 leaves room for the fp32 accumulation-order difference
+    assert ((v - vref).abs() <= 2.0 ** -10 * vref.abs() + 1e-5).all()
+    with pytest.raises(Exception):
+        ops.gemm_tap(a, w, f16_from_col=2 * c + 8)

@@ -24,8 +24,9 @@ def test_attn_spatial(frames, s, heads):
     from stableanimator_b200 import ops
     c = heads * 64
     qkv = rnd(frames * s, 3 * c, seed=1)
-    out = ops.attn_spatial(qkv, frames, s, heads)
     q, k, v = (O.heads_split(t.float().reshape(frames, s, c), heads) for t in qkv.chunk(3, dim=-1))
+    ops.v_block_to_f16_(qkv, c)  # the kernel takes v as fp16 bit patterns (exact re-encoding of these values)
+    out = ops.attn_spatial(qkv, frames, s, heads)
     ref = O.heads_merge(O.sdpa(q, k, v), heads).reshape(frames * s, c)
     assert_close(out, ref, what="attn_spatial")
 
