@@ -15,7 +15,7 @@
 // The two tiles ping-pong on the tensor core: while warpgroup A runs the softmax of S_A(j) the MMA
 // pipe computes P_B V(j-1), S_B(j), ...  Per tile and key block:
 //   S = Q K^T (128x128 fp32 in TMEM) -> softmax thread: one tcgen05.ld of its row, max, exp2, P as
-//   fp16 back into TMEM -> O += P [V | 1] (TS-form MMA, accumulating in TMEM; column 64 = row sum).
+//   fp16 back into TMEM -> O += P V (TS-form MMA, accumulating in TMEM).
 #include <math.h>
 #include <stdlib.h>
 
@@ -28,34 +28,37 @@ constexpr int FA_BM = 128, FA_BN = 128, FA_D = 64;
 constexpr int FA_TILE = 128 * 128;  // bytes of a [128][64] 16-bit tile
 
 // -----------------------------------------------------------------------------------------------------
-// Single-pass softmax, P and O resident in TMEM:
-//   * the softmax thread reads its whole S row (128 fp32) with ONE tcgen05.ld, takes the row max with
-//     3-input FMNMX, computes exp2 on packed fp32x2 lanes (FFMA2 / FADD2), and writes P
-//     back into TMEM over the first 64 columns of its own S row (tcgen05.st) -- as fp16 pairs: P is in
-//     (0, 256] so half precision holds it with an 11-bit significand (bf16: 8).  kind::f16 needs A and B in
-//     the same format (a mixed fp16 x bf16 descriptor traps), so the V block of qkv is fp16 too: the
-//     q|k|v projection writes it that way (sa_gemm_tap f16_from_col = 2C);
-//   * O = P V is a TS-form tcgen05.mma (A = P from TMEM, B = V MN-major from the TMA tile) that
+// Single-pass softmax, S / P / O resident in TMEM:
+//   * the softmax thread reads its whole S row (128 fp32) with ONE tcgen05.ld and immediately hands the
+//     S columns back (s_free), so the tensor core computes S(j+1) WHILE the row's softmax of block j
+//     runs -- the softmax warps never wait for Q K^T in steady state;
+//   * row max with 3-input FMNMX, exp2 on packed fp32x2 lanes (FFMA2 / FADD2); P goes back into TMEM
+//     (its own 64 columns per tile, tcgen05.st) as fp16 pairs: P is in (0, 256], so half precision holds
+//     it with an 11-bit significand (bf16: 8).  kind::f16 needs A and B in the same format (a mixed
+//     fp16 x bf16 descriptor traps), so the V block of qkv is fp16 too: the q|k|v projection writes it
+//     that way (sa_gemm_tap f16_from_col = 2C);
+//   * O += P V is a TS-form tcgen05.mma (A = P from TMEM, B = V MN-major from the TMA tile) that
 //     ACCUMULATES into O in TMEM over all key blocks -- no per-block fold through registers;
-//   * the running max is updated lazily: O / l are rescaled (TMEM read-modify-write by the row's own
+//   * the running max is updated lazily: O and l are rescaled (TMEM read-modify-write by the row's own
 //     thread) only when a block's max exceeds the reference max by more than 2^8, so P <= 256 and the
-//     common case has no correction work at all.  The decision is warp-uniform (any-lane vote).
-//   * the row sum comes out of the same MMA: V is extended by 16 columns of ones (a constant 2 KB smem
-//     atom addressed through the descriptor's leading-dimension offset, N = 80), so O[:, 64] = sum of
-//     the fp16-ROUNDED probabilities -- numerator and denominator use identical weights (a row
-//     dominated by one key reproduces that key's V exactly) and the softmax threads carry no sum.
-// TMEM columns: S_A/P_A [0,128) S_B/P_B [128,256) O_A [256,336) O_B [336,416).
-// smem: Q 2x16K | K 4x16K | V 4x16K | ones 2K = 162 KB + barriers -> one CTA per SM.
+//     common case has no correction work at all.  The decision is warp-uniform (any-lane vote);
+//   * the exp2 phase saturates a sub-partition's MUFU pipe on its own (1024 cycles per warp and block;
+//     measured: tools/probes/exp_loop.cu).  Left alone, the two softmax warps of a sub-partition (tile A,
+//     tile B) fall into lock step -- both in the exp phase at half rate, then both in the MUFU-free phase
+//     (tcgen05.ld, max, barriers) with the pipe idle -- so they take turns through a pair of mbarriers:
+//     A(j), B(j), A(j+1), ... puts one warp's MUFU-free work under the other's exp phase.
+// TMEM columns (all 512): S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384) P_A [384,448) P_B [448,512).
+// smem: Q 2x16K | K 4x16K | V 4x16K = 160 KB + barriers -> one CTA per SM.
 // -----------------------------------------------------------------------------------------------------
 constexpr int FA3_ST = 4;
-constexpr int FA3_ON = 80;      // P V output columns: 64 head dims + 16 ones columns (row sum)
-constexpr int FA3_SMEM = FA_TILE * (2 + 2 * FA3_ST) + 2048 + 1024 + 256;
+constexpr int FA3_SMEM = FA_TILE * (2 + 2 * FA3_ST) + 1024 + 256;
 constexpr float FA3_TAU = 8.0f;  // lazy-rescale threshold (log2 units)
 
 struct Fa3Bars {
   uint64_t q_full;
   uint64_t k_full[FA3_ST], v_full[FA3_ST], kv_empty[FA3_ST];
-  uint64_t s_full[2], o_full[2], p_full[2];
+  uint64_t s_full[2], s_free[2], o_full[2], p_full[2];
+  uint64_t order[2][4];  // MUFU turn-taking between the two softmax warps of an SM sub-partition
   uint32_t tmem_slot;
 };
 
@@ -67,8 +70,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm, int S, int C, __nv_bfl
   uint8_t* sQ = smem;                          // 2 tiles
   uint8_t* sK = smem + 2 * FA_TILE;            // FA3_ST stages
   uint8_t* sV = sK + FA3_ST * FA_TILE;         // FA3_ST stages
-  uint8_t* sOnes = sV + FA3_ST * FA_TILE;      // [16 keys][64] bf16 ones: second N-atom of every V operand
-  Fa3Bars* bars = reinterpret_cast<Fa3Bars*>(sOnes + 2048);
+  Fa3Bars* bars = reinterpret_cast<Fa3Bars*>(sV + FA3_ST * FA_TILE);
 
   const int warp = threadIdx.x >> 5;
   const int q0 = blockIdx.x * 2 * FA_BM;
@@ -88,13 +90,13 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm, int S, int C, __nv_bfl
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars->s_full[i], 1);
       mbar_init(&bars->o_full[i], 1);
+      mbar_init(&bars->s_free[i], 128);
       mbar_init(&bars->p_full[i], 128);
+      for (int q = 0; q < 4; ++q) mbar_init(&bars->order[i][q], 32);
     }
     fence_barrier_init();
   }
   if (warp == 9) tmem_alloc<512>(&bars->tmem_slot);
-  if (threadIdx.x < 128) reinterpret_cast<uint4*>(sOnes)[threadIdx.x] = make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u)  /* fp16 1.0 */;
-  fence_proxy_async();  // the ones atom is read by the tensor core (async proxy)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -119,8 +121,8 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm, int S, int C, __nv_bfl
   } else if (warp == 9) {
     // ------------------------------------------------------------ MMA issuer
     if (elect_one()) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, FA_BN, 0, 0);  // S = Q K^T (both K-major)
-      constexpr uint32_t idesc_o = umma_idesc_f16(128, FA3_ON, 0, 1);  // O += P [V | 1], fp16 x fp16 (V MN-major)
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, FA_BN, 0, 0);  // S = Q K^T (bf16, both K-major)
+      constexpr uint32_t idesc_o = umma_idesc_f16(128, FA_D, 0, 1);    // O += P V, fp16 x fp16 (V MN-major)
       auto issue_s = [&](int t, int j) {
         const uint64_t dq = umma_desc_sw128(smem_u32(sQ + t * FA_TILE));
         const uint64_t dk = umma_desc_sw128(smem_u32(sK + (j % FA3_ST) * FA_TILE));
@@ -135,26 +137,26 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm, int S, int C, __nv_bfl
       for (int t = 0; t < ntiles; ++t) issue_s(t, 0);
       for (int j = 0; j < nblk; ++j) {
         const int st = j % FA3_ST;
+        if (j + 1 < nblk) {
+          // S(j+1) as soon as the softmax threads hold S(j) in registers
+          mbar_wait(&bars->k_full[(j + 1) % FA3_ST], ((j + 1) / FA3_ST) & 1);
+          for (int t = 0; t < ntiles; ++t) {
+            mbar_wait(&bars->s_free[t], j & 1);
+            tc_fence_after();
+            issue_s(t, j + 1);
+          }
+        }
+        mbar_wait(&bars->v_full[st], (j / FA3_ST) & 1);
         for (int t = 0; t < ntiles; ++t) {
           mbar_wait(&bars->p_full[t], j & 1);  // P_t(j) in TMEM, O_t corrected if it had to be
-          if (t == 0) mbar_wait(&bars->v_full[st], (j / FA3_ST) & 1);
           tc_fence_after();
-          const uint32_t p_tmem = tmem_base + t * 128;
+          const uint32_t p_tmem = tmem_base + 384 + t * 64;
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk) {
-            // B = 16 keys x 80 columns: N-atom 0 = the V tile rows, N-atom 1 (leading-dimension offset) = ones
-            const uint32_t va = smem_u32(sV + st * FA_TILE + kk * 2048);
-            const uint64_t dv = umma_desc_sw128_lbo(va, smem_u32(sOnes) - va);
-            umma_f16_ts(tmem_base + 256 + t * FA3_ON, p_tmem + kk * 8, dv, idesc_o, (j | kk) != 0 ? 1u : 0u);
+            const uint64_t dv = umma_desc_sw128(smem_u32(sV + st * FA_TILE + kk * 2048));
+            umma_f16_ts(tmem_base + 256 + t * 64, p_tmem + kk * 8, dv, idesc_o, (j | kk) != 0 ? 1u : 0u);
           }
           umma_commit(&bars->o_full[t]);
-          if (j + 1 < nblk) {
-            if (t == 0) {
-              mbar_wait(&bars->k_full[(j + 1) % FA3_ST], ((j + 1) / FA3_ST) & 1);
-              tc_fence_after();
-            }
-            issue_s(t, j + 1);  // in-order after P V(j): may overwrite the S/P columns
-          }
         }
         umma_commit(&bars->kv_empty[st]);  // K_j (read by S(j)) and V_j (read by PV(j)) are free
       }
@@ -167,10 +169,15 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm, int S, int C, __nv_bfl
     if (t < ntiles) {
       const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
       const uint32_t s_addr = lane_addr + t * 128;
-      const uint32_t o_addr = lane_addr + 256 + t * FA3_ON;
+      const uint32_t o_addr = lane_addr + 256 + t * 64;
+      const uint32_t p_addr = lane_addr + 384 + t * 64;
       const float sl2 = 0.125f * 1.4426950408889634f;  // attn.scale * log2(e)
       const uint64_t sl22 = pack2(sl2, sl2);
       float m_ref = -INFINITY;                 // reference max the exponentials are taken against
+      uint64_t l2 = pack2(0.f, 0.f);           // row sum (two interleaved partial sums)
+      uint64_t* my_turn = &bars->order[t][warp & 3];
+      uint64_t* their_turn = &bars->order[t ^ 1][warp & 3];
+      const bool take_turns = ntiles == 2;
 
       for (int j = 0; j < nblk; ++j) {
         const int kv_left = S - j * FA_BN;
@@ -179,6 +186,8 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm, int S, int C, __nv_bfl
         uint32_t s[128];
         tmem_ld_32x128(s_addr, s);
         tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&bars->s_free[t]);  // the tensor core may overwrite S_t with S_t(j+1) now
         if (kv_left < FA_BN) {
 #pragma unroll
           for (int c = 0; c < FA_BN; ++c)
@@ -199,6 +208,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm, int S, int C, __nv_bfl
           const float alpha = ex2_approx(m_ref - m_new);  // 1 for lanes that keep their max, 0 on block 0
           m_ref = m_new;
           const uint64_t a2 = pack2(alpha, alpha);
+          l2 = mul2(l2, a2);
           if (j > 0) {
             // rescale O in TMEM: P V(j-1) must have completed; P V(j) is gated by our p_full arrival
             mbar_wait(&bars->o_full[t], (j - 1) & 1);
@@ -213,26 +223,31 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm, int S, int C, __nv_bfl
               o[d + 1] = __float_as_uint(f.y);
             }
             tmem_st_32x64(o_addr, o);
-            uint32_t ls[16];  // the row-sum columns
-            tmem_ld_32x16(o_addr + 64, ls);
-            tmem_ld_wait();
-#pragma unroll
-            for (int d = 0; d < 16; ++d) ls[d] = __float_as_uint(__uint_as_float(ls[d]) * alpha);
-            tmem_st_32x16(o_addr + 64, ls);
           }
         }
         const uint64_t nm2 = pack2(-m_ref, -m_ref);
         uint32_t pw[64];
+        uint64_t la = pack2(0.f, 0.f), lb = pack2(0.f, 0.f);
+        // my turn on the MUFU pipe: tile A's block j follows tile B's block j-1, tile B's follows tile A's
+        if (take_turns && (t == 1 || j > 0)) mbar_wait(my_turn, (t == 1 ? j : j - 1) & 1);
 #pragma unroll
         for (int c = 0; c < FA_BN; c += 4) {
           const float2 x0 = unpack2(fma2(pack2u(s[c], s[c + 1]), sl22, nm2));
           const float2 x1 = unpack2(fma2(pack2u(s[c + 2], s[c + 3]), sl22, nm2));
           const float e0 = ex2_approx(x0.x), e1 = ex2_approx(x0.y);
           const float e2 = ex2_approx(x1.x), e3 = ex2_approx(x1.y);
+          la = add2(la, pack2(e0, e1));
+          lb = add2(lb, pack2(e2, e3));
           pw[c >> 1] = pack_f16x2(e0, e1);        // P <= 2^8 (lazy max): fp16 keeps 11 significant bits
           pw[(c >> 1) + 1] = pack_f16x2(e2, e3);
         }
-        tmem_st_32x64(s_addr, pw);   // P over the first 64 columns of this row's S
+        if (take_turns) mbar_arrive(their_turn);
+        l2 = add2(l2, add2(la, lb));
+        if (j > 0) {  // P V(j-1) must be done reading P_t before it is overwritten (normally long since)
+          mbar_wait(&bars->o_full[t], (j - 1) & 1);
+          tc_fence_after();
+        }
+        tmem_st_32x64(p_addr, pw);
         tmem_st_wait();              // P (and a rescaled O) are in TMEM
         tc_fence_before();
         mbar_arrive(&bars->p_full[t]);
@@ -240,13 +255,13 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm, int S, int C, __nv_bfl
       // all P V accumulated
       mbar_wait(&bars->o_full[t], (nblk - 1) & 1);
       tc_fence_after();
-      uint32_t o[64], ls[16];
+      uint32_t o[64];
       tmem_ld_32x64(o_addr, o);
-      tmem_ld_32x16(o_addr + 64, ls);
       tmem_ld_wait();
       const int qrow = q0 + t * FA_BM + r;
       if (qrow < S) {
-        const float inv = 1.0f / __uint_as_float(ls[0]);
+        const float2 lf = unpack2(l2);
+        const float inv = 1.0f / (lf.x + lf.y);
         uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<long long>(frame) * S + qrow) * ldo + head * FA_D);
 #pragma unroll
         for (int g = 0; g < 8; ++g)
