@@ -495,6 +495,11 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
       tc_fence_after();
       const uint32_t acc = lane_addr + ab * ACC_STRIDE;
       auto mma_col = [&](int c) { return GEGLU ? ((c >> 1) * 128 + (c & 1) * 32) : c * EPI_CHUNK; };
+#ifdef SA_X_NOEPI
+      tc_fence_before();
+      mbar_arrive(&acc_empty[ab]);
+      continue;
+#endif
 
       uint32_t u[32], g[GEGLU ? 32 : 1];
       if (half < CPT) {
@@ -542,7 +547,11 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
         }
         if constexpr (GEGLU) {
 #pragma unroll
+#ifdef SA_X_NOGELU
+          for (int j = 0; j < 16; ++j) v2[j] = mul2(v2[j], g2[j]);
+#else
           for (int j = 0; j < 16; ++j) v2[j] = mul2(v2[j], gelu2(g2[j]));
+#endif
         }
         const int ncol = nout0 + c * EPI_CHUNK;
         if (p.row_bias) {
@@ -603,7 +612,9 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
         fence_proxy_async();  // staging rows visible to the TMA store
         __syncwarp();         // all 32 rows written (and this warp's reads of the X slot done)
         if (lane == 0) {
+#ifndef SA_X_NOSTORE
           tma_store_4d(&tmOut, sRO + slot * EPI_TILE_BYTES, ncol, q1 + w1, q2 + w2, q3 + w3);
+#endif
           tma_store_commit();
           // the slot of chunk gc-1 (== slot of chunk gc+2) is reusable once its store has read smem
           tma_store_wait_read<1>();
@@ -672,7 +683,7 @@ static int pick_tile(int m, int n, int geglu, long long k = 0) {
   for (int i = 0; i < 5; ++i) {
     const int bn = cand[i];
     if (n % bn != 0) continue;
-    if (geglu && bn != (k >= 1280 ? 256 : 128)) continue;  // measured: 256 wins from K = 1280 up
+    if (geglu && bn != (k >= 640 ? 256 : 128)) continue;  // measured (tools/gemm_bench.py): 256 wins from K = 640 up
     if (bn == 32 && n >= 64) continue;
     const long long ctas = m_tiles * (n / bn);
     const long long cost = ((ctas + sms - 1) / sms) * (bn + 16);

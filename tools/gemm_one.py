@@ -1,4 +1,4 @@
-"""Run a few representative sa_gemm_tap launches between cudaProfilerStart/Stop (for ncu --set full)."""
+"""Time sa_gemm_tap on one shape: python tools/gemm_one.py M K N [geglu] [tile]  (CUDA events, warm L2)."""
 import sys
 from pathlib import Path
 
@@ -7,27 +7,29 @@ import torch
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from stableanimator_b200 import ops  # noqa: E402
 
-dev = "cuda"
-cases = [("L0 qkv", 65536, 320, 960, False), ("L0 geglu", 65536, 320, 2560, True),
-         ("L1 ffout", 16384, 2560, 640, False)]
-ts = []
-for name, m, k, n, geglu in cases:
-    a = torch.randn(m, k, device=dev).bfloat16()
-    w = (torch.randn(n, k, device=dev) * k ** -0.5).bfloat16()
-    b = torch.randn(n, device=dev)
-    res = None if geglu else torch.randn(m, n, device=dev).bfloat16()
-    ts.append((a, w, b, geglu, res))
-x = torch.randn(16, 64, 64, 320, device=dev).bfloat16()
-wc = (torch.randn(320, 9 * 320, device=dev) * (9 * 320) ** -0.5).bfloat16()
-for _ in range(2):
-    for a, w, b, geglu, res in ts:
-        ops.gemm_tap(a, w, bias=b, geglu=geglu, residual=res)
-    ops.gemm_tap(x, wc, grid=(64, 64, 16), taps=ops.TAPS_3X3)
-torch.cuda.synchronize()
-torch.cuda.cudart().cudaProfilerStart()
-for a, w, b, geglu, res in ts:
-    ops.gemm_tap(a, w, bias=b, geglu=geglu, residual=res)
-ops.gemm_tap(x, wc, grid=(64, 64, 16), taps=ops.TAPS_3X3)
-torch.cuda.synchronize()
-torch.cuda.cudart().cudaProfilerStop()
-print("done")
+
+def main():
+    m, k, n = (int(x) for x in sys.argv[1:4])
+    geglu = len(sys.argv) > 4 and sys.argv[4] == "1"
+    tile = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+    a = torch.randn(m, k, device="cuda").bfloat16()
+    w = (torch.randn(n, k, device="cuda") * k ** -0.5).bfloat16()
+    b = torch.randn(n, device="cuda")
+    res = None if geglu else torch.randn(m, n, device="cuda").bfloat16()
+    for name, kw in (("bias", dict(bias=b)), ("bias+residual", dict(bias=b, residual=res))):
+        if geglu and name != "bias":
+            continue
+        for _ in range(3):
+            ops.gemm_tap(a, w, geglu=geglu, tile_n=tile, **kw)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            ops.gemm_tap(a, w, geglu=geglu, tile_n=tile, **kw)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 20
+        print(f"M={m} K={k} N={n} geglu={geglu} tile={tile or 'auto'} {name}: {ms * 1e3:.1f} us  {2.0 * m * k * n / ms / 1e9:.0f} TFLOP/s")
+
+
+if __name__ == "__main__":
+    main()
