@@ -8,8 +8,11 @@
 A "step" is one full 25-step denoise of the workload through ``AnimationSampler``.  N=1: BASELINE
 configs[1] (512x512 -> 64x64 latent, 16 frames, one tile, CFG cond/uncond fused in one B=2 batch).
 N>1 (torchrun): weak scaling of the long-video sampler -- N frame tiles of 16 frames (overlap 4,
-F = 16 + 12 (N-1) frames), one tile (both CFG branches) per rank, one NCCL all-reduce of the weighted
-noise accumulator per Euler step.  ``value`` = frames denoised by all ranks / max-over-ranks time.
+a video of 16 + 12 (N-1) frames), one tile (both CFG branches) per rank, one NCCL all-reduce of the
+weighted noise accumulator per Euler step.  ``value`` = tile frames denoised by all ranks (16 per rank:
+the unit of work a rank processes; overlap frames are denoised by both neighbouring tiles and blended,
+inference_pipeline_animation.py:656-689) / max-over-ranks time; the unique video frames per second are
+reported next to it as ``video_frames_per_s``.
 Prints ONE JSON line (rank 0).  Synthetic weights/inputs (stableanimator_b200/synth.py).
 """
 from __future__ import annotations
@@ -266,8 +269,9 @@ def run_ours(args):
 
     if rank == 0:
         sustained, burst, hbm, src = peaks()
-        value = frames / (ms / 1e3)
-        e2e = frames / (e2e_ms / 1e3)
+        tile_frames = tile * world  # frames denoised per bench step by all ranks (N=1: the 16-frame video)
+        value = tile_frames / (ms / 1e3)
+        e2e = tile_frames / (e2e_ms / 1e3)
         # roofline of the dominant kernel family (tcgen05 tapped GEMM): live CUDA-event pass
         ctx = unet.prepare_context(devt["encoder_hidden_states"])
         g_flops, g_ms, g_n, call_ms = gemm_family_time(unet, ctx, devt["added_time_ids"], 2, tile, hw, hw)
@@ -275,16 +279,19 @@ def run_ours(args):
         calls_per_step = args.euler_steps * 2 * world  # B=1-equivalent UNet calls per bench step
         step_tflops = None
         if args.size == "full" and hw == 64:
-            step_tflops = calls_per_step * FLOPS_PER_CALL_64x64x16 / (ms * 1e-3) / 1e12
+            step_tflops = calls_per_step * FLOPS_PER_CALL_64x64x16 / (ms * 1e-3) / 1e12 / world  # per GPU
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": (f"{hw * 8}x{hw * 8}x{frames}f, {args.euler_steps} Euler steps, CFG cond/uncond fused (B=2), "
                                     f"tile 16 / overlap 4" + (" (BASELINE configs[1])" if world == 1 else f", {world} frame tiles over {world} GPUs")),
+                       "frames_counted": (f"tile frames denoised per step by all ranks ({tile} x {world}); "
+                                          f"unique video frames = {frames}"),
                        "unet": args.size, "l2": "working set (3.1 GB weights + activations per UNet call) >> 126 MB L2; no flush",
                        "cuda_graph": not args.no_graph},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "video_frames_per_s": frames / (ms / 1e3),
             "gpu_launches": launches,
             "clocks": clk,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
@@ -293,7 +300,7 @@ def run_ours(args):
                          "launches_per_unet_call": g_n, "family_ms_per_unet_call": g_ms,
                          "unet_call_ms": call_ms, "family_share_of_call": g_ms / call_ms,
                          "how": "CUDA-graph replay of one B=2 UNet call minus the same graph with the GEMM launches elided",
-                         "whole_step_tflops_reference_graph": step_tflops,
+                         "whole_step_tflops_reference_graph_per_gpu": step_tflops,
                          "whole_step_frac": None if step_tflops is None else step_tflops / sustained},
         }
         if world == 1 and not args.no_cpu:

@@ -48,6 +48,8 @@ const char* sa_last_error(void);
  *   if geglu: v = v_value * gelu_erf(v_gate)   (GEGLU, unet.py:868-870; W rows interleaved in
  *                                               64-row blocks: [value block | gate block])
  *   v = v * out_scale + residual[m, n]
+ *   (f16_from_col > 0: columns >= f16_from_col are stored as saturating IEEE fp16 instead of bf16 -- the V
+ *    block of the spatial-attention q|k|v projection, which sa_attn_spatial consumes in half precision)
  *   if blend_x: v = alpha * blend_x[m, n] + (1 - alpha) * v    (AlphaBlender, unet.py:473)
  * ------------------------------------------------------------------------------------------ */
 typedef struct sa_gemm_args {
@@ -76,9 +78,7 @@ typedef struct sa_gemm_args {
   int32_t out_f32;
   int32_t tile_n;        /* 0 = auto; else one of 32, 64, 128, 160, 256 */
   float out_scale;       /* 0 = 1.0; scales (acc*row_scale + bias + row_bias [geglu]) before residual */
-  int32_t f16_from_col;  /* > 0: output columns >= this (a multiple of 32) are stored as IEEE fp16 (saturating)
-                            instead of bf16 -- the V block of the spatial-attention q|k|v projection, which
-                            sa_attn_spatial consumes in half precision; 0 = all bf16 */
+  int32_t f16_from_col;  /* > 0: output columns >= this (multiple of 32) are stored as fp16; 0 = all bf16 */
 } sa_gemm_args;
 
 int sa_gemm_tap(const sa_gemm_args* args, void* stream);
@@ -161,6 +161,9 @@ int sa_conv_direct(const void* x, int32_t n, int32_t h, int32_t w, int32_t cin, 
 int sa_upsample2x(const void* in, int32_t n, int32_t h, int32_t w, int32_t c, void* out, void* stream);
 /* im2col of the 3x3 stride-2 pad-1 Downsample2D conv (unet.py:1474): out bf16 [n*h/2*w/2, 9*c]. */
 int sa_im2col_s2(const void* in, int32_t n, int32_t h, int32_t w, int32_t c, void* out, void* stream);
+/* im2col of conv_in (3x3, pad 1, 8 input channels; unet.py:69,283): in bf16 [n, h, w, 8] ->
+ * out bf16 [n*h*w, 128] = 72 gathered values (ky, kx, ci) + 56 zeros, the K = 128 operand of sa_gemm_tap. */
+int sa_im2col3x3_c8(const void* in, int32_t n, int32_t h, int32_t w, void* out, void* stream);
 
 /* Boundary layout conversion: reference tensors are NCHW, the kernels are NHWC. */
 int sa_nchw_to_nhwc(const void* src, int32_t src_is_bf16, int32_t n, int32_t c, int32_t hw, void* dst,

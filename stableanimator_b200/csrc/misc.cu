@@ -179,6 +179,29 @@ __global__ void im2col_s2_kernel(const uint4* __restrict__ in, int N, int H, int
   }
 }
 
+// ------------------------------------------------------------------ im2col for conv_in (3x3, pad 1, Cin = 8)
+// conv_in (unet.py:69,283) has K = 9*8 = 72: too thin for an implicit-GEMM tap (64-channel TMA boxes), so
+// its rows are gathered once into [M, 128] (72 values + zero padding to two 64-wide K blocks) and the
+// tensor-core GEMM does the rest (with the pose residual in its epilogue).  One uint4 = one pixel's 8 channels.
+__global__ void im2col3x3_c8_kernel(const uint4* __restrict__ in, int N, int H, int W, uint4* __restrict__ out) {
+  const long long total = static_cast<long long>(N) * H * W * 16;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int tap = static_cast<int>(idx & 15);
+    long long p = idx >> 4;
+    const int x = static_cast<int>(p % W);
+    p /= W;
+    const int y = static_cast<int>(p % H);
+    const long long n = p / H;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (tap < 9) {
+      const int yi = y + tap / 3 - 1, xi = x + tap % 3 - 1;
+      if (yi >= 0 && yi < H && xi >= 0 && xi < W) v = __ldg(in + (n * H + yi) * W + xi);
+    }
+    out[idx] = v;
+  }
+}
+
 // ------------------------------------------------------------------ layout conversion (boundary)
 // src [N, C, HW] (fp32 or bf16) -> dst bf16 [N, HW, C]
 template <typename T>
@@ -347,6 +370,16 @@ extern "C" int sa_im2col_s2(const void* in, int32_t n, int32_t h, int32_t w, int
   const long long total = static_cast<long long>(n) * (h / 2) * (w / 2) * 9 * (c / 8);
   im2col_s2_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const uint4*>(in), n, h, w, c / 8,
                                                             static_cast<uint4*>(out));
+  SA_CUDA_CHECK(cudaGetLastError());
+  return SA_OK;
+}
+
+extern "C" int sa_im2col3x3_c8(const void* in, int32_t n, int32_t h, int32_t w, void* out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!in || !out || n <= 0 || h <= 0 || w <= 0) return fail(SA_ERR_INVALID, "sa_im2col3x3_c8: bad arguments");
+  const long long total = static_cast<long long>(n) * h * w * 16;
+  im2col3x3_c8_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const uint4*>(in), n, h, w,
+                                                               static_cast<uint4*>(out));
   SA_CUDA_CHECK(cudaGetLastError());
   return SA_OK;
 }

@@ -5,6 +5,8 @@
 // Replaces nn.GroupNorm(+nn.SiLU) at animation/modules/unet.py:171-173,575,1632,1640,1643
 // (per-frame statistics) and :1709,1722,1731 (TemporalResnetBlock: statistics over all frames of
 // the tile), and nn.LayerNorm at :499,510,521,892,898,907,916.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -233,6 +235,388 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, int ldx, long long M, int 
   }
 }
 
+
+// ------------------------------------------------------------------ LayerNorm, bulk-copy streamed
+// Same math and lane mapping as layernorm_kernel, but rows travel through shared memory: one producer
+// thread keeps LN_ST tiles of TILE_ROWS dense rows in flight with 1-D bulk copies (cp.async.bulk, mbarrier
+// completion), eight consumer warps normalise a tile IN PLACE in shared memory, and the same producer
+// thread writes it back with a bulk store.  ~60-130 KB of loads/stores are in flight per SM regardless of
+// register pressure -- the register-resident kernel above peaks near 2 TB/s on B200 (3 CTAs/SM, every warp
+// alternating load -> reduce -> store), this one streams.  Needs dense rows (ld == C).
+constexpr int LN_ST = 4;        // tiles in flight per CTA
+constexpr int LN_CW = 8;        // consumer warps
+
+template <int LPR, int OPL, bool XOUT>
+struct LnStream {
+  static constexpr int RPW = 32 / LPR;
+  static constexpr int TILE_ROWS = LN_CW * RPW;
+  static constexpr int C = LPR * OPL * 8;
+  static constexpr int TILE_BYTES = TILE_ROWS * C * 2;
+  static constexpr int STAGE_BYTES = TILE_BYTES * (XOUT ? 2 : 1);
+  static constexpr int SMEM = LN_ST * STAGE_BYTES + 2 * LN_ST * 8 + 128;
+};
+
+__device__ __forceinline__ void load8s(const uint8_t* p, float (&v)[8]) {
+  const uint4 q = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const float2 f = unpack_bf16x2(w[t]);
+    v[2 * t] = f.x;
+    v[2 * t + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void store8s(uint8_t* p, const float (&v)[8]) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                            pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
+
+template <int LPR, int OPL, bool XOUT>
+__global__ void __launch_bounds__(32 * (LN_CW + 1))
+layernorm_stream_kernel(const __nv_bfloat16* __restrict__ x, long long M, const float* __restrict__ addv,
+                        int rows_per_group, __nv_bfloat16* __restrict__ x_out, const float* __restrict__ gamma,
+                        const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y) {
+  using L = LnStream<LPR, OPL, XOUT>;
+  constexpr int C = L::C;
+  extern __shared__ uint8_t ln_smem_raw[];
+  uint8_t* smem = ln_smem_raw + ((128u - (smem_u32(ln_smem_raw) & 127u)) & 127u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + LN_ST * L::STAGE_BYTES);
+  uint64_t* done = full + LN_ST;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long n_tiles = (M + L::TILE_ROWS - 1) / L::TILE_ROWS;
+  // contiguous tile range per CTA
+  const long long t_begin = n_tiles * blockIdx.x / gridDim.x, t_end = n_tiles * (blockIdx.x + 1) / gridDim.x;
+  const int my_tiles = static_cast<int>(t_end - t_begin);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < LN_ST; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&done[i], LN_CW);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  auto tile_bytes = [&](long long tile) -> uint32_t {
+    long long rows = M - tile * L::TILE_ROWS;
+    if (rows > L::TILE_ROWS) rows = L::TILE_ROWS;
+    return static_cast<uint32_t>(rows * C * 2);
+  };
+  if (warp == LN_CW) {
+    // ------------------------------------------------------------ producer / store issuer (one thread)
+    if (lane == 0) {
+      auto issue_load = [&](int i) {
+        const long long tile = t_begin + i;
+        const int s = i % LN_ST;
+        const uint32_t bytes = tile_bytes(tile);
+        mbar_expect_tx(&full[s], bytes);
+        bulk_load(smem + s * L::STAGE_BYTES, x + tile * L::TILE_ROWS * C, bytes, &full[s]);
+      };
+      for (int i = 0; i < LN_ST && i < my_tiles; ++i) issue_load(i);
+      for (int i = 0; i < my_tiles; ++i) {
+        const int s = i % LN_ST;
+        const long long tile = t_begin + i;
+        mbar_wait(&done[s], (i / LN_ST) & 1);  // consumers wrote the normalised tile (and fenced it)
+        const uint32_t bytes = tile_bytes(tile);
+        bulk_store(y + tile * L::TILE_ROWS * C, smem + s * L::STAGE_BYTES, bytes);
+        if (XOUT) bulk_store(x_out + tile * L::TILE_ROWS * C, smem + s * L::STAGE_BYTES + L::TILE_BYTES, bytes);
+        tma_store_commit();
+        // the slot stored one iteration ago is reusable once that store has read it
+        if (i >= 1 && i - 1 + LN_ST < my_tiles) {
+          tma_store_wait_read<1>();
+          issue_load(i - 1 + LN_ST);
+        }
+      }
+      tma_store_wait_all();
+    }
+  } else {
+    // ------------------------------------------------------------ consumers
+    constexpr int RPW = L::RPW;
+    const int sub = lane / LPR, l = lane % LPR;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int s = i % LN_ST;
+      const long long row = (t_begin + i) * L::TILE_ROWS + warp * RPW + sub;
+      const bool active = row < M;
+      uint8_t* base = smem + s * L::STAGE_BYTES + (warp * RPW + sub) * (C * 2);
+      mbar_wait(&full[s], (i / LN_ST) & 1);
+      float v[OPL][8];
+      float sum = 0.f;
+      const float* av = (addv && active) ? addv + (row / rows_per_group) * C : nullptr;
+#pragma unroll
+      for (int o = 0; o < OPL; ++o) {
+        const int oc = l + LPR * o;
+        if (active) {
+          load8s(base + oc * 16, v[o]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[o][k] = 0.f;
+        }
+        if (av) {
+          const float4 a0 = __ldg(reinterpret_cast<const float4*>(av + oc * 8));
+          const float4 a1 = __ldg(reinterpret_cast<const float4*>(av + oc * 8 + 4));
+          v[o][0] += a0.x; v[o][1] += a0.y; v[o][2] += a0.z; v[o][3] += a0.w;
+          v[o][4] += a1.x; v[o][5] += a1.y; v[o][6] += a1.z; v[o][7] += a1.w;
+          if (XOUT) {
+            store8s(base + L::TILE_BYTES + oc * 16, v[o]);
+            // keep the bf16-rounded value: it is what every later consumer of the stream reads
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[o][k] = __bfloat162float(__float2bfloat16_rn(v[o][k]));
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sum += v[o][k];
+      }
+#pragma unroll
+      for (int d = LPR / 2; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+      const float mean = sum / static_cast<float>(C);
+      float var = 0.f;
+#pragma unroll
+      for (int o = 0; o < OPL; ++o) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float d = v[o][k] - mean;
+          var += d * d;
+        }
+      }
+#pragma unroll
+      for (int d = LPR / 2; d > 0; d >>= 1) var += __shfl_xor_sync(0xffffffffu, var, d);
+      const float rstd = rsqrtf(var / static_cast<float>(C) + eps);
+      if (active) {
+#pragma unroll
+        for (int o = 0; o < OPL; ++o) {
+          const int oc = l + LPR * o;
+          const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + oc * 8));
+          const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + oc * 8 + 4));
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + oc * 8));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + oc * 8 + 4));
+          const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          float o8[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o8[k] = fmaf((v[o][k] - mean) * rstd, g[k], bb[k]);
+          store8s(base + oc * 16, o8);
+        }
+      }
+      fence_proxy_async();  // our generic-proxy writes must be visible to the bulk store
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&done[s]);
+    }
+  }
+}
+
+
+// ------------------------------------------------------------------ GroupNorm, bulk-copy streamed
+// The register-resident kernels above run at ~2.2-2.8 TB/s on B200 (gn_apply: 96 registers -> 2 CTAs per SM;
+// ncu: profiles/r1_v4_ncu_memory_bound.txt).  Here one producer thread keeps GN_ST tiles of R dense rows in
+// flight with 1-D bulk copies (one per concat source), 256 consumer threads reduce (stats) or normalise
+// (apply, in place for a single source) them in shared memory, and the producer writes tiles back with bulk
+// stores.  Thread -> channel octet is fixed, so the per-channel scale/shift (apply) and the partial sums
+// (stats) stay in registers for all tiles of a statistics group.  512 consumer threads x 2 CTAs per SM: the
+// apply pass is bound by its own instruction stream (SiLU = 2 MUFU + packed FMA per element), not by HBM.
+constexpr int GN_ST = 4, GN_CW = 16, GN_CT = GN_CW * 32, GN_MAXCOL = 1;
+
+struct GnStreamP {
+  const __nv_bfloat16* x0;
+  const __nv_bfloat16* x1;
+  int C0, C1, R;            // channels per source, rows per tile
+  long long P;              // rows per statistics group (multiple of R)
+  long long n_tiles;        // ns * P / R
+  int cpg;
+  double* stats;            // [ns, 32, 2]
+  const float* gamma;
+  const float* beta;
+  float eps;
+  int do_silu;
+  __nv_bfloat16* out;       // apply only, dense [rows, C0 + C1]
+};
+
+template <bool APPLY>
+__global__ void __launch_bounds__(GN_CT + 32, 2)
+gn_stream_kernel(const GnStreamP p) {
+  extern __shared__ uint8_t gn_smem_raw[];
+  uint8_t* smem = gn_smem_raw + ((128u - (smem_u32(gn_smem_raw) & 127u)) & 127u);
+  const int C = p.C0 + p.C1;
+  const int in_bytes0 = p.R * p.C0 * 2, in_bytes1 = p.R * p.C1 * 2, in_bytes = in_bytes0 + in_bytes1;
+  const bool two_src = p.C1 > 0;
+  const int stage_bytes = in_bytes * ((APPLY && two_src) ? 2 : 1);  // concat input cannot be normalised in place
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + GN_ST * stage_bytes);
+  uint64_t* done = full + GN_ST;
+  double* sm_stats = reinterpret_cast<double*>(done + GN_ST);  // [32][2], stats kernel only
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long t_begin = p.n_tiles * blockIdx.x / gridDim.x, t_end = p.n_tiles * (blockIdx.x + 1) / gridDim.x;
+  const int my_tiles = static_cast<int>(t_end - t_begin);
+  const long long tiles_per_stat = p.P / p.R;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < GN_ST; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&done[i], GN_CW);
+    }
+    fence_barrier_init();
+  }
+  if (!APPLY && threadIdx.x < 64) sm_stats[threadIdx.x] = 0.0;
+  __syncthreads();
+
+  if (warp == GN_CW) {
+    // ------------------------------------------------------------ producer / store issuer
+    if (lane == 0) {
+      auto issue_load = [&](int i) {
+        const long long row0 = (t_begin + i) * p.R;
+        uint8_t* dst = smem + (i % GN_ST) * stage_bytes;
+        mbar_expect_tx(&full[i % GN_ST], in_bytes);
+        bulk_load(dst, p.x0 + row0 * p.C0, in_bytes0, &full[i % GN_ST]);
+        if (two_src) bulk_load(dst + in_bytes0, p.x1 + row0 * p.C1, in_bytes1, &full[i % GN_ST]);
+      };
+      for (int i = 0; i < GN_ST && i < my_tiles; ++i) issue_load(i);
+      for (int i = 0; i < my_tiles; ++i) {
+        const int s = i % GN_ST;
+        mbar_wait(&done[s], (i / GN_ST) & 1);
+        if (APPLY) {
+          const long long row0 = (t_begin + i) * p.R;
+          bulk_store(p.out + row0 * C, smem + s * stage_bytes + (two_src ? in_bytes : 0), in_bytes);
+          tma_store_commit();
+          if (i >= 1 && i - 1 + GN_ST < my_tiles) {
+            tma_store_wait_read<1>();  // the slot stored one iteration ago has been read
+            issue_load(i - 1 + GN_ST);
+          }
+        } else if (i + GN_ST < my_tiles) {
+          issue_load(i + GN_ST);
+        }
+      }
+      if (APPLY) tma_store_wait_all();
+    }
+    return;
+  }
+
+  // ---------------------------------------------------------------- consumers
+  const int noct = C >> 3, noct0 = p.C0 >> 3;
+  const int rl_n = noct >= GN_CT ? 1 : GN_CT / noct;     // row lanes
+  const int ncol = (noct + GN_CT - 1) / GN_CT;           // column sets per thread (1 or 2)
+  const int t = threadIdx.x;
+  const int rl = noct >= GN_CT ? 0 : t / noct;
+  const int oc_first = noct >= GN_CT ? t : t % noct;
+  const bool lane_active = rl < rl_n;
+  float a[GN_MAXCOL][8], b[GN_MAXCOL][8];   // apply: scale / shift; stats: sum / sum of squares
+  long long cur_stat = -1;
+
+  auto flush_stats = [&](long long ns) {
+    // fold this thread's channel sums into their groups, CTA-reduce in fp64 shared atomics, then one
+    // global fp64 atomic per (group, moment)
+#pragma unroll
+    for (int cs = 0; cs < GN_MAXCOL; ++cs) {
+      const int oc = oc_first + cs * GN_CT;
+      if (cs < ncol && oc < noct && lane_active) {
+        const int c = oc * 8;
+        int g_prev = c / p.cpg;
+        double as = 0.0, aq = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int g = (c + k) / p.cpg;
+          if (g != g_prev) {
+            atomicAdd(&sm_stats[g_prev * 2], as);
+            atomicAdd(&sm_stats[g_prev * 2 + 1], aq);
+            as = aq = 0.0;
+            g_prev = g;
+          }
+          as += static_cast<double>(a[cs][k]);
+          aq += static_cast<double>(b[cs][k]);
+          a[cs][k] = b[cs][k] = 0.f;
+        }
+        atomicAdd(&sm_stats[g_prev * 2], as);
+        atomicAdd(&sm_stats[g_prev * 2 + 1], aq);
+      }
+    }
+    named_bar_sync(1, GN_CT);
+    if (t < 64) {
+      atomicAdd(&p.stats[ns * 64 + t], sm_stats[t]);
+      sm_stats[t] = 0.0;
+    }
+    named_bar_sync(1, GN_CT);
+  };
+
+  if (!APPLY) {
+#pragma unroll
+    for (int cs = 0; cs < GN_MAXCOL; ++cs)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a[cs][k] = b[cs][k] = 0.f;
+  }
+
+  for (int i = 0; i < my_tiles; ++i) {
+    const int s = i % GN_ST;
+    const long long ns = (t_begin + i) / tiles_per_stat;
+    if (ns != cur_stat) {
+      if (APPLY) {
+        const double n = static_cast<double>(p.P) * p.cpg;
+#pragma unroll
+        for (int cs = 0; cs < GN_MAXCOL; ++cs) {
+          const int oc = oc_first + cs * GN_CT;
+          if (cs < ncol && oc < noct && lane_active) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const int c = oc * 8 + k, g = c / p.cpg;
+              const double mean = p.stats[(ns * 32 + g) * 2] / n;
+              double var = p.stats[(ns * 32 + g) * 2 + 1] / n - mean * mean;
+              if (var < 0.0) var = 0.0;
+              const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(p.eps)));
+              const float ga = p.gamma[c];
+              a[cs][k] = rstd * ga;
+              b[cs][k] = p.beta[c] - static_cast<float>(mean) * rstd * ga;
+            }
+          }
+        }
+      } else if (cur_stat >= 0) {
+        flush_stats(cur_stat);
+      }
+      cur_stat = ns;
+    }
+    uint8_t* slot = smem + s * stage_bytes;
+    mbar_wait(&full[s], (i / GN_ST) & 1);
+    if (lane_active) {
+#pragma unroll
+      for (int cs = 0; cs < GN_MAXCOL; ++cs) {
+        const int oc = oc_first + cs * GN_CT;
+        if (cs < ncol && oc < noct) {
+          const bool src0 = oc < noct0;
+          const uint8_t* src = src0 ? slot + oc * 16 : slot + in_bytes0 + (oc - noct0) * 16;
+          const int src_ld = (src0 ? p.C0 : p.C1) * 2;
+          uint8_t* dst = two_src ? slot + in_bytes + oc * 16 : slot + oc * 16;
+          for (int r = rl; r < p.R; r += rl_n) {
+            float v[8];
+            load8s(src + r * src_ld, v);
+            if (APPLY) {
+              // packed fp32x2 lanes; silu(y) = y / (1 + 2^(-y log2 e))
+              uint32_t w[4];
+#pragma unroll
+              for (int k = 0; k < 8; k += 2) {
+                const uint64_t y2 = fma2(pack2(v[k], v[k + 1]), pack2(a[cs][k], a[cs][k + 1]),
+                                         pack2(b[cs][k], b[cs][k + 1]));
+                if (p.do_silu) {
+                  const float2 n = unpack2(mul2(y2, pack2(-1.4426950408889634f, -1.4426950408889634f)));
+                  const float2 d = unpack2(add2(pack2(ex2_approx(n.x), ex2_approx(n.y)), pack2(1.0f, 1.0f)));
+                  float r0, r1;
+                  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d.x));
+                  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d.y));
+                  w[k >> 1] = pack_bf16x2_f2(mul2(y2, pack2(r0, r1)));
+                } else {
+                  w[k >> 1] = pack_bf16x2_f2(y2);
+                }
+              }
+              *reinterpret_cast<uint4*>(dst + r * (C * 2)) = make_uint4(w[0], w[1], w[2], w[3]);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                a[cs][k] += v[k];
+                b[cs][k] = fmaf(v[k], v[k], b[cs][k]);
+              }
+            }
+          }
+        }
+      }
+    }
+    if (APPLY) fence_proxy_async();  // normalised rows visible to the bulk store
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&done[s]);
+  }
+  if (!APPLY && cur_stat >= 0) flush_stats(cur_stat);
+}
+
 }  // namespace sa
 
 using namespace sa;
@@ -271,6 +655,51 @@ extern "C" int sa_groupnorm(const void* x0, const void* x1, int32_t c0, int32_t 
     return fail(SA_ERR_INVALID, "sa_groupnorm: C=%d unsupported", C);
   const int cpg = C / 32;
   SA_CUDA_CHECK(cudaMemsetAsync(stats_ws, 0, sizeof(double) * 64 * ns, stream));
+  // streamed path: dense sources / output, enough bytes to fill the pipeline, tile rows dividing the group
+  {
+    int R = 32;
+    while (R > 1 && R * C * 2 > 20 * 1024) R >>= 1;
+    const long long total_bytes = static_cast<long long>(rows_per_stat) * ns * C * 2;
+    const bool dense = ld0 == c0 && (c1 == 0 || ld1 == c1) && ldo == C;
+    static const bool force_reg = getenv("SA_GN_REG") != nullptr;
+    if (dense && !force_reg && rows_per_stat % R == 0 && total_bytes >= (8ll << 20) && C / 8 <= GN_MAXCOL * GN_CT &&
+        R * C * 2 <= 24 * 1024) {
+      GnStreamP sp;
+      sp.x0 = static_cast<const __nv_bfloat16*>(x0);
+      sp.x1 = static_cast<const __nv_bfloat16*>(x1);
+      sp.C0 = c0;
+      sp.C1 = c1;
+      sp.R = R;
+      sp.P = rows_per_stat;
+      sp.n_tiles = rows_per_stat / R * ns;
+      sp.cpg = cpg;
+      sp.stats = static_cast<double*>(stats_ws);
+      sp.gamma = gamma;
+      sp.beta = beta;
+      sp.eps = eps;
+      sp.do_silu = do_silu;
+      sp.out = static_cast<__nv_bfloat16*>(out);
+      const int tile = R * C * 2;
+      const int smem_stats = GN_ST * tile + 2 * GN_ST * 8 + 64 * 8 + 128;
+      const int smem_apply = GN_ST * tile * (c1 > 0 ? 2 : 1) + 2 * GN_ST * 8 + 64 * 8 + 128;
+      static bool cfgd = false;
+      if (!cfgd) {
+        SA_CUDA_CHECK(cudaFuncSetAttribute(gn_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        SA_CUDA_CHECK(cudaFuncSetAttribute(gn_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        cfgd = true;
+      }
+      const int sms = num_sms();
+      long long g1 = static_cast<long long>(sms) * (smem_stats <= 110 * 1024 ? 2 : 1);
+      long long g2 = static_cast<long long>(sms) * (smem_apply <= 110 * 1024 ? 2 : 1);
+      if (g1 > sp.n_tiles) g1 = sp.n_tiles;
+      if (g2 > sp.n_tiles) g2 = sp.n_tiles;
+      gn_stream_kernel<false><<<static_cast<unsigned>(g1), GN_CT + 32, smem_stats, stream>>>(sp);
+      SA_CUDA_CHECK(cudaGetLastError());
+      gn_stream_kernel<true><<<static_cast<unsigned>(g2), GN_CT + 32, smem_apply, stream>>>(sp);
+      SA_CUDA_CHECK(cudaGetLastError());
+      return SA_OK;
+    }
+  }
   gn_stats_kernel<<<grid, block, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(x0), static_cast<const __nv_bfloat16*>(x1), c0, c1, ld0, ld1,
       rows_per_stat, cpg, rpc, static_cast<double*>(stats_ws));
@@ -306,9 +735,30 @@ extern "C" int sa_layernorm(const void* x, int32_t ldx, int64_t rows, int32_t c,
   const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x);
   __nv_bfloat16* xo = static_cast<__nv_bfloat16*>(x_out);
   __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(y);
-#define SA_LN(LPR, OPL)                                                                             \
-  layernorm_kernel<LPR, OPL><<<grid, warps * 32, 0, stream>>>(xp, ldx, rows, c, addv, rpg, xo, ldxo, \
-                                                              gamma, beta, eps, yp, ldy)
+  const bool dense = ldx == c && ldy == c && (!x_out || ldxo == c) && (x_out == nullptr || addv != nullptr) &&
+                     rows * c * 2 >= (8ll << 20) && getenv("SA_LN_REG") == nullptr;
+  static int n_sm = num_sms();
+#define SA_LN_STREAM(LPR, OPL, XO)                                                                        \
+  do {                                                                                                    \
+    using L = LnStream<LPR, OPL, XO>;                                                                     \
+    static bool cfgd = false;                                                                             \
+    if (!cfgd) {                                                                                          \
+      SA_CUDA_CHECK(cudaFuncSetAttribute(layernorm_stream_kernel<LPR, OPL, XO>,                           \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM));          \
+      cfgd = true;                                                                                        \
+    }                                                                                                     \
+    const long long nt = (rows + L::TILE_ROWS - 1) / L::TILE_ROWS;                                        \
+    long long g = static_cast<long long>(n_sm) * (L::SMEM <= 110 * 1024 ? 2 : 1);                         \
+    if (g > nt) g = nt;                                                                                   \
+    layernorm_stream_kernel<LPR, OPL, XO><<<static_cast<unsigned>(g), 32 * (LN_CW + 1), L::SMEM, stream>>>( \
+        xp, rows, addv, rpg, xo, gamma, beta, eps, yp);                                                   \
+  } while (0)
+#define SA_LN(LPR, OPL)                                                                               \
+  if (dense && LnStream<LPR, OPL, true>::SMEM <= 227 * 1024) {                                        \
+    if (xo) SA_LN_STREAM(LPR, OPL, true); else SA_LN_STREAM(LPR, OPL, false);                         \
+  } else                                                                                              \
+    layernorm_kernel<LPR, OPL><<<grid, warps * 32, 0, stream>>>(xp, ldx, rows, c, addv, rpg, xo, ldxo, \
+                                                                gamma, beta, eps, yp, ldy)
 #define SA_LN_ROW(LPR)                                                         \
   switch (opl) {                                                               \
     case 1: SA_LN(LPR, 1); break;                                              \
@@ -323,6 +773,7 @@ extern "C" int sa_layernorm(const void* x, int32_t ldx, int64_t rows, int32_t c,
   if (lpr == 32) { SA_LN_ROW(32) } else if (lpr == 16) { SA_LN_ROW(16) } else { SA_LN_ROW(8) }
 #undef SA_LN_ROW
 #undef SA_LN
+#undef SA_LN_STREAM
   SA_CUDA_CHECK(cudaGetLastError());
   return SA_OK;
 }

@@ -310,6 +310,18 @@ def im2col_s2(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tens
     return out
 
 
+def im2col3x3_c8(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """conv_in gather: x bf16 [n, h, w, 8] -> bf16 [n*h*w, 128] (72 values (ky, kx, ci) + zero padding)."""
+    _chk_bf16(x, "x")
+    n, h, w, c = x.shape
+    if c != 8 or not x.is_contiguous():
+        raise ValueError("x must be contiguous [n, h, w, 8]")
+    if out is None:
+        out = torch.empty((n * h * w, 128), device=x.device, dtype=torch.bfloat16)
+    check(lib().sa_im2col3x3_c8(x.data_ptr(), n, h, w, out.data_ptr(), _stream()), "sa_im2col3x3_c8")
+    return out
+
+
 def nchw_to_nhwc(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """[n, c, h, w] fp32/bf16 contiguous -> bf16 [n, h, w, c]."""
     if not x.is_contiguous() or x.dtype not in (torch.float32, torch.bfloat16):

@@ -95,6 +95,10 @@ class UNetB200:
         t = sd["conv_in.weight"]
         w["conv_in.w"] = _bf16(t.permute(2, 3, 1, 0).reshape(-1, t.shape[0]), dev)
         w["conv_in.b"] = _f32(sd["conv_in.bias"], dev)
+        if t.shape[1] == 8 and t.shape[2:] == (3, 3):  # tensor-core path: [O, 72 (ky, kx, ci) | 56 zeros]
+            wg = torch.zeros(t.shape[0], 128, dtype=torch.float32)
+            wg[:, :72] = t.permute(0, 2, 3, 1).reshape(t.shape[0], 72).float().cpu()
+            w["conv_in.wg"] = _bf16(wg, dev)
         for n in ("time_embedding.linear_1", "time_embedding.linear_2", "add_embedding.linear_1",
                   "add_embedding.linear_2"):
             lin(n)
@@ -288,6 +292,24 @@ class UNetB200:
                           alpha=w[f"{t.name}.alpha"])
         return ops.gemm_tap(z4, w[f"{t.name}.proj_out.w"], bias=w[f"{t.name}.proj_out.b"], residual=x)
 
+    def _conv_in(self, x_in: torch.Tensor, pose: Optional[torch.Tensor], pose_from: int) -> torch.Tensor:
+        """conv_in (unet.py:283) + pose residual on the frames >= pose_from (:284-286) -> tokens [M, C0].
+        K = 72 is gathered to a [M, 128] operand and runs on the tensor-core GEMM (two launches when only
+        part of the batch carries the pose residual); other conv_in geometries use the direct kernel."""
+        w, c0 = self.w, self.cfg.block_out_channels[0]
+        n, h, wd, cin = x_in.shape
+        if "conv_in.wg" not in w or c0 % 64:
+            return ops.conv_direct(x_in, w["conv_in.w"], w["conv_in.b"], c0, 3, 1, 1, add=pose,
+                                   add_from=pose_from).reshape(-1, c0)
+        cols = ops.im2col3x3_c8(x_in.contiguous())
+        x = torch.empty((n * h * wd, c0), device=self.dev, dtype=torch.bfloat16)
+        r0 = pose_from * h * wd if pose is not None else n * h * wd
+        if r0 > 0:
+            ops.gemm_tap(cols[:r0], w["conv_in.wg"], bias=w["conv_in.b"], out=x[:r0])
+        if pose is not None:
+            ops.gemm_tap(cols[r0:], w["conv_in.wg"], bias=w["conv_in.b"], residual=pose.reshape(-1, c0), out=x[r0:])
+        return x
+
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
     def forward_nhwc(self, x_in: torch.Tensor, timestep: torch.Tensor, ctx: _Ctx, added_time_ids: torch.Tensor,
@@ -303,8 +325,7 @@ class UNetB200:
             raise ValueError("context batch does not match")
         temb = self._time_embedding(timestep, added_time_ids, B)
         c0 = cfg.block_out_channels[0]
-        x = ops.conv_direct(x_in.reshape(B * F, h, wd, cfg.in_channels), w["conv_in.w"], w["conv_in.b"], c0, 3, 1, 1,
-                            add=pose_nhwc, add_from=pose_batch_from * F).reshape(-1, c0)
+        x = self._conv_in(x_in.reshape(B * F, h, wd, cfg.in_channels), pose_nhwc, pose_batch_from * F)
         if taps is not None:
             taps["conv_in"] = x
         skips: List[Tuple[torch.Tensor, int]] = [x]

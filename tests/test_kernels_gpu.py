@@ -115,6 +115,48 @@ def test_groupnorm(ns, rows, c, silu):
     assert_close(out, ref.permute(0, 2, 1).reshape(ns * rows, c), what="groupnorm")
 
 
+@pytest.mark.parametrize("ns,rows,c0,c1,silu", [
+    (8, 4096, 320, 0, True),      # streamed path, per-frame statistics (L0 shape)
+    (2, 16 * 1024, 640, 0, True),  # per-tile statistics (TemporalResnetBlock, 5-D GroupNorm)
+    (4, 1024, 1280, 1280, True),  # concat, C = 2560: two column sets per thread, 4-row tiles
+    (6, 1024, 1280, 640, False),  # concat with a group straddling the two sources (cpg = 60)
+    (8, 2304, 640, 320, True),    # 576x1024 level-1 concat (S = 64 x 36)
+])
+def test_groupnorm_streamed(ns, rows, c0, c1, silu):
+    """Shapes large enough (>= 8 MB) to take the bulk-copy streamed kernels (gn_stream_kernel)."""
+    from stableanimator_b200 import ops
+    x0 = rnd(ns * rows, c0, scale=2.0, seed=16) + 0.5
+    x1 = rnd(ns * rows, c1, scale=3.0, seed=17) - 0.25 if c1 else None
+    c = c0 + c1
+    gamma, beta = torch.rand(c, device="cuda") + 0.5, torch.randn(c, device="cuda") * 0.1
+    out = ops.groupnorm(x0, gamma, beta, 1e-5, rows, x1=x1, silu=silu)
+    xc = x0 if x1 is None else torch.cat([x0, x1], dim=-1)
+    ref = F.group_norm(xc.float().reshape(ns, rows, c).permute(0, 2, 1), 32, gamma, beta, 1e-5)
+    if silu:
+        ref = F.silu(ref)
+    assert_close(out, ref.permute(0, 2, 1).reshape(ns * rows, c), what="groupnorm streamed")
+
+
+@pytest.mark.parametrize("rows,c,addv", [(65536, 320, False), (20000, 640, True), (8192, 1280, True)])
+def test_layernorm_streamed(rows, c, addv):
+    """>= 8 MB: bulk-copy streamed LayerNorm, with and without the fused vector add / residual output."""
+    from stableanimator_b200 import ops
+    x = rnd(rows, c, scale=2.0, seed=18) + 0.3
+    gamma, beta = torch.rand(c, device="cuda") + 0.5, torch.randn(c, device="cuda") * 0.1
+    if addv:
+        rpg = rows // 4
+        av = torch.randn(4, c, device="cuda")
+        xo = torch.empty_like(x)
+        out = ops.layernorm(x, gamma, beta, addv=av, rows_per_group=rpg, x_out=xo)
+        xs = (x.float() + av.repeat_interleave(rpg, dim=0))
+        assert_close(xo, xs, what="layernorm x_out")
+        ref = F.layer_norm(xs.bfloat16().float(), (c,), gamma, beta, 1e-5)
+    else:
+        out = ops.layernorm(x, gamma, beta)
+        ref = F.layer_norm(x.float(), (c,), gamma, beta, 1e-5)
+    assert_close(out, ref, what="layernorm streamed")
+
+
 def test_groupnorm_concat_straddling_groups():
     from stableanimator_b200 import ops
     ns, rows, c0, c1 = 2, 256, 1280, 640  # cpg = 60: group 21 straddles the two sources
