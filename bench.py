@@ -35,6 +35,10 @@ METRIC = "denoised frames/sec at 512x512x16f 25 steps"
 UNIT = "frames/s"
 # reference-graph FLOPs of one B=1 UNet call at F=16, 64x64 latent
 FLOPS_PER_CALL_64x64x16 = 20.311e12
+# average DRAM bytes (read + write) per sa_gemm_tap launch in one B=2 UNet call at 64x64x16, from the ncu pass
+# `--metrics dram__bytes_read.sum,dram__bytes_write.sum` over all 334 launches of the family
+# (profiles/r1_v5_launches_unet_b2_64x64x16.csv, summary next to it: read 98.2 MB + write 42.6 MB)
+GEMM_DRAM_BYTES_PER_LAUNCH = 140.7e6
 
 
 def peaks():
@@ -295,7 +299,10 @@ def run_ours(args):
             "gpu_launches": launches,
             "clocks": clk,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
-                         "frac": achieved / sustained, "traffic": None, "peak_source": src,
+                         "frac": achieved / sustained,
+                         "traffic": GEMM_DRAM_BYTES_PER_LAUNCH if (args.size == "full" and hw == 64) else None,
+                         "traffic_unit": "bytes of DRAM read+write per launch (ncu, family average)",
+                         "peak_source": src,
                          "kernel": "gemm_tap_kernel (tcgen05 tapped implicit GEMM, all instantiations)",
                          "launches_per_unet_call": g_n, "family_ms_per_unet_call": g_ms,
                          "unet_call_ms": call_ms, "family_share_of_call": g_ms / call_ms,
