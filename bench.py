@@ -208,6 +208,11 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the hot path has no CPU fallback); use --impl reference")
     torch.cuda.set_device(local)
+    # stdout carries exactly ONE JSON line (rank 0): everything else that lands on fd 1 during the run (NCCL's
+    # version banner, library chatter) is sent to stderr until the line is printed
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
@@ -317,6 +322,8 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": 16 / sec, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"1 B=1 fp32 oracle UNet call, F={sample_frames}, {hw}x{hw} latent, "
                                               f"scaled to F=16 and x50 calls"}
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
