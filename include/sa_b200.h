@@ -140,11 +140,21 @@ int sa_layernorm(const void* x, int32_t ldx, int64_t rows, int32_t c, const floa
                  const float* beta, float eps, void* y, int32_t ldy, void* stream);
 
 /* Skinny linear (m <= a few dozen rows), fp32 activations, bf16 weights [n, k], fp32 out:
- *   out (+)= act_out(act_in(x) @ W^T + b).  TimestepEmbedding (unet.py:429-436), time_emb_proj(silu(.))
+ *   out (+)= act_out(act_in(x) @ W^T + b); silu_out: 0 none, 1 SiLU, 2 exact GELU.  TimestepEmbedding (unet.py:429-436), time_emb_proj(silu(.))
  *   (:1669-1670,:1754-1755), context K/V projections (:1974-1975,:1999-2000,:1834-1835). */
 int sa_small_linear(const float* x, int32_t ldx, int32_t m, const void* w, int32_t k, int32_t n,
                     const float* bias, int32_t silu_in, int32_t silu_out, int32_t accumulate,
                     float* out, int32_t ldo, void* stream);
+
+/* FusionFaceId (animation/modules/id_encoder.py:102-148; face tokens of the conditioning, once per video).
+ * sa_small_linear above does its Linear layers (silu_out = 2 selects the exact GELU of nn.GELU, :60,:118).
+ * LayerNorm over c on m fp32 rows (:24-25,:59,:78,:125). */
+int sa_layernorm_f32(const float* x, int32_t ldx, int32_t m, int32_t c, const float* gamma, const float* beta,
+                     float eps, float* y, int32_t ldy, void* stream);
+/* PerceiverAttention core (:43-55): out[b, l, h*64+d] = softmax_n(q k^T / 8) v in fp32, head_dim 64, n <= 32.
+ * q fp32 [b, l, ldq]; kv fp32 [b, n, ldkv] with k at column h*64 and v at column voff + h*64. */
+int sa_perceiver_attn(const float* q, int32_t ldq, const float* kv, int32_t ldkv, int32_t voff, int32_t b,
+                      int32_t l, int32_t n, int32_t heads, float* out, int32_t ldo, void* stream);
 
 /* get_timestep_embedding (unet.py:365-390): out[i] = [cos(t_i f) | sin(t_i f)], fp32 [n, dim]. */
 int sa_sinusoid(const float* t, int32_t n, int32_t dim, float* out, void* stream);

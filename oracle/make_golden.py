@@ -68,6 +68,24 @@ def unet_case(cfg: UNetConfig, name: str, frames: int, h: int, w: int, t: float,
                GOLD / f"unet_{name}.pt")
 
 
+def face_case():
+    """FusionFaceId (id_encoder.py:102-148): pins oracle/face_oracle.py and writes tests/golden/face_fusion.pt."""
+    from oracle import face_oracle
+    from stableanimator_b200.synth import synth_face_inputs, synth_face_state_dict
+    _, _, rid = ref_loader.import_reference()
+    sd = synth_face_state_dict(SEED)
+    m = rid.FusionFaceId().eval()
+    m.load_state_dict({k: v.clone() for k, v in sd.items()}, strict=True)
+    ide, clip = synth_face_inputs(2, SEED)
+    with torch.no_grad():
+        out_ref = m(ide, clip)
+    out_mine = face_oracle.fusion_face_id(sd, ide, clip)
+    e = rel(out_mine, out_ref)
+    print(f"[face_fusion] oracle vs reference: {e:.2e}")
+    assert e < 1e-5
+    torch.save({"seed": SEED, "batch": 2, "out": out_ref.clone()}, GOLD / "face_fusion.pt")
+
+
 def main():
     GOLD.mkdir(parents=True, exist_ok=True)
     torch.manual_seed(0)
@@ -83,3 +101,4 @@ def main():
 
 if __name__ == "__main__":
     main()
+    face_case()

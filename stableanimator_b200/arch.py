@@ -233,6 +233,31 @@ def posenet_param_shapes(noise_latent_channels: int = 320) -> Dict[str, Tuple[in
     return d
 
 
+def face_param_shapes(cross_attention_dim: int = 1024, id_embeddings_dim: int = 512, clip_embeddings_dim: int = 1024,
+                      num_tokens: int = 4, depth: int = 4, ff_mult: int = 4) -> Dict[str, Tuple[int, ...]]:
+    """FusionFaceId (animation/modules/id_encoder.py:102-131) with its FacePerceiver (:66-92)."""
+    c, e = cross_attention_dim, id_embeddings_dim
+    d: Dict[str, Tuple[int, ...]] = {
+        "proj.0.weight": (2 * e, e), "proj.0.bias": (2 * e,),
+        "proj.2.weight": (c * num_tokens, 2 * e), "proj.2.bias": (c * num_tokens,),
+        "norm.weight": (c,), "norm.bias": (c,),
+        "fusion_model.proj_in.weight": (c, clip_embeddings_dim), "fusion_model.proj_in.bias": (c,),
+        "fusion_model.proj_out.weight": (c, c), "fusion_model.proj_out.bias": (c,),
+        "fusion_model.norm_out.weight": (c,), "fusion_model.norm_out.bias": (c,),
+    }
+    for i in range(depth):
+        a, f = f"fusion_model.layers.{i}.0", f"fusion_model.layers.{i}.1"
+        d[f"{a}.norm1.weight"] = (c,); d[f"{a}.norm1.bias"] = (c,)
+        d[f"{a}.norm2.weight"] = (c,); d[f"{a}.norm2.bias"] = (c,)
+        d[f"{a}.to_q.weight"] = (c, c)
+        d[f"{a}.to_kv.weight"] = (2 * c, c)
+        d[f"{a}.to_out.weight"] = (c, c)
+        d[f"{f}.0.weight"] = (c,); d[f"{f}.0.bias"] = (c,)
+        d[f"{f}.1.weight"] = (ff_mult * c, c)
+        d[f"{f}.3.weight"] = (c, ff_mult * c)
+    return d
+
+
 # PoseNet conv stack as (cin, cout, kernel, stride, pad)
 POSENET_CONVS = [(3, 3, 3, 1, 1), (3, 16, 4, 2, 1), (16, 16, 3, 1, 1), (16, 32, 4, 2, 1),
                  (32, 32, 3, 1, 1), (32, 64, 4, 2, 1), (64, 64, 3, 1, 1), (64, 128, 3, 1, 1)]

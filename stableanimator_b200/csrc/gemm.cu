@@ -500,6 +500,19 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
       mbar_arrive(&acc_empty[ab]);
       continue;
 #endif
+#ifdef SA_X_LDONLY
+      {  // read the accumulator (as the real epilogue does) and release it, nothing else
+        uint32_t uu[32];
+        for (int c = half; c < CPT; c += CSTRIDE) {
+          tmem_ld_32x32(acc + mma_col(c), uu);
+          tmem_ld_wait();
+          if (uu[3] == 0x7fc12345u && uu[7] == 0x1234567u) p.row_scale[0];
+        }
+        tc_fence_before();
+        mbar_arrive(&acc_empty[ab]);
+        continue;
+      }
+#endif
 
       uint32_t u[32], g[GEGLU ? 32 : 1];
       if (half < CPT) {
@@ -549,6 +562,8 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
 #pragma unroll
 #ifdef SA_X_NOGELU
           for (int j = 0; j < 16; ++j) v2[j] = mul2(v2[j], g2[j]);
+#elif defined(SA_X_HALFGELU)
+          for (int j = 0; j < 16; ++j) v2[j] = mul2(v2[j], (j & 1) ? g2[j] : gelu2(g2[j]));
 #else
           for (int j = 0; j < 16; ++j) v2[j] = mul2(v2[j], gelu2(g2[j]));
 #endif

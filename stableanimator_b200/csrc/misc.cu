@@ -9,6 +9,7 @@ namespace sa {
 
 // ------------------------------------------------------------------ skinny linear (M <= 16)
 // out[m, n] = act_out( sum_k act_in(x[m, k]) * W[n, k] + b[n] ).  One warp per output column.
+// act_out: 0 none, 1 SiLU, 2 exact GELU (FusionFaceId proj / FeedForward, id_encoder.py:57-64,116-120).
 // TimestepEmbedding (unet.py:429-436), time_emb_proj(silu(temb)) (:1669-1670, :1754-1755), the
 // K/V projections of the 5 context tokens (:1974-1975, :1999-2000, :1834-1835).
 template <int MT>
@@ -60,12 +61,74 @@ small_linear_kernel(const float* __restrict__ x, int ldx, int M, const __nv_bflo
     for (int m = 0; m < MT; ++m) {
       if (m0 + m < M) {
         float v = acc[m] + b;
-        if (silu_out) v = v / (1.0f + expf(-v));
+        if (silu_out == 1) v = v / (1.0f + expf(-v));
+        else if (silu_out == 2) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));  // exact GELU
         float* dst = out + static_cast<long long>(m0 + m) * ldo + n;
         *dst = accumulate ? *dst + v : v;
       }
     }
   }
+}
+
+// ------------------------------------------------------------------ FusionFaceId helpers (id_encoder.py)
+// The face-token encoder runs once per video on <= 10 rows of 1024 channels: fp32 activations, one warp per
+// row (LayerNorm) or per (batch, head, query) (PerceiverAttention).
+// LayerNorm over C on fp32 rows (id_encoder.py:24-25,34-35,59,78,125), two-pass variance.
+__global__ void layernorm_f32_kernel(const float* __restrict__ x, int ldx, int M, int C, const float* __restrict__ gamma,
+                                     const float* __restrict__ beta, float eps, float* __restrict__ y, int ldy) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float* xr = x + static_cast<long long>(row) * ldx;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += xr[c];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+  const float mean = s / static_cast<float>(C);
+  float v = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float dlt = xr[c] - mean;
+    v += dlt * dlt;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  const float rstd = rsqrtf(v / static_cast<float>(C) + eps);
+  float* yr = y + static_cast<long long>(row) * ldy;
+  for (int c = lane; c < C; c += 32) yr[c] = (xr[c] - mean) * rstd * gamma[c] + beta[c];
+}
+
+// PerceiverAttention core (id_encoder.py:48-55): out[b, l, h*64 + d] = softmax_n((q k^T) / 8) v, head_dim 64,
+// n <= 32 keys.  q fp32 [B, L, ldq]; k and v fp32 rows [B, N, ldkv] (k at column h*64, v at voff + h*64).
+// The reference scales q and k by 64^-1/4 each and takes the softmax in fp32 -- the same product.
+__global__ void perceiver_attn_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ kv, int ldkv,
+                                      int voff, int B, int L, int N, int heads, float* __restrict__ out, int ldo) {
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (w >= B * heads * L) return;
+  const int l = w % L, h = (w / L) % heads, b = w / (L * heads);
+  const float* qr = q + (static_cast<long long>(b) * L + l) * ldq + h * 64;
+  const float q0 = qr[lane], q1 = qr[lane + 32];
+  float sc[32];
+  float mx = -INFINITY;
+  for (int n = 0; n < N; ++n) {
+    const float* kr = kv + (static_cast<long long>(b) * N + n) * ldkv + h * 64;
+    float d = q0 * kr[lane] + q1 * kr[lane + 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    sc[n] = d * 0.125f;
+    mx = fmaxf(mx, sc[n]);
+  }
+  float den = 0.f, o0 = 0.f, o1 = 0.f;
+  for (int n = 0; n < N; ++n) {
+    const float pn = expf(sc[n] - mx);
+    const float* vr = kv + (static_cast<long long>(b) * N + n) * ldkv + voff + h * 64;
+    den += pn;
+    o0 += pn * vr[lane];
+    o1 += pn * vr[lane + 32];
+  }
+  float* orow = out + (static_cast<long long>(b) * L + l) * ldo + h * 64;
+  orow[lane] = o0 / den;
+  orow[lane + 32] = o1 / den;
 }
 
 // ------------------------------------------------------------------ sinusoidal embedding
@@ -322,6 +385,27 @@ extern "C" int sa_small_linear(const float* x, int32_t ldx, int32_t m, const voi
   } else {
     small_linear_kernel<8><<<dim3(gx, (m + 7) / 8), 256, 0, stream>>>(x, ldx, m, wp, k, n, bias, silu_in, silu_out, accumulate, out, ldo);
   }
+  SA_CUDA_CHECK(cudaGetLastError());
+  return SA_OK;
+}
+
+extern "C" int sa_layernorm_f32(const float* x, int32_t ldx, int32_t m, int32_t c, const float* gamma,
+                                const float* beta, float eps, float* y, int32_t ldy, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!x || !gamma || !beta || !y) return fail(SA_ERR_INVALID, "sa_layernorm_f32: null pointer");
+  if (m < 1 || c < 1 || ldx < c || ldy < c) return fail(SA_ERR_INVALID, "sa_layernorm_f32: bad sizes");
+  layernorm_f32_kernel<<<(m + 3) / 4, 128, 0, stream>>>(x, ldx, m, c, gamma, beta, eps, y, ldy);
+  SA_CUDA_CHECK(cudaGetLastError());
+  return SA_OK;
+}
+
+extern "C" int sa_perceiver_attn(const float* q, int32_t ldq, const float* kv, int32_t ldkv, int32_t voff, int32_t b,
+                                 int32_t l, int32_t n, int32_t heads, float* out, int32_t ldo, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!q || !kv || !out) return fail(SA_ERR_INVALID, "sa_perceiver_attn: null pointer");
+  if (b < 1 || l < 1 || n < 1 || n > 32 || heads < 1) return fail(SA_ERR_INVALID, "sa_perceiver_attn: n must be in [1, 32]");
+  const int warps = b * heads * l;
+  perceiver_attn_kernel<<<(warps + 3) / 4, 128, 0, stream>>>(q, ldq, kv, ldkv, voff, b, l, n, heads, out, ldo);
   SA_CUDA_CHECK(cudaGetLastError());
   return SA_OK;
 }

@@ -13,7 +13,7 @@ from typing import Dict, Tuple
 
 import torch
 
-from .arch import UNetConfig, posenet_param_shapes, unet_param_shapes
+from .arch import UNetConfig, face_param_shapes, posenet_param_shapes, unet_param_shapes
 
 
 def _gen(key: str, seed: int) -> torch.Generator:
@@ -33,7 +33,8 @@ def synth_tensor(key: str, shape: Tuple[int, ...], seed: int) -> torch.Tensor:
         t = torch.full(shape, 0.5) + 0.25 * (torch.rand(shape, generator=g) - 0.5)
     elif leaf == "scale":  # PoseNet output scale (pose_net.py:38)
         t = torch.full(shape, 2.0)
-    elif "norm" in key.rsplit(".", 2)[-2]:
+    elif "norm" in key.rsplit(".", 2)[-2] or (len(shape) == 1 and key.rsplit(".", 2)[-2] == "0" and ".layers." in key):
+        # LayerNorm / GroupNorm affine parameters (incl. the LayerNorm at index 0 of the perceiver FeedForward)
         if leaf == "weight":
             t = 1.0 + 0.1 * (torch.rand(shape, generator=g) * 2 - 1)
         else:
@@ -56,6 +57,19 @@ def synth_unet_state_dict(cfg: UNetConfig, seed: int = 23123134) -> Dict[str, to
 def synth_posenet_state_dict(noise_latent_channels: int = 320, seed: int = 23123134):
     return {k: synth_tensor("pose_net." + k, s, seed)
             for k, s in posenet_param_shapes(noise_latent_channels).items()}
+
+
+def synth_face_state_dict(seed: int = 23123134, **dims):
+    """FusionFaceId weights (animation/modules/id_encoder.py:102-131), keys as in its ``state_dict``."""
+    return {k: synth_tensor("face_encoder." + k, s, seed) for k, s in face_param_shapes(**dims).items()}
+
+
+def synth_face_inputs(batch: int = 1, seed: int = 23123134, id_dim: int = 512, clip_dim: int = 1024):
+    """ArcFace-like identity embedding [B, 512] and CLIP image embedding [B, 1, 1024] (ranges of
+    id_encoder.py:135-136)."""
+    ide = torch.randn(batch, id_dim, generator=_gen("input.id_embeds", seed))
+    clip = torch.randn(batch, 1, clip_dim, generator=_gen("input.clip_embeds", seed)) * 1.5
+    return bf16_round(ide), bf16_round(clip)
 
 
 def synth_inputs(cfg: UNetConfig, frames: int, h: int, w: int, seed: int = 23123134,

@@ -60,3 +60,17 @@ def test_oracle_batch2_equals_two_b1_calls():
     a = O.unet_forward(sd, cfg, s2[:1], c["t"], ehs2[:1], ati2[:1], None)
     b = O.unet_forward(sd, cfg, s2[1:], c["t"], ehs2[1:], ati2[1:], c["pose_latents"])
     assert ((both - torch.cat([a, b], 0)).abs().max() / both.abs().max()).item() < 1e-5
+
+
+def test_face_oracle_matches_reference_golden():
+    """FusionFaceId (id_encoder.py:102-148): oracle/face_oracle.py vs the reference output stored by
+    oracle/make_golden.py (same synthetic weights and embeddings, regenerated from the seed)."""
+    from pathlib import Path
+    from oracle import face_oracle
+    from stableanimator_b200.synth import synth_face_inputs, synth_face_state_dict
+    g = torch.load(Path(__file__).resolve().parent / "golden" / "face_fusion.pt", map_location="cpu", weights_only=False)
+    sd = synth_face_state_dict(g["seed"])
+    ide, clip = synth_face_inputs(g["batch"], g["seed"])
+    out = face_oracle.fusion_face_id(sd, ide, clip)
+    assert out.shape == g["out"].shape == (g["batch"], 4, 1024)
+    assert ((out - g["out"]).abs().max() / g["out"].abs().max()).item() < 2e-5
