@@ -156,6 +156,18 @@ int sa_layernorm_f32(const float* x, int32_t ldx, int32_t m, int32_t c, const fl
 int sa_perceiver_attn(const float* q, int32_t ldq, const float* kv, int32_t ldkv, int32_t voff, int32_t b,
                       int32_t l, int32_t n, int32_t heads, float* out, int32_t ldo, void* stream);
 
+/* Temporal VAE decoder (animation/modules/vae.py:387-479).  Its convolutions, GroupNorms, the
+ * temporal residual blocks and the q/k/v/out projections run on sa_gemm_tap / sa_groupnorm / sa_conv_direct /
+ * sa_upsample2x above; two helpers complete it:
+ * row softmax of the single-head mid-block attention (vae.py:92-94): scores fp32 [m, n] (Q K^T GEMM with
+ * out_f32) -> probabilities bf16 [m, n], p = softmax(scale * s). */
+int sa_softmax_rows(const float* s, int64_t lds, int32_t m, int32_t n, float scale, void* p, int64_t ldp,
+                    void* stream);
+/* time_conv_out (vae.py:423-429,470-475): Conv3d(c -> c, (3,1,1), zero padding over the f frames of each of the b
+ * clips).  x fp32 [b*f*hw, ldx] channel-innermost (first c columns) -> out fp32 NCHW [b*f, c, hw]; w [c, c, 3]. */
+int sa_time_conv_out(const float* x, int32_t ldx, int32_t b, int32_t f, int32_t hw, int32_t c, const float* w,
+                     const float* bias, float* out, void* stream);
+
 /* get_timestep_embedding (unet.py:365-390): out[i] = [cos(t_i f) | sin(t_i f)], fp32 [n, dim]. */
 int sa_sinusoid(const float* t, int32_t n, int32_t dim, float* out, void* stream);
 

@@ -86,6 +86,35 @@ def face_case():
     torch.save({"seed": SEED, "batch": 2, "out": out_ref.clone()}, GOLD / "face_fusion.pt")
 
 
+def vae_case():
+    """TemporalDecoder (vae.py:387-479) + decode_latents (inference_pipeline_animation.py:319-357): pins
+    oracle/vae_oracle.py and writes tests/golden/vae_decoder_tiny.pt (8 frames = two chunks of 4, 8x12 latent)."""
+    from oracle import vae_oracle
+    from stableanimator_b200.arch import VaeDecoderConfig
+    from stableanimator_b200.synth import synth_vae_decoder_state_dict, synth_vae_latents
+    ref_loader.import_reference()
+    import animation.modules.vae as ref_vae
+    cfg = VaeDecoderConfig.tiny()
+    sd = synth_vae_decoder_state_dict(cfg, SEED)
+    dec = ref_vae.TemporalDecoder(in_channels=cfg.in_channels, out_channels=cfg.out_channels,
+                                  block_out_channels=cfg.block_out_channels, layers_per_block=cfg.layers_per_block).eval()
+    dec.load_state_dict({k: v.clone() for k, v in sd.items()}, strict=True)
+    frames, h, w = 8, 8, 12
+    lat = synth_vae_latents(frames, h, w, SEED)
+    z = lat.flatten(0, 1) / cfg.scaling_factor
+    outs = []
+    with torch.no_grad():
+        for i in range(0, frames, 4):  # decode_latents chunks of 4 (vae.decode asserts num_frames == 4)
+            outs.append(dec(z[i:i + 4], image_only_indicator=torch.zeros(1, 4), num_frames=4))
+    out_ref = torch.cat(outs, 0).reshape(1, frames, 3, 8 * h, 8 * w).permute(0, 2, 1, 3, 4)
+    out_mine = vae_oracle.decode_latents(sd, cfg, lat, frames, 4)
+    e = rel(out_mine, out_ref)
+    print(f"[vae_decoder_tiny] oracle vs reference: {e:.2e}")
+    assert e < 1e-5
+    torch.save({"seed": SEED, "frames": frames, "h": h, "w": w, "out": out_ref.to(torch.float16).clone()},
+               GOLD / "vae_decoder_tiny.pt")
+
+
 def main():
     GOLD.mkdir(parents=True, exist_ok=True)
     torch.manual_seed(0)
@@ -102,3 +131,4 @@ def main():
 if __name__ == "__main__":
     main()
     face_case()
+    vae_case()

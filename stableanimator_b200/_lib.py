@@ -82,6 +82,8 @@ SIGNATURES: dict[str, list] = {
     "sa_layernorm": [_P, _I, _L, _I, _P, _I, _P, _I, _P, _P, _F, _P, _I, _P],
     "sa_small_linear": [_P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _P, _I, _P],
     "sa_sinusoid": [_P, _I, _I, _P, _P],
+    "sa_softmax_rows": [_P, _L, _I, _I, _F, _P, _L, _P],
+    "sa_time_conv_out": [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P],
     "sa_layernorm_f32": [_P, _I, _I, _I, _P, _P, _F, _P, _I, _P],
     "sa_perceiver_attn": [_P, _I, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P],
     "sa_conv_direct": [_P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _I, _P, _P],

@@ -233,6 +233,80 @@ def posenet_param_shapes(noise_latent_channels: int = 320) -> Dict[str, Tuple[in
     return d
 
 
+@dataclass
+class VaeDecoderConfig:
+    """TemporalDecoder of AutoencoderKLTemporalDecoder (animation/modules/vae.py:387-435)."""
+    in_channels: int = 4
+    out_channels: int = 3
+    block_out_channels: Tuple[int, ...] = (128, 256, 512, 512)
+    layers_per_block: int = 2
+    scaling_factor: float = 0.18215
+
+    @staticmethod
+    def full() -> "VaeDecoderConfig":
+        return VaeDecoderConfig()
+
+    @staticmethod
+    def tiny() -> "VaeDecoderConfig":
+        """Same graph, 4x narrower (channels stay multiples of 64 for the 64-channel TMA taps)."""
+        return VaeDecoderConfig(block_out_channels=(64, 64, 128, 128))
+
+
+def vae_decoder_blocks(cfg: VaeDecoderConfig):
+    """[(block name, [(resnet name, cin, cout)], upsampler name | None)] in execution order
+    (vae.py:395-416: mid block, then up blocks over the reversed channel list)."""
+    rev = list(reversed(cfg.block_out_channels))
+    c = rev[0]
+    blocks = [("mid_block", [(f"mid_block.resnets.{i}", c, c) for i in range(cfg.layers_per_block)], None)]
+    prev = c
+    for i, co in enumerate(rev):
+        res = [(f"up_blocks.{i}.resnets.{j}", prev if j == 0 else co, co) for j in range(cfg.layers_per_block + 1)]
+        up = f"up_blocks.{i}.upsamplers.0.conv" if i < len(rev) - 1 else None
+        blocks.append((f"up_blocks.{i}", res, up))
+        prev = co
+    return blocks
+
+
+def vae_decoder_param_shapes(cfg: VaeDecoderConfig) -> Dict[str, Tuple[int, ...]]:
+    """state_dict keys / shapes of the reference TemporalDecoder (vae.py:387-435,557-658,784-949)."""
+    d: Dict[str, Tuple[int, ...]] = {}
+    c_top = cfg.block_out_channels[-1]
+    d["conv_in.weight"] = (c_top, cfg.in_channels, 3, 3)
+    d["conv_in.bias"] = (c_top,)
+
+    def norm(n, c):
+        d[f"{n}.weight"] = (c,)
+        d[f"{n}.bias"] = (c,)
+
+    for _, res, up in vae_decoder_blocks(cfg):
+        for name, ci, co in res:
+            s_, t_ = f"{name}.spatial_res_block", f"{name}.temporal_res_block"
+            norm(f"{s_}.norm1", ci)
+            d[f"{s_}.conv1.weight"] = (co, ci, 3, 3); d[f"{s_}.conv1.bias"] = (co,)
+            norm(f"{s_}.norm2", co)
+            d[f"{s_}.conv2.weight"] = (co, co, 3, 3); d[f"{s_}.conv2.bias"] = (co,)
+            if ci != co:
+                d[f"{s_}.conv_shortcut.weight"] = (co, ci, 1, 1); d[f"{s_}.conv_shortcut.bias"] = (co,)
+            norm(f"{t_}.norm1", co)
+            d[f"{t_}.conv1.weight"] = (co, co, 3, 1, 1); d[f"{t_}.conv1.bias"] = (co,)
+            norm(f"{t_}.norm2", co)
+            d[f"{t_}.conv2.weight"] = (co, co, 3, 1, 1); d[f"{t_}.conv2.bias"] = (co,)
+            d[f"{name}.time_mixer.mix_factor"] = (1,)
+        if up:
+            co = res[-1][2]
+            d[f"{up}.weight"] = (co, co, 3, 3); d[f"{up}.bias"] = (co,)
+    a = "mid_block.attentions.0"
+    norm(f"{a}.group_norm", c_top)
+    for n in ("to_q", "to_k", "to_v", "to_out.0"):
+        d[f"{a}.{n}.weight"] = (c_top, c_top); d[f"{a}.{n}.bias"] = (c_top,)
+    c0 = cfg.block_out_channels[0]
+    norm("conv_norm_out", c0)
+    d["conv_out.weight"] = (cfg.out_channels, c0, 3, 3); d["conv_out.bias"] = (cfg.out_channels,)
+    d["time_conv_out.weight"] = (cfg.out_channels, cfg.out_channels, 3, 1, 1)
+    d["time_conv_out.bias"] = (cfg.out_channels,)
+    return d
+
+
 def face_param_shapes(cross_attention_dim: int = 1024, id_embeddings_dim: int = 512, clip_embeddings_dim: int = 1024,
                       num_tokens: int = 4, depth: int = 4, ff_mult: int = 4) -> Dict[str, Tuple[int, ...]]:
     """FusionFaceId (animation/modules/id_encoder.py:102-131) with its FacePerceiver (:66-92)."""

@@ -131,6 +131,53 @@ __global__ void perceiver_attn_kernel(const float* __restrict__ q, int ldq, cons
   orow[lane + 32] = o1 / den;
 }
 
+// ------------------------------------------------------------------ temporal VAE decoder helpers (vae.py)
+// Row softmax of the single-head, head_dim = C mid-block attention (vae.py:92-94): scores fp32 [M, N] from
+// the Q K^T GEMM -> probabilities bf16 [M, N] for the P V GEMM.  One warp per row, three L2-resident passes.
+__global__ void softmax_rows_kernel(const float* __restrict__ s, long long lds, int M, int N, float scale,
+                                    __nv_bfloat16* __restrict__ p, long long ldp) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float* sr = s + row * lds;
+  float mx = -INFINITY;
+  for (int c = lane; c < N; c += 32) mx = fmaxf(mx, sr[c]);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+  const float sl2 = scale * 1.4426950408889634f;
+  float sum = 0.f;
+  for (int c = lane; c < N; c += 32) sum += exp2f((sr[c] - mx) * sl2);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+  const float inv = 1.0f / sum;
+  __nv_bfloat16* pr = p + row * ldp;
+  for (int c = lane; c < N; c += 32) pr[c] = __float2bfloat16_rn(exp2f((sr[c] - mx) * sl2) * inv);
+}
+
+// time_conv_out (vae.py:423-429,470-475): Conv3d(C -> C, kernel (3,1,1), zero padding over frames) on the
+// conv_out result.  x fp32 [B*F*HW, ldx] (first C columns, channel-innermost) -> out fp32 NCHW [B*F, C, HW].
+__global__ void time_conv_out_kernel(const float* __restrict__ x, int ldx, int B, int F, int HW, int C,
+                                     const float* __restrict__ w, const float* __restrict__ bias,
+                                     float* __restrict__ out) {
+  const long long total = static_cast<long long>(B) * F * HW;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int pix = static_cast<int>(idx % HW);
+    const long long bf = idx / HW;
+    const int f = static_cast<int>(bf % F);
+    for (int co = 0; co < C; ++co) {
+      float acc = bias[co];
+      for (int kt = 0; kt < 3; ++kt) {
+        const int fi = f + kt - 1;
+        if (fi < 0 || fi >= F) continue;
+        const float* xr = x + ((bf - f + fi) * HW + pix) * ldx;
+        for (int ci = 0; ci < C; ++ci) acc += w[(co * C + ci) * 3 + kt] * xr[ci];
+      }
+      out[(bf * C + co) * HW + pix] = acc;
+    }
+  }
+}
+
 // ------------------------------------------------------------------ sinusoidal embedding
 // get_timestep_embedding (unet.py:365-390): out[i] = [cos(t_i f_k) | sin(t_i f_k)], f_k = 1e4^(-k/half)
 __global__ void sinusoid_kernel(const float* __restrict__ t, int n, int dim, float* __restrict__ out) {
@@ -406,6 +453,27 @@ extern "C" int sa_perceiver_attn(const float* q, int32_t ldq, const float* kv, i
   if (b < 1 || l < 1 || n < 1 || n > 32 || heads < 1) return fail(SA_ERR_INVALID, "sa_perceiver_attn: n must be in [1, 32]");
   const int warps = b * heads * l;
   perceiver_attn_kernel<<<(warps + 3) / 4, 128, 0, stream>>>(q, ldq, kv, ldkv, voff, b, l, n, heads, out, ldo);
+  SA_CUDA_CHECK(cudaGetLastError());
+  return SA_OK;
+}
+
+extern "C" int sa_softmax_rows(const float* s, int64_t lds, int32_t m, int32_t n, float scale, void* p, int64_t ldp,
+                               void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!s || !p) return fail(SA_ERR_INVALID, "sa_softmax_rows: null pointer");
+  if (m < 1 || n < 1 || lds < n || ldp < n) return fail(SA_ERR_INVALID, "sa_softmax_rows: bad sizes");
+  softmax_rows_kernel<<<(m + 7) / 8, 256, 0, stream>>>(s, lds, m, n, scale, static_cast<__nv_bfloat16*>(p), ldp);
+  SA_CUDA_CHECK(cudaGetLastError());
+  return SA_OK;
+}
+
+extern "C" int sa_time_conv_out(const float* x, int32_t ldx, int32_t b, int32_t f, int32_t hw, int32_t c, const float* w,
+                                const float* bias, float* out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!x || !w || !bias || !out) return fail(SA_ERR_INVALID, "sa_time_conv_out: null pointer");
+  if (b < 1 || f < 1 || hw < 1 || c < 1 || c > 8 || ldx < c) return fail(SA_ERR_INVALID, "sa_time_conv_out: bad sizes");
+  const long long total = static_cast<long long>(b) * f * hw;
+  time_conv_out_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x, ldx, b, f, hw, c, w, bias, out);
   SA_CUDA_CHECK(cudaGetLastError());
   return SA_OK;
 }

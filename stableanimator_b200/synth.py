@@ -13,7 +13,8 @@ from typing import Dict, Tuple
 
 import torch
 
-from .arch import UNetConfig, face_param_shapes, posenet_param_shapes, unet_param_shapes
+from .arch import (UNetConfig, VaeDecoderConfig, face_param_shapes, posenet_param_shapes, unet_param_shapes,
+                   vae_decoder_param_shapes)
 
 
 def _gen(key: str, seed: int) -> torch.Generator:
@@ -57,6 +58,16 @@ def synth_unet_state_dict(cfg: UNetConfig, seed: int = 23123134) -> Dict[str, to
 def synth_posenet_state_dict(noise_latent_channels: int = 320, seed: int = 23123134):
     return {k: synth_tensor("pose_net." + k, s, seed)
             for k, s in posenet_param_shapes(noise_latent_channels).items()}
+
+
+def synth_vae_decoder_state_dict(cfg: VaeDecoderConfig, seed: int = 23123134):
+    """TemporalDecoder weights (animation/modules/vae.py:387-435), keys as in its ``state_dict``."""
+    return {k: synth_tensor("vae.decoder." + k, s, seed) for k, s in vae_decoder_param_shapes(cfg).items()}
+
+
+def synth_vae_latents(frames: int, h: int, w: int, seed: int = 23123134) -> torch.Tensor:
+    """Denoised latents [1, F, 4, h, w] in the sampler's scale (|z| ~ 1; the decoder divides by 0.18215)."""
+    return bf16_round(torch.randn(1, frames, 4, h, w, generator=_gen("input.vae_latents", seed)))
 
 
 def synth_face_state_dict(seed: int = 23123134, **dims):

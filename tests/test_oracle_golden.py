@@ -74,3 +74,20 @@ def test_face_oracle_matches_reference_golden():
     out = face_oracle.fusion_face_id(sd, ide, clip)
     assert out.shape == g["out"].shape == (g["batch"], 4, 1024)
     assert ((out - g["out"]).abs().max() / g["out"].abs().max()).item() < 2e-5
+
+
+def test_vae_oracle_matches_reference_golden():
+    """TemporalDecoder + decode_latents (vae.py:387-479, inference_pipeline_animation.py:319-357): the oracle
+    vs the reference frames stored (as fp16) by oracle/make_golden.py."""
+    from pathlib import Path
+    from oracle import vae_oracle
+    from stableanimator_b200.arch import VaeDecoderConfig
+    from stableanimator_b200.synth import synth_vae_decoder_state_dict, synth_vae_latents
+    g = torch.load(Path(__file__).resolve().parent / "golden" / "vae_decoder_tiny.pt", map_location="cpu", weights_only=False)
+    cfg = VaeDecoderConfig.tiny()
+    sd = synth_vae_decoder_state_dict(cfg, g["seed"])
+    lat = synth_vae_latents(g["frames"], g["h"], g["w"], g["seed"])
+    out = vae_oracle.decode_latents(sd, cfg, lat, g["frames"], 4)
+    ref = g["out"].float()
+    assert out.shape == ref.shape == (1, 3, g["frames"], 8 * g["h"], 8 * g["w"])
+    assert ((out - ref).abs().max() / ref.abs().max()).item() < 1e-3  # fp16 storage of the fixture
