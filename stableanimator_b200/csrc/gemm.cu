@@ -14,6 +14,12 @@
 //
 // Replaces: nn.Linear / nn.Conv2d 3x3 & 1x1 / nn.Conv3d (3,1,1) call sites of
 // animation/modules/unet.py (see include/sa_b200.h for the per-site citations).
+//
+// Ablation knobs (compile-time, off in the product build; `nvcc -DSA_X_...` on this file only):
+//   SA_X_NOEPI    epilogue warps only release the accumulator  -> main-loop (TMA + MMA) time
+//   SA_X_LDONLY   ... after reading it with tcgen05.ld          -> + TMEM read
+//   SA_X_NOSTORE  full epilogue without the TMA store           -> cost of the store path
+//   SA_X_NOGELU / SA_X_HALFGELU  GEGLU without / with half of the GELUs -> MUFU / issue sensitivity
 #include <stdlib.h>
 
 #include "common.cuh"

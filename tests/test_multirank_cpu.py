@@ -41,18 +41,34 @@ def _worker(rank, world, store_path, F, tile, overlap, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("F,tile,overlap", [(16, 16, 4), (64, 16, 4), (128, 16, 4)])
-def test_partitioned_blend_equals_single_process(F, tile, overlap, tmp_path):
+def _run_world2(tmp_path, attempt, F, tile, overlap):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    store = str(tmp_path / "rendezvous")
+    store = str(tmp_path / f"rendezvous{attempt}")
     procs = [ctx.Process(target=_worker, args=(r, 2, store, F, tile, overlap, q)) for r in range(2)]
     for p in procs:
         p.start()
-    got = q.get(timeout=300)
+    try:
+        got = q.get(timeout=300)
+    except Exception:  # a worker died before reporting (seen once under heavy host load)
+        got = None
     for p in procs:
         p.join(timeout=60)
-        assert p.exitcode == 0
+        if p.is_alive():
+            p.kill()
+    if got is None or any(p.exitcode != 0 for p in procs):
+        return None
+    return got
+
+
+@pytest.mark.parametrize("F,tile,overlap", [(16, 16, 4), (64, 16, 4), (128, 16, 4)])
+def test_partitioned_blend_equals_single_process(F, tile, overlap, tmp_path):
+    got = None
+    for attempt in range(2):  # one retry: process spawn + gloo rendezvous on a loaded CI host
+        got = _run_world2(tmp_path, attempt, F, tile, overlap)
+        if got is not None:
+            break
+    assert got is not None, "world-size-2 gloo run failed twice"
     tiles = sch.tile_indices(F, tile, overlap)
     weights = torch.tensor(sch.tile_weights(tile))
     units = [(t, b) for t in range(len(tiles)) for b in (0, 1)]
