@@ -454,31 +454,41 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
     // lane 0 prepares the staging slots of this warp's chunks strictly in order (chunk 0, 1, 2, ...),
     // two chunks ahead of their use: TMA-load the residual / blend sub-boxes, or just mark the slot free
     int nx_g = 0, nx_tile = blockIdx.x, nx_c = half;
+    int nx_n0 = 0, nx_q1 = 0, nx_q2 = 0, nx_q3 = 0;  // tile coordinates of nx_tile (div/mod chain once per tile)
+    bool nx_fresh = true;
     auto issue_next = [&]() {
       if (nx_g >= total_chunks) return;
-      int n0, q1, q2, q3;
-      tile_origin(nx_tile, n0, q1, q2, q3);
-      const int col = (GEGLU ? n0 / 2 : n0) + nx_c * EPI_CHUNK;
+      if (nx_fresh) {
+        tile_origin(nx_tile, nx_n0, nx_q1, nx_q2, nx_q3);
+        nx_fresh = false;
+      }
+      const int col = (GEGLU ? nx_n0 / 2 : nx_n0) + nx_c * EPI_CHUNK;
       const int slot = nx_g % EPI_RO_SLOTS;
       if (p.residual) {
         mbar_expect_tx(&ro_ready[slot], EPI_TILE_BYTES);
-        tma_load_4d(sRO + slot * EPI_TILE_BYTES, &tmRes, &ro_ready[slot], col, q1 + w1, q2 + w2, q3 + w3);
+        tma_load_4d(sRO + slot * EPI_TILE_BYTES, &tmRes, &ro_ready[slot], col, nx_q1 + w1, nx_q2 + w2, nx_q3 + w3);
       } else {
         mbar_arrive(&ro_ready[slot]);
       }
       if (p.blend_x) {
         const int xs = nx_g % EPI_X_SLOTS;
         mbar_expect_tx(&x_ready[xs], EPI_TILE_BYTES);
-        tma_load_4d(sX + xs * EPI_TILE_BYTES, &tmBld, &x_ready[xs], col, q1 + w1, q2 + w2, q3 + w3);
+        tma_load_4d(sX + xs * EPI_TILE_BYTES, &tmBld, &x_ready[xs], col, nx_q1 + w1, nx_q2 + w2, nx_q3 + w3);
       }
       ++nx_g;
       nx_c += CSTRIDE;
       if (nx_c >= CPT) {
         nx_c = half;
         nx_tile += gridDim.x;
+        nx_fresh = true;
       }
     };
-    if (lane == 0) {
+    // Without residual / blend operands nothing is prefetched into the staging slots: a slot is free as soon
+    // as the store issued from it two chunks ago has read it (wait_group.read below), so the whole
+    // issue_next / ro_ready machinery (two div/mod chains and a barrier round trip per chunk -- the short-K
+    // GEMMs are issue-bound) is skipped.
+    const bool staged = (p.residual != nullptr) || (p.blend_x != nullptr);
+    if (lane == 0 && staged) {
       issue_next();
       issue_next();
     }
@@ -591,7 +601,7 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
         }
         // staging slot of this chunk: holds the residual sub-box (if any) and is free for our output
         const int slot = gc % EPI_RO_SLOTS;
-        mbar_wait(&ro_ready[slot], (gc / EPI_RO_SLOTS) & 1);
+        if (staged) mbar_wait(&ro_ready[slot], (gc / EPI_RO_SLOTS) & 1);
         uint8_t* ro = my_ro + slot * EPI_TILE_BYTES;
         if (p.residual) {
 #pragma unroll
@@ -639,7 +649,7 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
           tma_store_commit();
           // the slot of chunk gc-1 (== slot of chunk gc+2) is reusable once its store has read smem
           tma_store_wait_read<1>();
-          issue_next();
+          if (staged) issue_next();
         }
         __syncwarp();
       }
