@@ -183,6 +183,10 @@ int sa_conv_direct(const void* x, int32_t n, int32_t h, int32_t w, int32_t cin, 
 int sa_upsample2x(const void* in, int32_t n, int32_t h, int32_t w, int32_t c, void* out, void* stream);
 /* im2col of the 3x3 stride-2 pad-1 Downsample2D conv (unet.py:1474): out bf16 [n*h/2*w/2, 9*c]. */
 int sa_im2col_s2(const void* in, int32_t n, int32_t h, int32_t w, int32_t c, void* out, void* stream);
+/* same gather with selectable padding: pad = 1 as above; pad = 0 is the VAE encoder's Downsample2D
+ * (F.pad(x, (0,1,0,1)) then a padding-0 stride-2 conv, vae.py:731-741). */
+int sa_im2col_s2_pad(const void* in, int32_t n, int32_t h, int32_t w, int32_t c, int32_t pad, void* out,
+                     void* stream);
 /* im2col of conv_in (3x3, pad 1, 8 input channels; unet.py:69,283): in bf16 [n, h, w, 8] ->
  * out bf16 [n*h*w, 128] = 72 gathered values (ky, kx, ci) + 56 zeros, the K = 128 operand of sa_gemm_tap. */
 int sa_im2col3x3_c8(const void* in, int32_t n, int32_t h, int32_t w, void* out, void* stream);

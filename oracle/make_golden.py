@@ -115,6 +115,29 @@ def vae_case():
                GOLD / "vae_decoder_tiny.pt")
 
 
+def vae_encoder_case():
+    """Encoder + quant_conv + latent_dist.mode() (vae.py:236-256,482-556; inference_pipeline_animation.py:257):
+    pins oracle/vae_oracle.vae_encode_mode and writes tests/golden/vae_encoder_tiny.pt."""
+    from oracle import vae_oracle
+    from stableanimator_b200.arch import VaeDecoderConfig
+    from stableanimator_b200.synth import synth_image, synth_vae_encoder_state_dict
+    ref_loader.import_reference()
+    import animation.modules.vae as ref_vae
+    cfg = VaeDecoderConfig.tiny()
+    sd = synth_vae_encoder_state_dict(cfg, SEED)
+    vae = ref_vae.AutoencoderKLTemporalDecoder(block_out_channels=list(cfg.block_out_channels)).eval()
+    missing, unexpected = vae.load_state_dict({k: v.clone() for k, v in sd.items()}, strict=False)
+    assert not unexpected and all(k.startswith("decoder.") for k in missing)
+    img = synth_image(64, 96, SEED, batch=2)
+    with torch.no_grad():
+        out_ref = vae.encode(img).latent_dist.mode()
+    out_mine = vae_oracle.vae_encode_mode(sd, cfg, img)
+    e = rel(out_mine, out_ref)
+    print(f"[vae_encoder_tiny] oracle vs reference: {e:.2e}")
+    assert e < 1e-5
+    torch.save({"seed": SEED, "h": 64, "w": 96, "batch": 2, "out": out_ref.clone()}, GOLD / "vae_encoder_tiny.pt")
+
+
 def main():
     GOLD.mkdir(parents=True, exist_ok=True)
     torch.manual_seed(0)
@@ -132,3 +155,4 @@ if __name__ == "__main__":
     main()
     face_case()
     vae_case()
+    vae_encoder_case()

@@ -15,7 +15,7 @@ from typing import Dict
 import torch
 import torch.nn.functional as F
 
-from stableanimator_b200.arch import VaeDecoderConfig, vae_decoder_blocks
+from stableanimator_b200.arch import VaeDecoderConfig, vae_decoder_blocks, vae_encoder_blocks
 
 SD = Dict[str, torch.Tensor]
 
@@ -95,3 +95,28 @@ def decode_latents(sd: SD, cfg: VaeDecoderConfig, latents: torch.Tensor, num_fra
         frames.append(temporal_decoder(sd, cfg, chunk, chunk.shape[0]))
     frames = torch.cat(frames, dim=0)
     return frames.reshape(-1, num_frames, *frames.shape[1:]).permute(0, 2, 1, 3, 4).float()
+
+
+def vae_encode_moments(sd: SD, cfg: VaeDecoderConfig, image: torch.Tensor) -> torch.Tensor:
+    """AutoencoderKLTemporalDecoder.encode up to the posterior parameters (vae.py:253-256): Encoder.forward
+    (vae.py:537-555: conv_in, DownEncoderBlock2D x4 with Downsample2D = F.pad(0,1,0,1) + stride-2 conv (:731-741),
+    UNetMidBlock2D (:380-384), GroupNorm + SiLU + conv_out) followed by quant_conv.  image [B, 3, H, W] ->
+    moments [B, 8, H/8, W/8] (mean | logvar)."""
+    x = F.conv2d(image, sd["encoder.conv_in.weight"], sd["encoder.conv_in.bias"], padding=1)
+    for res, down in vae_encoder_blocks(cfg):
+        for name, _, _ in res:
+            x = resnet_block_2d(sd, f"encoder.{name}", x)
+        if down:
+            x = F.conv2d(F.pad(x, (0, 1, 0, 1)), sd[f"encoder.{down}.weight"], sd[f"encoder.{down}.bias"], stride=2)
+    x = resnet_block_2d(sd, "encoder.mid_block.resnets.0", x)
+    x = attention(sd, "encoder.mid_block.attentions.0", x)
+    x = resnet_block_2d(sd, "encoder.mid_block.resnets.1", x)
+    x = F.conv2d(F.silu(_gn(sd, "encoder.conv_norm_out", x, 1e-6)), sd["encoder.conv_out.weight"],
+                 sd["encoder.conv_out.bias"], padding=1)
+    return F.conv2d(x, sd["quant_conv.weight"], sd["quant_conv.bias"])
+
+
+def vae_encode_mode(sd: SD, cfg: VaeDecoderConfig, image: torch.Tensor) -> torch.Tensor:
+    """``vae.encode(image).latent_dist.mode()`` (inference_pipeline_animation.py:257; vae.py:183,203-204):
+    the mean half of the moments, [B, 4, H/8, W/8]."""
+    return vae_encode_moments(sd, cfg, image).chunk(2, dim=1)[0]

@@ -89,6 +89,7 @@ SIGNATURES: dict[str, list] = {
     "sa_conv_direct": [_P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _I, _P, _P],
     "sa_upsample2x": [_P, _I, _I, _I, _I, _P, _P],
     "sa_im2col_s2": [_P, _I, _I, _I, _I, _P, _P],
+    "sa_im2col_s2_pad": [_P, _I, _I, _I, _I, _I, _P, _P],
     "sa_im2col3x3_c8": [_P, _I, _I, _I, _P, _P],
     "sa_nchw_to_nhwc": [_P, _I, _I, _I, _I, _P, _P],
     "sa_nhwc_to_nchw_f32": [_P, _I, _I, _I, _I, _P, _P],

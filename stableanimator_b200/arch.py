@@ -307,6 +307,52 @@ def vae_decoder_param_shapes(cfg: VaeDecoderConfig) -> Dict[str, Tuple[int, ...]
     return d
 
 
+def vae_encoder_blocks(cfg: VaeDecoderConfig):
+    """[(resnet names with (cin, cout)), downsampler name | None] per DownEncoderBlock2D (vae.py:500-517)."""
+    blocks, prev = [], cfg.block_out_channels[0]
+    for i, co in enumerate(cfg.block_out_channels):
+        res = [(f"down_blocks.{i}.resnets.{j}", prev if j == 0 else co, co) for j in range(cfg.layers_per_block)]
+        down = f"down_blocks.{i}.downsamplers.0.conv" if i < len(cfg.block_out_channels) - 1 else None
+        blocks.append((res, down))
+        prev = co
+    return blocks
+
+
+def vae_encoder_param_shapes(cfg: VaeDecoderConfig, image_channels: int = 3) -> Dict[str, Tuple[int, ...]]:
+    """state_dict keys / shapes of ``Encoder`` (vae.py:482-556, keys prefixed ``encoder.``) plus ``quant_conv``
+    (vae.py:247) of the reference AutoencoderKLTemporalDecoder."""
+    d: Dict[str, Tuple[int, ...]] = {}
+    c0, ct = cfg.block_out_channels[0], cfg.block_out_channels[-1]
+    d["encoder.conv_in.weight"] = (c0, image_channels, 3, 3)
+    d["encoder.conv_in.bias"] = (c0,)
+
+    def resnet(n, ci, co):
+        d[f"{n}.norm1.weight"] = (ci,); d[f"{n}.norm1.bias"] = (ci,)
+        d[f"{n}.conv1.weight"] = (co, ci, 3, 3); d[f"{n}.conv1.bias"] = (co,)
+        d[f"{n}.norm2.weight"] = (co,); d[f"{n}.norm2.bias"] = (co,)
+        d[f"{n}.conv2.weight"] = (co, co, 3, 3); d[f"{n}.conv2.bias"] = (co,)
+        if ci != co:
+            d[f"{n}.conv_shortcut.weight"] = (co, ci, 1, 1); d[f"{n}.conv_shortcut.bias"] = (co,)
+
+    for res, down in vae_encoder_blocks(cfg):
+        for name, ci, co in res:
+            resnet(f"encoder.{name}", ci, co)
+        if down:
+            co = res[-1][2]
+            d[f"encoder.{down}.weight"] = (co, co, 3, 3); d[f"encoder.{down}.bias"] = (co,)
+    for j in range(2):
+        resnet(f"encoder.mid_block.resnets.{j}", ct, ct)
+    a = "encoder.mid_block.attentions.0"
+    d[f"{a}.group_norm.weight"] = (ct,); d[f"{a}.group_norm.bias"] = (ct,)
+    for n in ("to_q", "to_k", "to_v", "to_out.0"):
+        d[f"{a}.{n}.weight"] = (ct, ct); d[f"{a}.{n}.bias"] = (ct,)
+    d["encoder.conv_norm_out.weight"] = (ct,); d["encoder.conv_norm_out.bias"] = (ct,)
+    d["encoder.conv_out.weight"] = (2 * cfg.in_channels, ct, 3, 3); d["encoder.conv_out.bias"] = (2 * cfg.in_channels,)
+    d["quant_conv.weight"] = (2 * cfg.in_channels, 2 * cfg.in_channels, 1, 1)
+    d["quant_conv.bias"] = (2 * cfg.in_channels,)
+    return d
+
+
 def face_param_shapes(cross_attention_dim: int = 1024, id_embeddings_dim: int = 512, clip_embeddings_dim: int = 1024,
                       num_tokens: int = 4, depth: int = 4, ff_mult: int = 4) -> Dict[str, Tuple[int, ...]]:
     """FusionFaceId (animation/modules/id_encoder.py:102-131) with its FacePerceiver (:66-92)."""

@@ -71,3 +71,9 @@ def load_vae_decoder(path: PathLike, cfg: Optional[VaeDecoderConfig] = None, dev
     if any(k.startswith("decoder.") for k in sd):
         sd = {k[len("decoder."):]: v for k, v in sd.items() if k.startswith("decoder.")}
     return TemporalDecoderB200(cfg or VaeDecoderConfig.full(), sd, device)
+
+
+def load_vae_encoder(path: PathLike, cfg: Optional[VaeDecoderConfig] = None, device="cuda"):
+    """SVD ``vae/diffusion_pytorch_model.safetensors`` -> VaeEncoderB200 (takes ``encoder.*`` and ``quant_conv.*``)."""
+    from .vae_encoder import VaeEncoderB200
+    return VaeEncoderB200(cfg or VaeDecoderConfig.full(), read_state_dict(path), device)

@@ -268,7 +268,9 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ in, int N, int H, in
 
 // ------------------------------------------------------------------ im2col for 3x3 stride 2 pad 1
 // Downsample2D conv (unet.py:1474): out[(n, yo, xo), tap*C + c] = in[n, 2yo+ky-1, 2xo+kx-1, c] | 0
-__global__ void im2col_s2_kernel(const uint4* __restrict__ in, int N, int H, int W, int C8,
+// pad = 1: symmetric zero padding (UNet Downsample2D); pad = 0: F.pad(x, (0, 1, 0, 1)) + padding-0 conv of the
+// VAE encoder's Downsample2D (vae.py:731-741) -- taps reach one pixel past the right / bottom edge only.
+__global__ void im2col_s2_kernel(const uint4* __restrict__ in, int N, int H, int W, int C8, int pad,
                                  uint4* __restrict__ out) {
   const int Ho = H >> 1, Wo = W >> 1;
   const long long total = static_cast<long long>(N) * Ho * Wo * 9 * C8;
@@ -282,7 +284,7 @@ __global__ void im2col_s2_kernel(const uint4* __restrict__ in, int N, int H, int
     p /= Wo;
     const int yo = static_cast<int>(p % Ho);
     const long long n = p / Ho;
-    const int yi = 2 * yo + tap / 3 - 1, xi = 2 * xo + tap % 3 - 1;
+    const int yi = 2 * yo + tap / 3 - pad, xi = 2 * xo + tap % 3 - pad;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
     if (yi >= 0 && yi < H && xi >= 0 && xi < W) v = __ldg(in + ((n * H + yi) * W + xi) * C8 + c);
     out[idx] = v;
@@ -520,7 +522,19 @@ extern "C" int sa_im2col_s2(const void* in, int32_t n, int32_t h, int32_t w, int
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!in || !out || c % 8 || h % 2 || w % 2) return fail(SA_ERR_INVALID, "sa_im2col_s2: bad arguments");
   const long long total = static_cast<long long>(n) * (h / 2) * (w / 2) * 9 * (c / 8);
-  im2col_s2_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const uint4*>(in), n, h, w, c / 8,
+  im2col_s2_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const uint4*>(in), n, h, w, c / 8, 1,
+                                                            static_cast<uint4*>(out));
+  SA_CUDA_CHECK(cudaGetLastError());
+  return SA_OK;
+}
+
+extern "C" int sa_im2col_s2_pad(const void* in, int32_t n, int32_t h, int32_t w, int32_t c, int32_t pad, void* out,
+                                void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!in || !out || c % 8 || h % 2 || w % 2 || pad < 0 || pad > 1)
+    return fail(SA_ERR_INVALID, "sa_im2col_s2_pad: bad arguments");
+  const long long total = static_cast<long long>(n) * (h / 2) * (w / 2) * 9 * (c / 8);
+  im2col_s2_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const uint4*>(in), n, h, w, c / 8, pad,
                                                             static_cast<uint4*>(out));
   SA_CUDA_CHECK(cudaGetLastError());
   return SA_OK;

@@ -301,12 +301,16 @@ def upsample2x(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Ten
     return out
 
 
-def im2col_s2(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def im2col_s2(x: torch.Tensor, out: Optional[torch.Tensor] = None, pad: int = 1) -> torch.Tensor:
+    """3x3 stride-2 gather: pad=1 symmetric (UNet), pad=0 = F.pad(x, (0, 1, 0, 1)) (VAE encoder)."""
     _chk_bf16(x, "x")
     n, h, w, c = x.shape
     if out is None:
         out = torch.empty((n * (h // 2) * (w // 2), 9 * c), device=x.device, dtype=torch.bfloat16)
-    check(lib().sa_im2col_s2(x.data_ptr(), n, h, w, c, out.data_ptr(), _stream()), "sa_im2col_s2")
+    if pad == 1:
+        check(lib().sa_im2col_s2(x.data_ptr(), n, h, w, c, out.data_ptr(), _stream()), "sa_im2col_s2")
+    else:
+        check(lib().sa_im2col_s2_pad(x.data_ptr(), n, h, w, c, pad, out.data_ptr(), _stream()), "sa_im2col_s2_pad")
     return out
 
 

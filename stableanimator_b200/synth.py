@@ -14,7 +14,7 @@ from typing import Dict, Tuple
 import torch
 
 from .arch import (UNetConfig, VaeDecoderConfig, face_param_shapes, posenet_param_shapes, unet_param_shapes,
-                   vae_decoder_param_shapes)
+                   vae_decoder_param_shapes, vae_encoder_param_shapes)
 
 
 def _gen(key: str, seed: int) -> torch.Generator:
@@ -63,6 +63,19 @@ def synth_posenet_state_dict(noise_latent_channels: int = 320, seed: int = 23123
 def synth_vae_decoder_state_dict(cfg: VaeDecoderConfig, seed: int = 23123134):
     """TemporalDecoder weights (animation/modules/vae.py:387-435), keys as in its ``state_dict``."""
     return {k: synth_tensor("vae.decoder." + k, s, seed) for k, s in vae_decoder_param_shapes(cfg).items()}
+
+
+def synth_vae_encoder_state_dict(cfg: VaeDecoderConfig, seed: int = 23123134):
+    """``encoder.*`` + ``quant_conv.*`` of AutoencoderKLTemporalDecoder (vae.py:236-247,482-556)."""
+    return {k: synth_tensor("vae." + k, s, seed) for k, s in vae_encoder_param_shapes(cfg).items()}
+
+
+def synth_image(h: int, w: int, seed: int = 23123134, batch: int = 1) -> torch.Tensor:
+    """Reference image in [-1, 1] (smooth low-frequency pattern + noise), [B, 3, H, W]."""
+    g = _gen("input.image", seed)
+    base = torch.nn.functional.interpolate(torch.randn(batch, 3, max(h // 16, 1), max(w // 16, 1), generator=g),
+                                           size=(h, w), mode="bilinear", align_corners=False)
+    return bf16_round((0.6 * base + 0.1 * torch.randn(batch, 3, h, w, generator=g)).clamp(-1, 1))
 
 
 def synth_vae_latents(frames: int, h: int, w: int, seed: int = 23123134) -> torch.Tensor:

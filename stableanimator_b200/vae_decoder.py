@@ -121,9 +121,9 @@ class TemporalDecoderB200:
         return ops.gemm_tap(n4, w[f"{t_}.conv2.w"], grid=gridt, taps=ops.TAPS_T3, bias=w[f"{t_}.conv2.b"],
                             residual=xs, out_scale=w[f"{name}.s"])
 
-    def _attention(self, x, BF, S):
+    def _attention(self, x, BF, S, a="mid_block.attentions.0"):
         """Attention.forward (vae.py:60-111): one head of dimension C over the S tokens of each frame."""
-        w, a = self.w, "mid_block.attentions.0"
+        w = self.w
         c = x.shape[-1]
         n = ops.groupnorm(x, w[f"{a}.group_norm.g"], w[f"{a}.group_norm.b"], 1e-6, S, silu=False)
         q = ops.gemm_tap(n, w[f"{a}.to_q.w"], bias=w[f"{a}.to_q.b"])

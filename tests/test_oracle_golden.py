@@ -91,3 +91,17 @@ def test_vae_oracle_matches_reference_golden():
     ref = g["out"].float()
     assert out.shape == ref.shape == (1, 3, g["frames"], 8 * g["h"], 8 * g["w"])
     assert ((out - ref).abs().max() / ref.abs().max()).item() < 1e-3  # fp16 storage of the fixture
+
+
+def test_vae_encoder_oracle_matches_reference_golden():
+    """Encoder + quant_conv + latent_dist.mode() (vae.py:236-256,482-556): oracle vs the stored reference output."""
+    from pathlib import Path
+    from oracle import vae_oracle
+    from stableanimator_b200.arch import VaeDecoderConfig
+    from stableanimator_b200.synth import synth_image, synth_vae_encoder_state_dict
+    g = torch.load(Path(__file__).resolve().parent / "golden" / "vae_encoder_tiny.pt", map_location="cpu", weights_only=False)
+    cfg = VaeDecoderConfig.tiny()
+    sd = synth_vae_encoder_state_dict(cfg, g["seed"])
+    out = vae_oracle.vae_encode_mode(sd, cfg, synth_image(g["h"], g["w"], g["seed"], batch=g["batch"]))
+    assert out.shape == g["out"].shape == (g["batch"], 4, g["h"] // 8, g["w"] // 8)
+    assert ((out - g["out"]).abs().max() / g["out"].abs().max()).item() < 2e-5

@@ -77,3 +77,38 @@ def test_vae_decoder_forward_signature_and_strictness():
     assert y.shape == (4, 3, 64, 64) and torch.isfinite(y).all()
     with pytest.raises(ValueError):
         dec(z, None, num_frames=3)
+
+
+def test_im2col_s2_pad0_matches_asymmetric_pad_conv():
+    """sa_im2col_s2_pad(pad=0) + GEMM == F.pad(x, (0,1,0,1)) + stride-2 conv (Downsample2D, vae.py:731-741)."""
+    from stableanimator_b200 import ops
+    n, h, w, c, co = 2, 12, 16, 64, 64
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(n, h, w, c, generator=g, device="cuda").bfloat16()
+    wt = (torch.randn(co, c, 3, 3, generator=g, device="cuda") * (9 * c) ** -0.5).bfloat16()
+    cols = ops.im2col_s2(x, pad=0)
+    out = ops.gemm_tap(cols, wt.permute(0, 2, 3, 1).reshape(co, -1).contiguous())
+    ref = F.conv2d(F.pad(x.float().permute(0, 3, 1, 2), (0, 1, 0, 1)), wt.float(), stride=2)
+    assert_close(out, ref.permute(0, 2, 3, 1).reshape(-1, co), what="downsample pad (0,1,0,1)")
+
+
+def test_vae_encoder_matches_oracle_and_reference_golden():
+    from oracle import vae_oracle
+    from stableanimator_b200.arch import VaeDecoderConfig
+    from stableanimator_b200.synth import synth_image, synth_vae_encoder_state_dict
+    from stableanimator_b200.vae_encoder import VaeEncoderB200
+    g = torch.load(Path(__file__).resolve().parent / "golden" / "vae_encoder_tiny.pt", map_location="cpu", weights_only=False)
+    cfg = VaeDecoderConfig.tiny()
+    sd = synth_vae_encoder_state_dict(cfg, g["seed"])
+    img = synth_image(g["h"], g["w"], g["seed"], batch=g["batch"])
+    enc = VaeEncoderB200(cfg, sd, "cuda")
+    out = enc.encode_mode(img.cuda()).cpu()
+    ref = vae_oracle.vae_encode_mode(sd, cfg, img)
+    l2 = rel_l2(out, ref)
+    print(f"vae encoder rel-L2 vs fp32 oracle: {l2:.3e}; vs reference golden: {rel_l2(out, g['out']):.3e}")
+    assert out.shape == ref.shape and out.dtype == torch.float32
+    assert l2 <= 2.5e-2 and rel_l2(out, g["out"]) <= 2.5e-2   # bf16 activations through 11 residual blocks
+    bad = dict(sd)
+    bad.pop("quant_conv.bias")
+    with pytest.raises(KeyError):
+        VaeEncoderB200(cfg, bad, "cuda")
