@@ -313,7 +313,10 @@ struct Gemm2Smem {
 // EW = number of epilogue warps: 8 (two per TMEM quadrant, alternating chunks) for short-K problems
 // whose epilogue must keep up with a short main loop, 4 (less staging smem -> one more pipeline stage)
 // for long-K problems.
-template <int BN, int STAGES, bool GEGLU, int EW>
+// PLAIN: the epilogue is bias (+ GEGLU) only -- no row scale / row bias / output scale / residual / blend /
+// fp16 block.  The short-K GEMMs are bound by the sub-partition issue port, so the instantiation without the
+// per-chunk feature tests and the staging-slot machinery is worth having for the launches that need nothing else.
+template <int BN, int STAGES, bool GEGLU, int EW, bool PLAIN>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                         const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
@@ -487,12 +490,12 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
     // as the store issued from it two chunks ago has read it (wait_group.read below), so the whole
     // issue_next / ro_ready machinery (two div/mod chains and a barrier round trip per chunk -- the short-K
     // GEMMs are issue-bound) is skipped.
-    const bool staged = (p.residual != nullptr) || (p.blend_x != nullptr);
+    const bool staged = !PLAIN && ((p.residual != nullptr) || (p.blend_x != nullptr));
     if (lane == 0 && staged) {
       issue_next();
       issue_next();
     }
-    const bool need_grp = (p.row_scale != nullptr) || (p.row_bias != nullptr);
+    const bool need_grp = !PLAIN && ((p.row_scale != nullptr) || (p.row_bias != nullptr));
 
     int gc = 0, ti = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
@@ -504,7 +507,7 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
         if ((p1 < p.d1) && (p2 < p.d2) && (p3 < p.d3))
           grp = static_cast<int>(p.fd_rpg.div(static_cast<uint32_t>((p3 * p.d2 + p2) * p.d1 + p1)));
       }
-      const float rs = p.row_scale ? p.row_scale[grp] : 1.0f;
+      const float rs = (!PLAIN && p.row_scale) ? p.row_scale[grp] : 1.0f;
       const int nout0 = GEGLU ? n0 / 2 : n0;
       const int ab = ti & 1;
       mbar_wait_relaxed(&acc_full[ab], (ti >> 1) & 1);
@@ -546,12 +549,18 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 b = __ldg(b4 + j);
-            v2[2 * j] = fma2(pack2u(u[4 * j], u[4 * j + 1]), rs2, pack2(b.x, b.y));
-            v2[2 * j + 1] = fma2(pack2u(u[4 * j + 2], u[4 * j + 3]), rs2, pack2(b.z, b.w));
+            if constexpr (PLAIN) {
+              v2[2 * j] = add2(pack2u(u[4 * j], u[4 * j + 1]), pack2(b.x, b.y));
+              v2[2 * j + 1] = add2(pack2u(u[4 * j + 2], u[4 * j + 3]), pack2(b.z, b.w));
+            } else {
+              v2[2 * j] = fma2(pack2u(u[4 * j], u[4 * j + 1]), rs2, pack2(b.x, b.y));
+              v2[2 * j + 1] = fma2(pack2u(u[4 * j + 2], u[4 * j + 3]), rs2, pack2(b.z, b.w));
+            }
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v2[j] = mul2(pack2u(u[2 * j], u[2 * j + 1]), rs2);
+          for (int j = 0; j < 16; ++j)
+            v2[j] = PLAIN ? pack2u(u[2 * j], u[2 * j + 1]) : mul2(pack2u(u[2 * j], u[2 * j + 1]), rs2);
         }
         if constexpr (GEGLU) {
           if (p.bias) {
@@ -559,12 +568,18 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float4 b = __ldg(b4 + j);
-              g2[2 * j] = fma2(pack2u(g[4 * j], g[4 * j + 1]), rs2, pack2(b.x, b.y));
-              g2[2 * j + 1] = fma2(pack2u(g[4 * j + 2], g[4 * j + 3]), rs2, pack2(b.z, b.w));
+              if constexpr (PLAIN) {
+                g2[2 * j] = add2(pack2u(g[4 * j], g[4 * j + 1]), pack2(b.x, b.y));
+                g2[2 * j + 1] = add2(pack2u(g[4 * j + 2], g[4 * j + 3]), pack2(b.z, b.w));
+              } else {
+                g2[2 * j] = fma2(pack2u(g[4 * j], g[4 * j + 1]), rs2, pack2(b.x, b.y));
+                g2[2 * j + 1] = fma2(pack2u(g[4 * j + 2], g[4 * j + 3]), rs2, pack2(b.z, b.w));
+              }
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) g2[j] = mul2(pack2u(g[2 * j], g[2 * j + 1]), rs2);
+            for (int j = 0; j < 16; ++j)
+              g2[j] = PLAIN ? pack2u(g[2 * j], g[2 * j + 1]) : mul2(pack2u(g[2 * j], g[2 * j + 1]), rs2);
           }
         }
         if (c + CSTRIDE < CPT) {  // prefetch the next chunk's accumulator columns
@@ -585,7 +600,7 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
 #endif
         }
         const int ncol = nout0 + c * EPI_CHUNK;
-        if (p.row_bias) {
+        if (!PLAIN && p.row_bias) {
           const float4* b4 = reinterpret_cast<const float4*>(p.row_bias + static_cast<long long>(grp) * p.ldrb + ncol);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -594,7 +609,7 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
             v2[2 * j + 1] = add2(v2[2 * j + 1], pack2(b.z, b.w));
           }
         }
-        if (gs != 1.0f) {
+        if (!PLAIN && gs != 1.0f) {
           const uint64_t gs2 = pack2(gs, gs);
 #pragma unroll
           for (int j = 0; j < 16; ++j) v2[j] = mul2(v2[j], gs2);
@@ -603,7 +618,7 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
         const int slot = gc % EPI_RO_SLOTS;
         if (staged) mbar_wait(&ro_ready[slot], (gc / EPI_RO_SLOTS) & 1);
         uint8_t* ro = my_ro + slot * EPI_TILE_BYTES;
-        if (p.residual) {
+        if (!PLAIN && p.residual) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint4 q = *reinterpret_cast<const uint4*>(ro + ((j ^ sw) << 4));
@@ -613,7 +628,7 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
             v2[4 * j + 3] = add2(v2[4 * j + 3], bf16x2_to_f32x2(q.w));
           }
         }
-        if (p.blend_x) {
+        if (!PLAIN && p.blend_x) {
           const int xs = gc % EPI_X_SLOTS;
           mbar_wait(&x_ready[xs], (gc / EPI_X_SLOTS) & 1);
           const uint8_t* xr = my_x + xs * EPI_TILE_BYTES;
@@ -627,7 +642,7 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
             v2[4 * j + 3] = fma2(al2, bf16x2_to_f32x2(q.w), mul2(be2, v2[4 * j + 3]));
           }
         }
-        if (p.f16_from > 0 && ncol >= p.f16_from) {  // chunk-uniform: half-precision block (attention V)
+        if (!PLAIN && p.f16_from > 0 && ncol >= p.f16_from) {  // chunk-uniform: half-precision block (attention V)
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             *reinterpret_cast<uint4*>(ro + ((j ^ sw) << 4)) =
@@ -686,7 +701,9 @@ static int launch_persist(const CUtensorMap* a0, const CUtensorMap* a1, const CU
   using L = Gemm2Smem<BN, STAGES, EW>;
   static bool configured = false;
   if (!configured) {
-    SA_CUDA_CHECK(cudaFuncSetAttribute(gemm_tap_persist_kernel<BN, STAGES, GEGLU, EW>,
+    SA_CUDA_CHECK(cudaFuncSetAttribute(gemm_tap_persist_kernel<BN, STAGES, GEGLU, EW, false>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    SA_CUDA_CHECK(cudaFuncSetAttribute(gemm_tap_persist_kernel<BN, STAGES, GEGLU, EW, true>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
   }
@@ -698,7 +715,11 @@ static int launch_persist(const CUtensorMap* a0, const CUtensorMap* a1, const CU
   p.fd_rpg.init(p.rows_per_group);
   int grid = num_sms();
   if (grid > p.total_tiles) grid = p.total_tiles;
-  gemm_tap_persist_kernel<BN, STAGES, GEGLU, EW><<<grid, 64 + 32 * EW, L::TOTAL, stream>>>(*a0, *a1, *b, *o, *r, *x, p);
+  const bool plain = !p.row_scale && !p.row_bias && p.out_scale == 1.0f && !p.residual && !p.blend_x && p.f16_from == 0;
+  if (plain)
+    gemm_tap_persist_kernel<BN, STAGES, GEGLU, EW, true><<<grid, 64 + 32 * EW, L::TOTAL, stream>>>(*a0, *a1, *b, *o, *r, *x, p);
+  else
+    gemm_tap_persist_kernel<BN, STAGES, GEGLU, EW, false><<<grid, 64 + 32 * EW, L::TOTAL, stream>>>(*a0, *a1, *b, *o, *r, *x, p);
   SA_CUDA_CHECK(cudaGetLastError());
   return SA_OK;
 }
