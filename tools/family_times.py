@@ -105,6 +105,17 @@ def main():
         tot += full - rest
         print(f"  {fam:16s} {full - rest:8.3f} ms  {100 * (full - rest) / full:5.1f}%")
     print(f"  {'(other)':16s} {full - tot:8.3f} ms  {100 * (full - tot) / full:5.1f}%")
+    # every family elided at once: what is left is the small kernels outside the families plus launch gaps
+    fams = ("gemm_tap", "groupnorm", "layernorm", "attn_spatial", "attn_temporal", "attn_id")
+    origs = {f: getattr(ops, f) for f in fams}
+    for f in fams:
+        setattr(ops, f, elided(f))
+    try:
+        res["none_ms"] = graph_ms(run, a.reps)
+    finally:
+        for f in fams:
+            setattr(ops, f, origs[f])
+    print(f"  all families elided: {res['none_ms']:.3f} ms remain (kernels outside the families)")
     if a.json:
         Path(a.json).write_text(json.dumps(res))
 

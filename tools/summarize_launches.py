@@ -41,6 +41,8 @@ def main(path):
             per[k]["wr"] = val * SCALE_MB.get(u, 1e-6)
         elif m.startswith("sm__pipe_tensor_cycles_active"):
             per[k]["tensor"] = val
+        elif m.startswith("sm__pipe_tensor_subpipe_hmma_cycles_active"):
+            per[k].setdefault("tensor", val)  # % of active cycles (no elapsed-based metric in this pass)
     agg = defaultdict(lambda: [0, 0.0, 0.0, 0.0, 0.0])
     for k in order:
         d = per[k]
