@@ -211,6 +211,31 @@ int sa_sampler_accumulate(const float* unet_out, int32_t ldo, const int32_t* idx
 int sa_sampler_step(const float* noise, const float* cnt, const float* guidance, int32_t f, int32_t chw,
                     float sigma, float sigma_next, float* latents, void* stream);
 
+/* Image conditioning, once per video: InferenceAnimationPipeline._encode_image
+ * (inference_pipeline_animation.py:192-244).  The vision tower's Linear / LayerNorm layers run on sa_gemm_tap /
+ * sa_layernorm / sa_small_linear / sa_layernorm_f32 above; these four complete it.
+ *  sa_gauss_blur_axis     : one pass of _gaussian_blur2d (:83-96, _filter2d :44-64): depthwise k-tap correlation along
+ *                           rows (axis 0) or columns (axis 1) of `planes` fp32 [h, w] planes, reflect padding
+ *                           ((k - 1) / 2 each side, k odd); taps: k device floats; in != out.  Each input value is
+ *                           read as in_scale * x + in_shift (the `image * 2.0 - 1.0` of :208 on the first pass).
+ *  sa_resize_bicubic_norm : F.interpolate(mode="bicubic", align_corners=True) (:124) of fp32 [b, 3, h, w] to
+ *                           [b, 3, oh, ow], then (x + 1) / 2 (:210) and the CLIPImageProcessor normalisation
+ *                           (x - mean[c]) / std[c] (:213-220); mean3 / std3: three HOST floats each.
+ *  sa_patchify            : im2col of the patch embedding Conv2d(3 -> C, kernel = stride = patch, no bias) of
+ *                           transformers' CLIPVisionEmbeddings: pix fp32 [b, c, hw, hw] -> bf16
+ *                           [b * (hw/patch)^2, ldo], column (ci * patch + ky) * patch + kx, zero beyond c*patch^2.
+ *  sa_attn_tokens         : CLIPAttention core: out[i, h*d + :] = softmax_j(q_i . k_j * scale) v_j per image and head
+ *                           over n tokens; qkv bf16 [b*n, ld] with q | k | v column blocks of width heads*d
+ *                           (d even, <= 128); out bf16 [b*n, ldo]; fp32 math. */
+int sa_gauss_blur_axis(const float* in, float* out, int32_t planes, int32_t h, int32_t w, const float* taps,
+                       int32_t k, int32_t axis, float in_scale, float in_shift, void* stream);
+int sa_resize_bicubic_norm(const float* in, int32_t b, int32_t c, int32_t h, int32_t w, int32_t oh, int32_t ow,
+                           const float* mean3, const float* std3, float* out, void* stream);
+int sa_patchify(const float* pix, int32_t b, int32_t c, int32_t hw, int32_t patch, void* out, int32_t ldo,
+                void* stream);
+int sa_attn_tokens(const void* qkv, int32_t ld, int32_t b, int32_t n, int32_t heads, int32_t d, float scale,
+                   void* out, int32_t ldo, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -138,6 +138,69 @@ def vae_encoder_case():
     torch.save({"seed": SEED, "h": 64, "w": 96, "batch": 2, "out": out_ref.clone()}, GOLD / "vae_encoder_tiny.pt")
 
 
+def _reference_resize_fn():
+    """The reference's own ``_resize_with_antialiasing`` and helpers, executed from the unmodified source file
+    (inference_pipeline_animation.py:22-125).  The module itself cannot be imported offline (it pulls in diffusers'
+    pipeline classes), so the five torch-only function definitions are compiled out of it with ``ast``."""
+    import ast
+    from typing import List
+    src = (ref_loader.REFERENCE_ROOT / "animation/pipelines/inference_pipeline_animation.py").read_text()
+    want = {"_compute_padding", "_filter2d", "_gaussian", "_gaussian_blur2d", "_resize_with_antialiasing"}
+    tree = ast.parse(src)
+    tree.body = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in want]
+    assert {n.name for n in tree.body} == want
+    ns = {"torch": torch, "List": List}
+    exec(compile(tree, "inference_pipeline_animation.py", "exec"), ns)  # noqa: S102
+    return ns["_resize_with_antialiasing"]
+
+
+def clip_case(full: bool = False):
+    """``_encode_image`` (inference_pipeline_animation.py:192-244): pins oracle/clip_oracle.py against the reference's
+    own resize code and against transformers' CLIPImageProcessor / CLIPVisionModelWithProjection on the synthetic
+    weights, and writes tests/golden/clip_vision_tiny.pt."""
+    import transformers
+    from transformers import CLIPImageProcessor, CLIPVisionConfig, CLIPVisionModelWithProjection
+    from oracle import clip_oracle
+    from stableanimator_b200.arch import ClipVisionConfig
+    from stableanimator_b200.synth import synth_clip_vision_state_dict, synth_image
+    cfg = ClipVisionConfig.full() if full else ClipVisionConfig.tiny()
+    tag = "full" if full else "tiny"
+    sd = synth_clip_vision_state_dict(cfg, SEED)
+    m = CLIPVisionModelWithProjection(CLIPVisionConfig(
+        hidden_size=cfg.hidden_size, intermediate_size=cfg.intermediate_size, num_hidden_layers=cfg.num_hidden_layers,
+        num_attention_heads=cfg.num_attention_heads, image_size=cfg.image_size, patch_size=cfg.patch_size,
+        projection_dim=cfg.projection_dim, hidden_act="gelu", layer_norm_eps=cfg.layer_norm_eps)).eval()
+    missing, unexpected = m.load_state_dict({k: v.clone() for k, v in sd.items()}, strict=False)
+    assert not unexpected and all(k.endswith("position_ids") for k in missing), (missing, unexpected)
+    proc = CLIPImageProcessor(do_resize=False, do_center_crop=False, do_rescale=False, do_normalize=True,
+                              image_mean=list(cfg.image_mean), image_std=list(cfg.image_std))
+    resize = _reference_resize_fn()
+    outs = {}
+    # tiny: blur kernels (3, 3) and (3, 5); full: the 512x512 reference image of BASELINE configs[1] (ViT-H/14)
+    sizes = {"a": (512, 512)} if full else {"a": (128, 128), "b": (144, 256)}
+    batch = 1 if full else 2
+    for name, (h, w) in sizes.items():
+        image01 = (synth_image(h, w, SEED, batch=batch) + 1.0) / 2.0
+        with torch.no_grad():
+            r = resize(image01 * 2.0 - 1.0, (cfg.image_size, cfg.image_size))
+            mine_r = clip_oracle.resize_with_antialiasing(image01 * 2.0 - 1.0, (cfg.image_size, cfg.image_size))
+            e0 = rel(mine_r, r)
+            pix = proc(images=(r + 1.0) / 2.0, return_tensors="pt").pixel_values
+            mine_pix = clip_oracle.clip_pixel_values(image01, cfg)
+            e1 = rel(mine_pix, pix)
+            emb = m(pix).image_embeds
+            mine = clip_oracle.clip_image_embeds(sd, cfg, mine_pix)
+            e2 = rel(mine, emb)
+        print(f"[clip_vision_{tag}/{name}] oracle vs reference resize {e0:.2e}, vs CLIPImageProcessor {e1:.2e}, "
+              f"vs transformers {transformers.__version__} image_embeds {e2:.2e}")
+        assert e0 < 1e-6 and e1 < 1e-5 and e2 < 1e-5
+        outs[name] = {"h": h, "w": w, "image_embeds": emb.clone()}
+        if not full:
+            outs[name]["pixel_values"] = pix.clone()
+    torch.save({"seed": SEED, "batch": batch, "cases": outs, "transformers": transformers.__version__},
+               GOLD / f"clip_vision_{tag}.pt")
+
+
 def main():
     GOLD.mkdir(parents=True, exist_ok=True)
     torch.manual_seed(0)
@@ -156,3 +219,6 @@ if __name__ == "__main__":
     face_case()
     vae_case()
     vae_encoder_case()
+    clip_case()
+    if "--full" in sys.argv:
+        clip_case(full=True)

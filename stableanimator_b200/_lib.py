@@ -96,6 +96,10 @@ SIGNATURES: dict[str, list] = {
     "sa_sampler_prepare": [_P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P],
     "sa_sampler_accumulate": [_P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P],
     "sa_sampler_step": [_P, _P, _P, _I, _I, _F, _F, _P, _P],
+    "sa_gauss_blur_axis": [_P, _P, _I, _I, _I, _P, _I, _I, _F, _F, _P],
+    "sa_resize_bicubic_norm": [_P, _I, _I, _I, _I, _I, _I, C.POINTER(C.c_float), C.POINTER(C.c_float), _P, _P],
+    "sa_patchify": [_P, _I, _I, _I, _I, _P, _I, _P],
+    "sa_attn_tokens": [_P, _I, _I, _I, _I, _I, _F, _P, _I, _P],
 }
 
 

@@ -381,3 +381,57 @@ def face_param_shapes(cross_attention_dim: int = 1024, id_embeddings_dim: int = 
 # PoseNet conv stack as (cin, cout, kernel, stride, pad)
 POSENET_CONVS = [(3, 3, 3, 1, 1), (3, 16, 4, 2, 1), (16, 16, 3, 1, 1), (16, 32, 4, 2, 1),
                  (32, 32, 3, 1, 1), (32, 64, 4, 2, 1), (64, 64, 3, 1, 1), (64, 128, 3, 1, 1)]
+
+
+@dataclass
+class ClipVisionConfig:
+    """``CLIPVisionModelWithProjection`` of the SVD ``image_encoder`` (third-party ``transformers``; loaded at
+    inference_basic.py:241-243, called at inference_pipeline_animation.py:224): ViT-H/14, exact-erf GELU."""
+    hidden_size: int = 1280
+    intermediate_size: int = 5120
+    num_hidden_layers: int = 32
+    num_attention_heads: int = 16
+    image_size: int = 224
+    patch_size: int = 14
+    projection_dim: int = 1024
+    layer_norm_eps: float = 1e-5
+    # CLIPImageProcessor statistics of the SVD ``feature_extractor`` (inference_basic.py:226)
+    image_mean: Tuple[float, float, float] = (0.48145466, 0.4578275, 0.40821073)
+    image_std: Tuple[float, float, float] = (0.26862954, 0.26130258, 0.27577711)
+
+    @property
+    def num_patches(self) -> int:
+        return (self.image_size // self.patch_size) ** 2
+
+    @staticmethod
+    def full() -> "ClipVisionConfig":
+        return ClipVisionConfig()
+
+    @staticmethod
+    def tiny() -> "ClipVisionConfig":
+        """Same graph: 2 layers, 4 heads of the real head_dim 80, 56x56 input (16 patches + class token)."""
+        return ClipVisionConfig(hidden_size=320, intermediate_size=640, num_hidden_layers=2, num_attention_heads=4,
+                                image_size=56, projection_dim=128)
+
+
+def clip_vision_param_shapes(cfg: ClipVisionConfig) -> Dict[str, Tuple[int, ...]]:
+    """``state_dict`` keys / shapes of transformers' CLIPVisionModelWithProjection (bias-free patch conv and
+    projection; the misspelt ``pre_layrnorm`` is the library's own key)."""
+    c, i, v = cfg.hidden_size, cfg.intermediate_size, "vision_model"
+    d: Dict[str, Tuple[int, ...]] = {
+        f"{v}.embeddings.class_embedding": (c,),
+        f"{v}.embeddings.patch_embedding.weight": (c, 3, cfg.patch_size, cfg.patch_size),
+        f"{v}.embeddings.position_embedding.weight": (cfg.num_patches + 1, c),
+        f"{v}.pre_layrnorm.weight": (c,), f"{v}.pre_layrnorm.bias": (c,),
+    }
+    for l in range(cfg.num_hidden_layers):
+        b = f"{v}.encoder.layers.{l}"
+        for n in ("k_proj", "v_proj", "q_proj", "out_proj"):
+            d[f"{b}.self_attn.{n}.weight"] = (c, c); d[f"{b}.self_attn.{n}.bias"] = (c,)
+        d[f"{b}.layer_norm1.weight"] = (c,); d[f"{b}.layer_norm1.bias"] = (c,)
+        d[f"{b}.mlp.fc1.weight"] = (i, c); d[f"{b}.mlp.fc1.bias"] = (i,)
+        d[f"{b}.mlp.fc2.weight"] = (c, i); d[f"{b}.mlp.fc2.bias"] = (c,)
+        d[f"{b}.layer_norm2.weight"] = (c,); d[f"{b}.layer_norm2.bias"] = (c,)
+    d[f"{v}.post_layernorm.weight"] = (c,); d[f"{v}.post_layernorm.bias"] = (c,)
+    d["visual_projection.weight"] = (cfg.projection_dim, c)
+    return d

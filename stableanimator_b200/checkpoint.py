@@ -77,3 +77,11 @@ def load_vae_encoder(path: PathLike, cfg: Optional[VaeDecoderConfig] = None, dev
     """SVD ``vae/diffusion_pytorch_model.safetensors`` -> VaeEncoderB200 (takes ``encoder.*`` and ``quant_conv.*``)."""
     from .vae_encoder import VaeEncoderB200
     return VaeEncoderB200(cfg or VaeDecoderConfig.full(), read_state_dict(path), device)
+
+
+def load_image_encoder(path: PathLike, cfg=None, device="cuda"):
+    """SVD ``image_encoder/model.safetensors`` (transformers CLIPVisionModelWithProjection, inference_basic.py:241-243)
+    -> ClipImageEncoderB200."""
+    from .arch import ClipVisionConfig
+    from .clip_encoder import ClipImageEncoderB200
+    return ClipImageEncoderB200(cfg or ClipVisionConfig.full(), read_state_dict(path), device)

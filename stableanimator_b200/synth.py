@@ -13,8 +13,8 @@ from typing import Dict, Tuple
 
 import torch
 
-from .arch import (UNetConfig, VaeDecoderConfig, face_param_shapes, posenet_param_shapes, unet_param_shapes,
-                   vae_decoder_param_shapes, vae_encoder_param_shapes)
+from .arch import (ClipVisionConfig, UNetConfig, VaeDecoderConfig, clip_vision_param_shapes, face_param_shapes,
+                   posenet_param_shapes, unet_param_shapes, vae_decoder_param_shapes, vae_encoder_param_shapes)
 
 
 def _gen(key: str, seed: int) -> torch.Generator:
@@ -68,6 +68,11 @@ def synth_vae_decoder_state_dict(cfg: VaeDecoderConfig, seed: int = 23123134):
 def synth_vae_encoder_state_dict(cfg: VaeDecoderConfig, seed: int = 23123134):
     """``encoder.*`` + ``quant_conv.*`` of AutoencoderKLTemporalDecoder (vae.py:236-247,482-556)."""
     return {k: synth_tensor("vae." + k, s, seed) for k, s in vae_encoder_param_shapes(cfg).items()}
+
+
+def synth_clip_vision_state_dict(cfg: ClipVisionConfig, seed: int = 23123134):
+    """CLIPVisionModelWithProjection weights, keys as in its ``state_dict``."""
+    return {k: synth_tensor("image_encoder." + k, s, seed) for k, s in clip_vision_param_shapes(cfg).items()}
 
 
 def synth_image(h: int, w: int, seed: int = 23123134, batch: int = 1) -> torch.Tensor:

@@ -66,3 +66,21 @@ def test_other_modules_and_vae_prefix(tmp_path):
     save_file(whole, str(tmp_path / "vae.safetensors"))
     dec = ck.load_vae_decoder(tmp_path / "vae.safetensors", vcfg, "cpu")
     assert dec.w["conv_in.w"].shape == (36, 128)
+
+
+def test_image_encoder_checkpoint(tmp_path):
+    """CLIPVisionModelWithProjection safetensors (incl. the legacy position_ids buffer) -> packed layout, strict."""
+    from safetensors.torch import save_file
+    from stableanimator_b200.arch import ClipVisionConfig
+    from stableanimator_b200.synth import synth_clip_vision_state_dict
+    cfg = ClipVisionConfig.tiny()
+    sd = {k: v.contiguous() for k, v in synth_clip_vision_state_dict(cfg).items()}
+    sd["vision_model.embeddings.position_ids"] = torch.arange(cfg.num_patches + 1)[None]
+    save_file(sd, str(tmp_path / "model.safetensors"))
+    enc = ck.load_image_encoder(tmp_path / "model.safetensors", cfg, "cpu")
+    assert enc.w["patch.w"].shape == (cfg.hidden_size, 640) and enc.w["0.fc1.w"].shape == (2 * cfg.intermediate_size, cfg.hidden_size)
+    assert enc.w["0.qkv.w"].shape == (3 * cfg.hidden_size, cfg.hidden_size)
+    sd.pop("visual_projection.weight")
+    save_file(sd, str(tmp_path / "bad.safetensors"))
+    with pytest.raises(KeyError):
+        ck.load_image_encoder(tmp_path / "bad.safetensors", cfg, "cpu")

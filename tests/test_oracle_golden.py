@@ -105,3 +105,35 @@ def test_vae_encoder_oracle_matches_reference_golden():
     out = vae_oracle.vae_encode_mode(sd, cfg, synth_image(g["h"], g["w"], g["seed"], batch=g["batch"]))
     assert out.shape == g["out"].shape == (g["batch"], 4, g["h"] // 8, g["w"] // 8)
     assert ((out - g["out"]).abs().max() / g["out"].abs().max()).item() < 2e-5
+
+
+def test_clip_oracle_matches_reference_golden():
+    """_encode_image (inference_pipeline_animation.py:192-244): oracle/clip_oracle.py vs the pixel values produced by
+    the reference's own _resize_with_antialiasing + transformers' CLIPImageProcessor, and the image_embeds of
+    transformers' CLIPVisionModelWithProjection on the same synthetic weights (stored by oracle/make_golden.py)."""
+    from pathlib import Path
+    from oracle import clip_oracle
+    from stableanimator_b200.arch import ClipVisionConfig
+    from stableanimator_b200.synth import synth_clip_vision_state_dict, synth_image
+    g = torch.load(Path(__file__).resolve().parent / "golden" / "clip_vision_tiny.pt", map_location="cpu", weights_only=False)
+    cfg = ClipVisionConfig.tiny()
+    sd = synth_clip_vision_state_dict(cfg, g["seed"])
+    for name, c in g["cases"].items():
+        image01 = (synth_image(c["h"], c["w"], g["seed"], batch=g["batch"]) + 1.0) / 2.0
+        pix = clip_oracle.clip_pixel_values(image01, cfg)
+        assert ((pix - c["pixel_values"]).abs().max() / c["pixel_values"].abs().max()).item() < 1e-6, name
+        emb = clip_oracle.clip_image_embeds(sd, cfg, pix)
+        assert emb.shape == c["image_embeds"].shape == (g["batch"], cfg.projection_dim)
+        assert ((emb - c["image_embeds"]).abs().max() / c["image_embeds"].abs().max()).item() < 2e-5, name
+    both = clip_oracle.encode_image(sd, cfg, image01)
+    assert both.shape == (2 * g["batch"], 1, cfg.projection_dim) and not both[:g["batch"]].any()
+
+
+def test_clip_blur_geometry_of_the_baseline_resolutions():
+    """Kernel sizes the reference derives (:100-120): 512x512 -> 3x3 taps; 1024x576 (h x w) -> 7 rows x 3 columns."""
+    from oracle import clip_oracle
+    assert clip_oracle.blur_geometry((512, 512), (224, 224))[1] == (3, 3)
+    assert clip_oracle.blur_geometry((1024, 576), (224, 224))[1] == (7, 3)
+    assert clip_oracle.blur_geometry((224, 224), (224, 224)) == ((0.001, 0.001), (3, 3))
+    t = clip_oracle.gaussian_taps(7, 1.7857)
+    assert abs(t.sum().item() - 1.0) < 1e-6 and torch.equal(t, t.flip(0))
