@@ -13,6 +13,9 @@ weighted noise accumulator per Euler step.  ``value`` = tile frames denoised by 
 the unit of work a rank processes; overlap frames are denoised by both neighbouring tiles and blended,
 inference_pipeline_animation.py:656-689) / max-over-ranks time; the unique video frames per second are
 reported next to it as ``video_frames_per_s``.
+``--config 2|3|4`` selects the other BASELINE.json configs (fixed videos, strong scaling: 576x1024x16f with the CFG
+branches on two GPUs; 512x512x64f and 576x1024x128f with the (frame tile, CFG branch) units spread over the ranks);
+there ``value`` = the video's frames / max-over-ranks time.
 Prints ONE JSON line (rank 0).  Synthetic weights/inputs (stableanimator_b200/synth.py).
 """
 from __future__ import annotations
@@ -33,8 +36,16 @@ import torch  # noqa: E402
 
 METRIC = "denoised frames/sec at 512x512x16f 25 steps"
 UNIT = "frames/s"
-# reference-graph FLOPs of one B=1 UNet call at F=16, 64x64 latent
+# reference-graph FLOPs of one B=1 UNet call at F=16, 64x64 / 128x72 latent
 FLOPS_PER_CALL_64x64x16 = 20.311e12
+FLOPS_PER_CALL_128x72x16 = 51.200e12
+# BASELINE.json configs[i] -> (latent h, latent w, video frames | None = weak scaling, description)
+CONFIGS = {
+    1: (64, 64, None, "512x512, 16-frame tiles, CFG cond/uncond fused (B=2)"),
+    2: (128, 72, 16, "576x1024 (w x h), 16 frames, CFG branches split over the ranks"),
+    3: (64, 64, 64, "512x512, 64-frame long video, tile 16 / overlap 4, (tile, CFG branch) units over the ranks"),
+    4: (128, 72, 128, "576x1024 (w x h), 128-frame long video, tile 16 / overlap 4, (tile, CFG branch) units over the ranks"),
+}
 # average DRAM bytes (read + write) per sa_gemm_tap launch in one B=2 UNet call at 64x64x16, from the ncu pass
 # `--metrics dram__bytes_read.sum,dram__bytes_write.sum` over all 334 launches of the family
 # (profiles/r1_v5_launches_unet_b2_64x64x16.csv, summary next to it: read 98.2 MB + write 42.6 MB)
@@ -95,7 +106,7 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------- reference / CPU leg
-def cpu_reference_sample(frames: int, hw: int, cfg_name: str = "full"):
+def cpu_reference_sample(frames: int, hw: int, cfg_name: str = "full", w: int = 0):
     """Time ONE B=1 UNet call of the oracle port (fp32, all host cores) at the workload's shape and
     extrapolate to the 50 calls (25 steps x 2 CFG branches) of a 16-frame denoise."""
     from oracle import unet_oracle as O
@@ -105,7 +116,7 @@ def cpu_reference_sample(frames: int, hw: int, cfg_name: str = "full"):
     torch.set_num_threads(cores)
     cfg = UNetConfig.full() if cfg_name == "full" else UNetConfig.tiny()
     sd = synth_unet_state_dict(cfg)
-    inp = synth_inputs(cfg, frames, hw, hw)
+    inp = synth_inputs(cfg, frames, lh, lw)
     sample = torch.cat([inp["latents"].expand(1, frames, 4, hw, hw), inp["image_latents"][:1]], dim=2)
     t0 = time.perf_counter()
     O.unet_forward(sd, cfg, sample, torch.tensor(1.0), inp["encoder_hidden_states"][:1], inp["added_time_ids"][:1])
@@ -219,12 +230,17 @@ def run_ours(args):
     _lib.lib()  # fail loudly if the CUDA library is missing
 
     cfg = UNetConfig.tiny() if args.size == "tiny" else UNetConfig.full()
-    hw = args.latent
+    lh, lw, fixed_frames, cfg_desc = CONFIGS[args.config]
+    if args.latent != 64:
+        lh = lw = args.latent
+    hw = lh
     tile = 16
-    frames = tile + (tile - 4) * (world - 1)  # N tiles of 16 frames, overlap 4
+    # configs[1]: weak scaling, N tiles of 16 frames (overlap 4); configs[2..4]: one fixed video, strong scaling
+    frames = fixed_frames if fixed_frames else tile + (tile - 4) * (world - 1)
+    strong = fixed_frames is not None
     unet = UNetB200(cfg, synth_unet_state_dict(cfg), dev)
     pose_net = PoseNetB200(synth_posenet_state_dict(cfg.block_out_channels[0]), cfg.block_out_channels[0], dev)
-    inp = synth_inputs(cfg, frames, hw, hw)
+    inp = synth_inputs(cfg, frames, lh, lw)
     host = {k: inp[k].pin_memory() for k in ("image_latents", "encoder_hidden_states", "added_time_ids", "pose")}
     host["latents"] = inp["latents"][:, :tile].contiguous().pin_memory()
     devt = {k: v.to(dev) for k, v in host.items()}
@@ -261,7 +277,7 @@ def run_ours(args):
     clk = clocks.stop() if rank == 0 else None
 
     # ---- end-to-end timing through the public API with HOST buffers (H2D + D2H inside)
-    out_host = torch.empty((1, frames, 4, hw, hw), dtype=torch.float32).pin_memory()
+    out_host = torch.empty((1, frames, 4, lh, lw), dtype=torch.float32).pin_memory()
     call(host)
     barrier()
     t0 = time.perf_counter()
@@ -278,24 +294,31 @@ def run_ours(args):
 
     if rank == 0:
         sustained, burst, hbm, src = peaks()
-        tile_frames = tile * world  # frames denoised per bench step by all ranks (N=1: the 16-frame video)
+        # weak: frames denoised per bench step by all ranks (N=1: the 16-frame video); strong: the video's frames
+        tile_frames = frames if strong else tile * world
         value = tile_frames / (ms / 1e3)
         e2e = tile_frames / (e2e_ms / 1e3)
         # roofline of the dominant kernel family (tcgen05 tapped GEMM): live CUDA-event pass
         ctx = unet.prepare_context(devt["encoder_hidden_states"])
-        g_flops, g_ms, g_n, call_ms = gemm_family_time(unet, ctx, devt["added_time_ids"], 2, tile, hw, hw)
+        g_flops, g_ms, g_n, call_ms = gemm_family_time(unet, ctx, devt["added_time_ids"], 2, tile, lh, lw)
         achieved = g_flops / (g_ms * 1e-3) / 1e12
-        calls_per_step = args.euler_steps * 2 * world  # B=1-equivalent UNet calls per bench step
+        from stableanimator_b200 import scheduler as sch
+        n_tiles = len(sch.tile_indices(frames, tile, 4))
+        calls_per_step = args.euler_steps * 2 * n_tiles  # B=1-equivalent UNet calls per bench step
         step_tflops = None
-        if args.size == "full" and hw == 64:
-            step_tflops = calls_per_step * FLOPS_PER_CALL_64x64x16 / (ms * 1e-3) / 1e12 / world  # per GPU
+        per_call = {(64, 64): FLOPS_PER_CALL_64x64x16, (128, 72): FLOPS_PER_CALL_128x72x16}.get((lh, lw))
+        if args.size == "full" and per_call:
+            step_tflops = calls_per_step * per_call / (ms * 1e-3) / 1e12 / world  # per GPU
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": (f"{hw * 8}x{hw * 8}x{frames}f, {args.euler_steps} Euler steps, CFG cond/uncond fused (B=2), "
-                                    f"tile 16 / overlap 4" + (" (BASELINE configs[1])" if world == 1 else f", {world} frame tiles over {world} GPUs")),
-                       "frames_counted": (f"tile frames denoised per step by all ranks ({tile} x {world}); "
+            "config": {"workload": (f"{lw * 8}x{lh * 8}x{frames}f, {args.euler_steps} Euler steps, {cfg_desc}, "
+                                    f"tile 16 / overlap 4 (BASELINE configs[{args.config}])"
+                                    + ("" if world == 1 else f", {n_tiles} frame tiles over {world} GPUs")),
+                       "frames_counted": (f"the video's {frames} frames (fixed video, {2 * n_tiles} UNet units per step)" if strong else
+                                          f"tile frames denoised per step by all ranks ({tile} x {world}); "
                                           f"unique video frames = {frames}"),
                        "unet": args.size, "l2": "working set (3.1 GB weights + activations per UNet call) >> 126 MB L2; no flush",
                        "cuda_graph": not args.no_graph},
@@ -305,7 +328,7 @@ def run_ours(args):
             "clocks": clk,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
                          "frac": achieved / sustained,
-                         "traffic": GEMM_DRAM_BYTES_PER_LAUNCH if (args.size == "full" and hw == 64) else None,
+                         "traffic": GEMM_DRAM_BYTES_PER_LAUNCH if (args.size == "full" and (lh, lw) == (64, 64)) else None,
                          "traffic_unit": "bytes of DRAM read+write per launch (ncu, family average)",
                          "peak_source": src,
                          "kernel": "gemm_tap_kernel (tcgen05 tapped implicit GEMM, all instantiations)",
@@ -317,10 +340,10 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu:
             sample_frames = 16 if (os.cpu_count() or 1) >= 32 else 4
-            dt, cores = cpu_reference_sample(sample_frames, hw, args.size)
+            dt, cores = cpu_reference_sample(sample_frames, lh, args.size, lw)
             sec = dt * (16 / sample_frames) * 50
             line["cpu_baseline"] = {"value": 16 / sec, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"1 B=1 fp32 oracle UNet call, F={sample_frames}, {hw}x{hw} latent, "
+                                    "sample": f"1 B=1 fp32 oracle UNet call, F={sample_frames}, {lh}x{lw} latent, "
                                               f"scaled to F=16 and x50 calls"}
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
@@ -338,6 +361,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", default="full", choices=["full", "tiny"], help="tiny = debug-size UNet (not a bench result)")
     ap.add_argument("--latent", type=int, default=64, help="latent height = width (64 = 512x512)")
+    ap.add_argument("--config", type=int, default=1, choices=sorted(CONFIGS),
+                    help="BASELINE.json configs[i]: 1 = the metric's config (default; weak scaling for N > 1), "
+                         "2 = 576x1024x16f CFG split (2 GPUs), 3 = 512x512x64f (4 / 8 GPUs), 4 = 576x1024x128f (8 GPUs)")
     ap.add_argument("--euler-steps", type=int, default=25)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
