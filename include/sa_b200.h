@@ -79,6 +79,14 @@ typedef struct sa_gemm_args {
   int32_t tile_n;        /* 0 = auto; else one of 32, 64, 128, 160, 256 */
   float out_scale;       /* 0 = 1.0; scales (acc*row_scale + bias + row_bias [geglu]) before residual */
   int32_t f16_from_col;  /* > 0: output columns >= this (multiple of 32) are stored as fp16; 0 = all bf16 */
+  /* Fused GroupNorm statistics of the OUTPUT (the tensor the next nn.GroupNorm normalises, unet.py:1632-1643, */
+  /* :1709-1731, :575): when gn_stats != NULL the epilogue adds Sum / Sum^2 of the bf16-rounded results into    */
+  /* gn_stats fp64 [M / gn_rows_per_stat, n_out / gn_cpg, 2] (zeroed by the call) -- exactly what the statistics */
+  /* pass of sa_groupnorm would read back from HBM; consume them with sa_groupnorm_apply.  bf16 output only      */
+  /* (no geglu / out_f32 / f16_from_col), n % tile == 0, M % gn_rows_per_stat == 0, n_out % gn_cpg == 0.         */
+  void* gn_stats;
+  int32_t gn_cpg;            /* channels per group (n_out / 32 for nn.GroupNorm(32, n_out)) */
+  int32_t gn_rows_per_stat;  /* rows sharing one statistic: h*w (per frame) or F*h*w (whole tile) */
 } sa_gemm_args;
 
 int sa_gemm_tap(const sa_gemm_args* args, void* stream);
@@ -128,9 +136,14 @@ int sa_attn_id_finalize(const void* stats, const float* vclip, int64_t vclip_bat
  * and :1709,1722,1731 (rows_per_stat = F*h*w: TemporalResnetBlock, whole tile).  x0 (+ optional x1,
  * channel concat = torch.cat skip input :1347,1433) bf16 [ns*rows_per_stat, ld*]; out bf16
  * [.., c0+c1]; stats_ws: fp64 [ns, 32, 2]. */
+/* sa_groupnorm_apply: the normalise (+SiLU) pass alone, on statistics already accumulated in stats_ws by the
+ * epilogue of the sa_gemm_tap launch that produced x0 (sa_gemm_args.gn_stats); same arguments. */
 int sa_groupnorm(const void* x0, const void* x1, int32_t c0, int32_t c1, int32_t ld0, int32_t ld1,
                  int64_t rows_per_stat, int32_t ns, const float* gamma, const float* beta, float eps,
                  int32_t do_silu, void* stats_ws, void* out, int32_t ldo, void* stream);
+int sa_groupnorm_apply(const void* x0, const void* x1, int32_t c0, int32_t c1, int32_t ld0, int32_t ld1,
+                       int64_t rows_per_stat, int32_t ns, const float* gamma, const float* beta, float eps,
+                       int32_t do_silu, const void* stats_ws, void* out, int32_t ldo, void* stream);
 
 /* LayerNorm over C (unet.py:499,510,521,892,898,907,916), eps 1e-5:
  *   y = LN(x + addv[row / rows_per_group]); if x_out: x_out = x + addv (the new residual stream).

@@ -43,6 +43,7 @@ class GemmArgs(C.Structure):
         ("tile_n", C.c_int32),
         ("out_scale", C.c_float),
         ("f16_from_col", C.c_int32),
+        ("gn_stats", C.c_void_p), ("gn_cpg", C.c_int32), ("gn_rows_per_stat", C.c_int32),
     ]
 
 
@@ -79,6 +80,7 @@ SIGNATURES: dict[str, list] = {
     "sa_attn_id": [_P, _I, _P, _P, _L, _L, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P],
     "sa_attn_id_finalize": [_P, _P, _L, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P],
     "sa_groupnorm": [_P, _P, _I, _I, _I, _I, _L, _I, _P, _P, _F, _I, _P, _P, _I, _P],
+    "sa_groupnorm_apply": [_P, _P, _I, _I, _I, _I, _L, _I, _P, _P, _F, _I, _P, _P, _I, _P],
     "sa_layernorm": [_P, _I, _L, _I, _P, _I, _P, _I, _P, _P, _F, _P, _I, _P],
     "sa_small_linear": [_P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _P, _I, _P],
     "sa_sinusoid": [_P, _I, _I, _P, _P],
@@ -111,7 +113,7 @@ def _declare(l: C.CDLL) -> None:
 
 
 # kernels launched by one successful call of each entry point (for bench.py's gpu_launches claim)
-KERNELS_PER_CALL = {"sa_groupnorm": 2}
+KERNELS_PER_CALL = {"sa_groupnorm": 2, "sa_groupnorm_apply": 1}
 launch_count = 0
 
 

@@ -53,7 +53,9 @@ struct GemmKParams {
   int n_tiles_n, total_tiles;
   float out_scale;  // v = (acc*rs + bias + row_bias [geglu]) * out_scale + residual ...
   int f16_from;     // > 0: output columns >= f16_from are stored as fp16 instead of bf16
-  FastDiv fd_ntn, fd_t1, fd_t2, fd_rpg;
+  double* gn_stats; // fused GroupNorm statistics of the output: fp64 [M / rows_per_stat, n_out / cpg, 2] or null
+  int gn_groups;    // n_out / cpg
+  FastDiv fd_ntn, fd_t1, fd_t2, fd_rpg, fd_gcpg, fd_grps;
 };
 
 template <int BN>
@@ -508,6 +510,16 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
           grp = static_cast<int>(p.fd_rpg.div(static_cast<uint32_t>((p3 * p.d2 + p2) * p.d1 + p1)));
       }
       const float rs = (!PLAIN && p.row_scale) ? p.row_scale[grp] : 1.0f;
+      // fused GroupNorm statistics: statistic index of this thread's row (-1 = row outside the grid); the fast path
+      // below needs it uniform over the warp's 32 rows
+      int gn_sid = -1;
+      bool gn_uniform = false;
+      if (!PLAIN && !GEGLU && p.gn_stats) {
+        const int p1 = q1 + i1, p2 = q2 + i2, p3 = q3 + i3;
+        if ((p1 < p.d1) && (p2 < p.d2) && (p3 < p.d3))
+          gn_sid = static_cast<int>(p.fd_grps.div(static_cast<uint32_t>((p3 * p.d2 + p2) * p.d1 + p1)));
+        gn_uniform = __all_sync(0xffffffffu, gn_sid == __shfl_sync(0xffffffffu, gn_sid, 0)) && gn_sid >= 0;
+      }
       const int nout0 = GEGLU ? n0 / 2 : n0;
       const int ab = ti & 1;
       mbar_wait_relaxed(&acc_full[ab], (ti >> 1) & 1);
@@ -666,6 +678,66 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
           tma_store_wait_read<1>();
           if (staged) issue_next();
         }
+        if constexpr (!PLAIN && !GEGLU) {
+          if (p.gn_stats) {
+            // Sum / Sum^2 of the bf16 values just staged (what a separate statistics pass would read back from HBM),
+            // while the TMA store of the same tile is in flight.  Lane j takes COLUMN ncol + j of the 32 x 32 tile
+            // (conflict-free: one 64-byte row per step), a segmented warp reduction merges the columns of a group,
+            // the first lane of each group adds to the fp64 accumulators.
+            const uint8_t* tile = sRO + slot * EPI_TILE_BYTES;
+            const int gid = static_cast<int>(p.fd_gcpg.div(static_cast<uint32_t>(ncol + lane)));
+            // bf16 values and their squares are exact in fp32; the sums run in fp64, so the statistics do not depend on
+            // how rows fall into tiles / warps (B = 2 gives the bits of two B = 1 calls) and carry no fp32 partial-sum noise
+            if (gn_uniform) {
+              double s1 = 0.0, s2 = 0.0;
+              const int cj = lane >> 3, ej = (lane & 7) * 2;
+#pragma unroll 8
+              for (int rr = 0; rr < 32; ++rr) {
+                const float v = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(
+                    tile + rr * 64 + ((cj ^ ((rr >> 1) & 3)) << 4) + ej));
+                s1 += static_cast<double>(v);
+                s2 += static_cast<double>(v * v);
+              }
+#pragma unroll
+              for (int off = 1; off < 32; off <<= 1) {
+                const double t1 = __shfl_down_sync(0xffffffffu, s1, off);
+                const double t2 = __shfl_down_sync(0xffffffffu, s2, off);
+                const int g2_ = __shfl_down_sync(0xffffffffu, gid, off);
+                if (lane + off < 32 && g2_ == gid) {
+                  s1 += t1;
+                  s2 += t2;
+                }
+              }
+              const int gprev = __shfl_up_sync(0xffffffffu, gid, 1);
+              if (lane == 0 || gprev != gid) {
+                double* dst = p.gn_stats + (static_cast<long long>(gn_sid) * p.gn_groups + gid) * 2;
+                atomicAdd(dst, s1);
+                atomicAdd(dst + 1, s2);
+              }
+            } else if (gn_sid >= 0) {
+              // rows of this warp belong to different statistics (or some lie outside the grid): every lane walks
+              // its own row and flushes at group boundaries
+              const uint8_t* rowp = tile + lane * 64;
+              double s1 = 0.0, s2 = 0.0;
+              int gcur = static_cast<int>(p.fd_gcpg.div(static_cast<uint32_t>(ncol)));
+              int left = (gcur + 1) * static_cast<int>(p.fd_gcpg.d) - ncol;  // columns until the group ends
+              for (int j = 0; j < 32; ++j) {
+                const float v = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(
+                    rowp + (((j >> 3) ^ sw) << 4) + (j & 7) * 2));
+                s1 += static_cast<double>(v);
+                s2 += static_cast<double>(v * v);
+                if (--left == 0 || j == 31) {
+                  double* dst = p.gn_stats + (static_cast<long long>(gn_sid) * p.gn_groups + gcur) * 2;
+                  atomicAdd(dst, s1);
+                  atomicAdd(dst + 1, s2);
+                  s1 = s2 = 0.0;
+                  ++gcur;
+                  left = static_cast<int>(p.fd_gcpg.d);
+                }
+              }
+            }
+          }
+        }
         __syncwarp();
       }
     }
@@ -715,7 +787,8 @@ static int launch_persist(const CUtensorMap* a0, const CUtensorMap* a1, const CU
   p.fd_rpg.init(p.rows_per_group);
   int grid = num_sms();
   if (grid > p.total_tiles) grid = p.total_tiles;
-  const bool plain = !p.row_scale && !p.row_bias && p.out_scale == 1.0f && !p.residual && !p.blend_x && p.f16_from == 0;
+  const bool plain = !p.row_scale && !p.row_bias && p.out_scale == 1.0f && !p.residual && !p.blend_x && p.f16_from == 0 &&
+                     !p.gn_stats;
   if (plain)
     gemm_tap_persist_kernel<BN, STAGES, GEGLU, EW, true><<<grid, 64 + 32 * EW, L::TOTAL, stream>>>(*a0, *a1, *b, *o, *r, *x, p);
   else
@@ -865,6 +938,17 @@ extern "C" int sa_gemm_tap(const sa_gemm_args* a, void* stream_) {
   if (a->f16_from_col < 0 || a->f16_from_col % 32) return fail(SA_ERR_INVALID, "sa_gemm_tap: f16_from_col must be a multiple of 32");
   static const bool force_v1 = getenv("SA_GEMM_V1") != nullptr;
   const bool v2_ok = !force_v1 && !a->out_f32 && (a->n % bn == 0) && bn >= 64;
+  if (a->gn_stats) {
+    if (!v2_ok || a->geglu || a->f16_from_col > 0)
+      return fail(SA_ERR_INVALID, "sa_gemm_tap: gn_stats needs the persistent bf16 path without geglu / f16 columns");
+    if (a->gn_cpg < 1 || a->n % a->gn_cpg || a->gn_rows_per_stat < 1 || M % a->gn_rows_per_stat)
+      return fail(SA_ERR_INVALID, "sa_gemm_tap: gn_cpg must divide n and gn_rows_per_stat must divide M");
+    p.gn_stats = static_cast<double*>(a->gn_stats);
+    p.gn_groups = a->n / a->gn_cpg;
+    p.fd_gcpg.init(static_cast<uint32_t>(a->gn_cpg));
+    p.fd_grps.init(static_cast<uint32_t>(a->gn_rows_per_stat));
+    SA_CUDA_CHECK(cudaMemsetAsync(a->gn_stats, 0, sizeof(double) * 2 * p.gn_groups * (M / a->gn_rows_per_stat), stream));
+  }
   if (v2_ok) {
     // epilogue tensor maps: [n_out cols, d1, d2, d3]; box = (32 columns) x the 32-row sub-box
     // (s1, s2, s3) of the tile box that one epilogue warp owns, SWIZZLE_64B

@@ -641,10 +641,11 @@ static int gn_geometry(int C, long long P, int ns, dim3* block, dim3* grid, int*
 
 // x0 [rows, C0] (+ optional x1 [rows, C1], channel concat) -> stats [ns, 32, 2] (fp64 sum, sumsq)
 // then out [rows, C0+C1] = silu?(GN(x)).  rows = ns * rows_per_stat.
-extern "C" int sa_groupnorm(const void* x0, const void* x1, int32_t c0, int32_t c1, int32_t ld0,
-                            int32_t ld1, int64_t rows_per_stat, int32_t ns, const float* gamma,
-                            const float* beta, float eps, int32_t do_silu, void* stats_ws,
-                            void* out, int32_t ldo, void* stream_) {
+// have_stats: stats_ws already holds the sums (accumulated by the producing GEMM's epilogue) -> apply pass only
+static int groupnorm_impl(const void* x0, const void* x1, int32_t c0, int32_t c1, int32_t ld0,
+                          int32_t ld1, int64_t rows_per_stat, int32_t ns, const float* gamma,
+                          const float* beta, float eps, int32_t do_silu, void* stats_ws,
+                          void* out, int32_t ldo, void* stream_, bool have_stats) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int C = c0 + c1;
   if (!x0 || !out || !stats_ws || !gamma || !beta) return fail(SA_ERR_INVALID, "sa_groupnorm: null pointer");
@@ -654,7 +655,7 @@ extern "C" int sa_groupnorm(const void* x0, const void* x1, int32_t c0, int32_t 
   if (gn_geometry(C, rows_per_stat, ns, &block, &grid, &rpc))
     return fail(SA_ERR_INVALID, "sa_groupnorm: C=%d unsupported", C);
   const int cpg = C / 32;
-  SA_CUDA_CHECK(cudaMemsetAsync(stats_ws, 0, sizeof(double) * 64 * ns, stream));
+  if (!have_stats) SA_CUDA_CHECK(cudaMemsetAsync(stats_ws, 0, sizeof(double) * 64 * ns, stream));
   // streamed path: dense sources / output, enough bytes to fill the pipeline, tile rows dividing the group
   {
     int R = 32;
@@ -693,23 +694,43 @@ extern "C" int sa_groupnorm(const void* x0, const void* x1, int32_t c0, int32_t 
       long long g2 = static_cast<long long>(sms) * (smem_apply <= 110 * 1024 ? 2 : 1);
       if (g1 > sp.n_tiles) g1 = sp.n_tiles;
       if (g2 > sp.n_tiles) g2 = sp.n_tiles;
-      gn_stream_kernel<false><<<static_cast<unsigned>(g1), GN_CT + 32, smem_stats, stream>>>(sp);
-      SA_CUDA_CHECK(cudaGetLastError());
+      if (!have_stats) {
+        gn_stream_kernel<false><<<static_cast<unsigned>(g1), GN_CT + 32, smem_stats, stream>>>(sp);
+        SA_CUDA_CHECK(cudaGetLastError());
+      }
       gn_stream_kernel<true><<<static_cast<unsigned>(g2), GN_CT + 32, smem_apply, stream>>>(sp);
       SA_CUDA_CHECK(cudaGetLastError());
       return SA_OK;
     }
   }
-  gn_stats_kernel<<<grid, block, 0, stream>>>(
-      static_cast<const __nv_bfloat16*>(x0), static_cast<const __nv_bfloat16*>(x1), c0, c1, ld0, ld1,
-      rows_per_stat, cpg, rpc, static_cast<double*>(stats_ws));
-  SA_CUDA_CHECK(cudaGetLastError());
+  if (!have_stats) {
+    gn_stats_kernel<<<grid, block, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(x0), static_cast<const __nv_bfloat16*>(x1), c0, c1, ld0, ld1,
+        rows_per_stat, cpg, rpc, static_cast<double*>(stats_ws));
+    SA_CUDA_CHECK(cudaGetLastError());
+  }
   gn_apply_kernel<<<grid, block, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(x0), static_cast<const __nv_bfloat16*>(x1), c0, c1, ld0, ld1,
       rows_per_stat, cpg, rpc, static_cast<const double*>(stats_ws), gamma, beta, eps, do_silu,
       static_cast<__nv_bfloat16*>(out), ldo);
   SA_CUDA_CHECK(cudaGetLastError());
   return SA_OK;
+}
+
+extern "C" int sa_groupnorm(const void* x0, const void* x1, int32_t c0, int32_t c1, int32_t ld0,
+                            int32_t ld1, int64_t rows_per_stat, int32_t ns, const float* gamma,
+                            const float* beta, float eps, int32_t do_silu, void* stats_ws,
+                            void* out, int32_t ldo, void* stream_) {
+  return groupnorm_impl(x0, x1, c0, c1, ld0, ld1, rows_per_stat, ns, gamma, beta, eps, do_silu, stats_ws, out, ldo,
+                        stream_, false);
+}
+
+extern "C" int sa_groupnorm_apply(const void* x0, const void* x1, int32_t c0, int32_t c1, int32_t ld0,
+                                  int32_t ld1, int64_t rows_per_stat, int32_t ns, const float* gamma,
+                                  const float* beta, float eps, int32_t do_silu, const void* stats_ws,
+                                  void* out, int32_t ldo, void* stream_) {
+  return groupnorm_impl(x0, x1, c0, c1, ld0, ld1, rows_per_stat, ns, gamma, beta, eps, do_silu,
+                        const_cast<void*>(stats_ws), out, ldo, stream_, true);
 }
 
 extern "C" int sa_layernorm(const void* x, int32_t ldx, int64_t rows, int32_t c, const float* addv,

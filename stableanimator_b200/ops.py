@@ -68,6 +68,8 @@ def gemm_tap(
     tile_n: int = 0,
     out_scale: float = 1.0,
     f16_from_col: int = 0,
+    gn_stats: Optional[torch.Tensor] = None,
+    gn_rows_per_stat: int = 0,
 ) -> torch.Tensor:
     """``out = epilogue(sum_taps A(shifted) @ W^T)`` -- see ``sa_gemm_tap`` in include/sa_b200.h.
 
@@ -129,6 +131,12 @@ def gemm_tap(
     args.tile_n = tile_n
     args.out_scale = float(out_scale)
     args.f16_from_col = int(f16_from_col)
+    if gn_stats is not None:
+        # fused statistics of the output for the GroupNorm(32) that consumes it: fp64 [rows / rows_per_stat, 32, 2]
+        if gn_stats.dtype != torch.float64 or not gn_stats.is_contiguous() or n_out % 32 or \
+                gn_stats.numel() != rows // gn_rows_per_stat * 64:
+            raise ValueError("gn_stats must be a contiguous fp64 [rows / gn_rows_per_stat, 32, 2] tensor")
+        args.gn_stats, args.gn_cpg, args.gn_rows_per_stat = gn_stats.data_ptr(), n_out // 32, int(gn_rows_per_stat)
     check(lib().sa_gemm_tap(C.byref(args), _stream()), "sa_gemm_tap")
     return out
 
@@ -210,7 +218,9 @@ def attn_id_finalize(stats, vclip, wv, w_rowsum, bias, b, f, s, c, row_scale, ro
 # ----------------------------------------------------------------------------- normalisation
 def groupnorm(x0: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, rows_per_stat: int,
               *, x1: Optional[torch.Tensor] = None, silu: bool = True, stats_ws: Optional[torch.Tensor] = None,
-              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+              out: Optional[torch.Tensor] = None, stats_ready: bool = False) -> torch.Tensor:
+    """``stats_ready``: ``stats_ws`` was filled by the epilogue of the ``gemm_tap(..., gn_stats=stats_ws)`` launch that
+    produced ``x0`` -- only the normalise (+SiLU) pass runs (``sa_groupnorm_apply``)."""
     _chk_bf16(x0, "x0")
     c0 = x0.shape[-1]
     rows = x0.numel() // c0
@@ -221,15 +231,18 @@ def groupnorm(x0: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: fl
     ns = rows // rows_per_stat
     if ns * rows_per_stat != rows:
         raise ValueError("rows must be a multiple of rows_per_stat")
+    if stats_ready and (stats_ws is None or x1 is not None or stats_ws.numel() != ns * 64):
+        raise ValueError("stats_ready needs the fp64 [ns, 32, 2] statistics of a single-source input")
     if stats_ws is None:
         stats_ws = torch.empty((ns, 32, 2), device=x0.device, dtype=torch.float64)
     if out is None:
         out = torch.empty((rows, c0 + c1), device=x0.device, dtype=torch.bfloat16)
     _chk_f32(gamma, "gamma")
     _chk_f32(beta, "beta")
-    check(lib().sa_groupnorm(x0.data_ptr(), _ptr(x1), c0, c1, x0.stride(-2), ld1, rows_per_stat, ns,
-                             gamma.data_ptr(), beta.data_ptr(), float(eps), int(silu), stats_ws.data_ptr(),
-                             out.data_ptr(), out.stride(-2), _stream()), "sa_groupnorm")
+    fn, what = (lib().sa_groupnorm_apply, "sa_groupnorm_apply") if stats_ready else (lib().sa_groupnorm, "sa_groupnorm")
+    check(fn(x0.data_ptr(), _ptr(x1), c0, c1, x0.stride(-2), ld1, rows_per_stat, ns,
+             gamma.data_ptr(), beta.data_ptr(), float(eps), int(silu), stats_ws.data_ptr(),
+             out.data_ptr(), out.stride(-2), _stream()), what)
     return out
 
 

@@ -17,6 +17,7 @@ elements ``>= pose_batch_from`` only, cf. inference_pipeline_animation.py:663-68
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -54,6 +55,11 @@ class UNetB200:
             if tuple(state_dict[k].shape) != tuple(shp):
                 raise ValueError(f"{k}: shape {tuple(state_dict[k].shape)} != {shp}")
         self.w: Dict[str, torch.Tensor] = {}
+        # GroupNorm statistics accumulated by the producing convolution's epilogue instead of a separate statistics
+        # pass.  Correct and B-invariant (tests/test_gemm_gpu.py), but measured 0.5 ms SLOWER per B=2 call at 64x64x16
+        # (tools/unet_ab.py: the statistics pass re-reads a tensor that is still L2-resident, the epilogue work is
+        # not free) -- off by default, SA_GN_FUSE=1 turns it on
+        self.fuse_gn_stats = os.environ.get("SA_GN_FUSE", "0") == "1"
         self._pos_cache: Dict[Tuple[str, int, int], torch.Tensor] = {}
         self._pack(state_dict)
 
@@ -213,42 +219,57 @@ class UNetB200:
         return self._pos_cache[key]
 
     # ------------------------------------------------------------------ blocks
-    def _res_block(self, r: ResSpec, x0, x1, temb, B, F, h, wd):
-        """SpatioTemporalResBlock.forward (unet.py:1579-1608) on NHWC tokens.  x0 [M, C0] (+ skip x1)."""
+    def _res_block(self, r: ResSpec, x0, x1, temb, B, F, h, wd, x0_stats=None, out_stats=None):
+        """SpatioTemporalResBlock.forward (unet.py:1579-1608) on NHWC tokens.  x0 [M, C0] (+ skip x1).
+        The statistics of the three inner GroupNorms are accumulated by the epilogue of the convolution that
+        produces their input (sa_gemm_args.gn_stats), so each of them is a single normalise pass.  ``x0_stats``:
+        per-frame statistics of ``x0`` from its producer (single-source input only); ``out_stats``: fp64
+        [B*F, 32, 2] to fill with the per-frame statistics of the block's output for the GroupNorm that follows."""
         w = self.w
         S = h * wd
         s_, t_ = f"{r.name}.spatial_res_block", f"{r.name}.temporal_res_block"
         grid2d, gridt = (wd, h, B * F), (S, F, B)
-        n1 = ops.groupnorm(x0, w[f"{s_}.norm1.g"], w[f"{s_}.norm1.b"], r.eps, S, x1=x1, silu=True)
+        fuse = self.fuse_gn_stats
+        st_f = torch.empty((B * F, 32, 2), device=self.dev, dtype=torch.float64) if fuse else None   # per frame
+        st_t1 = torch.empty((B, 32, 2), device=self.dev, dtype=torch.float64) if fuse else None      # whole tile
+        st_t2 = torch.empty((B, 32, 2), device=self.dev, dtype=torch.float64) if fuse else None
+        n1 = ops.groupnorm(x0, w[f"{s_}.norm1.g"], w[f"{s_}.norm1.b"], r.eps, S, x1=x1, silu=True,
+                           stats_ws=x0_stats, stats_ready=x0_stats is not None)
         o_s = self.temb_off[s_]
         h1 = ops.gemm_tap(n1, w[f"{s_}.conv1.w"], grid=grid2d, taps=ops.TAPS_3X3, bias=w[f"{s_}.conv1.b"],
-                          row_bias=temb[:, o_s:o_s + r.cout], rows_per_group=F * S)
-        n2 = ops.groupnorm(h1, w[f"{s_}.norm2.g"], w[f"{s_}.norm2.b"], r.eps, S, silu=True)
+                          row_bias=temb[:, o_s:o_s + r.cout], rows_per_group=F * S, gn_stats=st_f, gn_rows_per_stat=S)
+        n2 = ops.groupnorm(h1, w[f"{s_}.norm2.g"], w[f"{s_}.norm2.b"], r.eps, S, silu=True, stats_ws=st_f,
+                           stats_ready=fuse)
         if r.shortcut:
             sc = ops.gemm_tap(x0, w[f"{s_}.conv_shortcut.w"], a1=x1, bias=w[f"{s_}.conv_shortcut.b"])
         else:
             sc = x0
         xs = ops.gemm_tap(n2, w[f"{s_}.conv2.w"], grid=grid2d, taps=ops.TAPS_3X3, bias=w[f"{s_}.conv2.b"],
-                          residual=sc)
+                          residual=sc, gn_stats=st_t1, gn_rows_per_stat=F * S)
         # temporal: GroupNorm statistics over the whole tile (5-D input, unet.py:1749), 3-tap conv over frames
-        n3 = ops.groupnorm(xs, w[f"{t_}.norm1.g"], w[f"{t_}.norm1.b"], r.eps, F * S, silu=True)
+        n3 = ops.groupnorm(xs, w[f"{t_}.norm1.g"], w[f"{t_}.norm1.b"], r.eps, F * S, silu=True, stats_ws=st_t1,
+                           stats_ready=fuse)
         o_t = self.temb_off[t_]
         h2 = ops.gemm_tap(n3, w[f"{t_}.conv1.w"], grid=gridt, taps=ops.TAPS_T3, bias=w[f"{t_}.conv1.b"],
-                          row_bias=temb[:, o_t:o_t + r.cout], rows_per_group=F * S)
-        n4 = ops.groupnorm(h2, w[f"{t_}.norm2.g"], w[f"{t_}.norm2.b"], r.eps, F * S, silu=True)
+                          row_bias=temb[:, o_t:o_t + r.cout], rows_per_group=F * S, gn_stats=st_t2,
+                          gn_rows_per_stat=F * S)
+        n4 = ops.groupnorm(h2, w[f"{t_}.norm2.g"], w[f"{t_}.norm2.b"], r.eps, F * S, silu=True, stats_ws=st_t2,
+                           stats_ready=fuse)
         # conv2 + residual (xs), then AlphaBlender: alpha*xs + (1-alpha)*(xs + conv2) == xs + (1-alpha)*conv2,
         # one epilogue with a single residual read
         return ops.gemm_tap(n4, w[f"{t_}.conv2.w"], grid=gridt, taps=ops.TAPS_T3, bias=w[f"{t_}.conv2.b"],
-                            residual=xs, out_scale=1.0 - w[f"{r.name}.alpha"])
+                            residual=xs, out_scale=1.0 - w[f"{r.name}.alpha"], gn_stats=out_stats, gn_rows_per_stat=S)
 
-    def _tst(self, t: TstSpec, x, ctx: _Ctx, B, F, h, wd):
-        """TransformerSpatioTemporalModel.forward (unet.py:623-708) on NHWC tokens x [M, C]."""
+    def _tst(self, t: TstSpec, x, ctx: _Ctx, B, F, h, wd, x_stats=None):
+        """TransformerSpatioTemporalModel.forward (unet.py:623-708) on NHWC tokens x [M, C].  ``x_stats``: per-frame
+        GroupNorm statistics of ``x`` accumulated by the res block that produced it."""
         w = self.w
         S, c, heads = h * wd, t.c, t.heads
         BF = B * F
         b = f"{t.name}.transformer_blocks.0"
         tb = f"{t.name}.temporal_transformer_blocks.0"
-        n = ops.groupnorm(x, w[f"{t.name}.norm.g"], w[f"{t.name}.norm.b"], 1e-6, S, silu=False)
+        n = ops.groupnorm(x, w[f"{t.name}.norm.g"], w[f"{t.name}.norm.b"], 1e-6, S, silu=False, stats_ws=x_stats,
+                          stats_ready=x_stats is not None)
         y = ops.gemm_tap(n, w[f"{t.name}.proj_in.w"], bias=w[f"{t.name}.proj_in.b"])
         # --- BasicTransformerBlock (unet.py:525-556)
         a = ops.layernorm(y, w[f"{b}.norm1.g"], w[f"{b}.norm1.b"])
@@ -292,6 +313,9 @@ class UNetB200:
                           alpha=w[f"{t.name}.alpha"])
         return ops.gemm_tap(z4, w[f"{t.name}.proj_out.w"], bias=w[f"{t.name}.proj_out.b"], residual=x)
 
+    def _frame_stats(self, n: int) -> Optional[torch.Tensor]:
+        return torch.empty((n, 32, 2), device=self.dev, dtype=torch.float64) if self.fuse_gn_stats else None
+
     def _conv_in(self, x_in: torch.Tensor, pose: Optional[torch.Tensor], pose_from: int) -> torch.Tensor:
         """conv_in (unet.py:283) + pose residual on the frames >= pose_from (:284-286) -> tokens [M, C0].
         K = 72 is gathered to a [M, 128] operand and runs on the tensor-core GEMM (two launches when only
@@ -333,11 +357,12 @@ class UNetB200:
         for st in self.stages:
             if st.kind == "down":
                 for r, t in zip(st.res, st.tst):
-                    x = self._res_block(r, x, None, temb, B, F, ch, cw)
+                    xst = self._frame_stats(B * F) if t is not None else None
+                    x = self._res_block(r, x, None, temb, B, F, ch, cw, out_stats=xst)
                     if taps is not None:
                         taps[r.name] = x
                     if t is not None:
-                        x = self._tst(t, x, ctx, B, F, ch, cw)
+                        x = self._tst(t, x, ctx, B, F, ch, cw, x_stats=xst)
                         if taps is not None:
                             taps[t.name] = x
                     skips.append(x)
@@ -347,16 +372,18 @@ class UNetB200:
                     ch, cw = ch // 2, cw // 2
                     skips.append(x)
             elif st.kind == "mid":
-                x = self._res_block(st.res[0], x, None, temb, B, F, ch, cw)
-                x = self._tst(st.tst[0], x, ctx, B, F, ch, cw)
+                xst = self._frame_stats(B * F)
+                x = self._res_block(st.res[0], x, None, temb, B, F, ch, cw, out_stats=xst)
+                x = self._tst(st.tst[0], x, ctx, B, F, ch, cw, x_stats=xst)
                 x = self._res_block(st.res[1], x, None, temb, B, F, ch, cw)
                 if taps is not None:
                     taps["mid_block"] = x
             else:
                 for r, t in zip(st.res, st.tst):
-                    x = self._res_block(r, x, skips.pop(), temb, B, F, ch, cw)
+                    xst = self._frame_stats(B * F) if t is not None else None
+                    x = self._res_block(r, x, skips.pop(), temb, B, F, ch, cw, out_stats=xst)
                     if t is not None:
-                        x = self._tst(t, x, ctx, B, F, ch, cw)
+                        x = self._tst(t, x, ctx, B, F, ch, cw, x_stats=xst)
                     if taps is not None:
                         taps[r.name] = x
                 if st.upsample:

@@ -179,3 +179,52 @@ def test_fp16_column_block():
     assert ((v - vref).abs() <= 2.0 ** -10 * vref.abs() + 1e-5).all()
     with pytest.raises(Exception):
         ops.gemm_tap(a, w, f16_from_col=2 * c + 8)
+
+
+@pytest.mark.parametrize("f,h,w_,cin,cout,per_frame", [
+    (4, 16, 16, 64, 64, True),       # cpg 2, uniform warps
+    (4, 16, 16, 128, 320, True),     # cpg 10: groups straddle the 32-column chunks
+    (4, 16, 16, 128, 320, False),    # whole-tile statistics (temporal GroupNorm)
+    (2, 8, 8, 64, 640, True),        # S = 64: two frames per 128-row tile
+    (3, 18, 9, 64, 1280, True),      # cpg 40 > 32; ragged boxes (rows outside the grid, mixed frames per warp)
+    (2, 72, 36, 64, 320, True),      # the 576x1024 geometry one level down
+])
+def test_conv3x3_fused_groupnorm_statistics(f, h, w_, cin, cout, per_frame):
+    """sa_gemm_args.gn_stats: Sum / Sum^2 of the bf16 output per (statistic, group) accumulated by the epilogue equal
+    the sums over the tensor the launch wrote, and sa_groupnorm_apply on them equals the two-pass sa_groupnorm."""
+    from stableanimator_b200 import ops
+    x = rnd(f, h, w_, cin, seed=31)
+    wp = rnd(cout, 9 * cin, scale=(9 * cin) ** -0.5, seed=32)
+    bias = torch.randn(cout, device="cuda")
+    res = rnd(f * h * w_, cout, seed=33)
+    rps = h * w_ if per_frame else f * h * w_
+    ns = f * h * w_ // rps
+    st = torch.full((ns, 32, 2), 7.0, device="cuda", dtype=torch.float64)   # the call zeroes it
+    plain = ops.gemm_tap(x, wp, grid=(w_, h, f), taps=ops.TAPS_3X3, bias=bias, residual=res, out_scale=0.5)
+    out = ops.gemm_tap(x, wp, grid=(w_, h, f), taps=ops.TAPS_3X3, bias=bias, residual=res, out_scale=0.5,
+                       gn_stats=st, gn_rows_per_stat=rps)
+    assert torch.equal(out, plain)                                          # the output itself is untouched
+    v = out.double().reshape(ns, rps, 32, cout // 32)
+    ref = torch.stack([v.sum(dim=(1, 3)), (v * v).sum(dim=(1, 3))], dim=-1)
+    assert torch.allclose(st, ref, rtol=2e-6, atol=1e-6 * ref.abs().max().item()), (st - ref).abs().max().item()
+    gamma, beta = torch.rand(cout, device="cuda") + 0.5, torch.randn(cout, device="cuda")
+    two_pass = ops.groupnorm(out, gamma, beta, 1e-5, rps, silu=True)
+    fused = ops.groupnorm(out, gamma, beta, 1e-5, rps, silu=True, stats_ws=st, stats_ready=True)
+    assert (two_pass.float() - fused.float()).abs().max().item() <= 2.0 ** -7 * two_pass.float().abs().max().item()
+
+
+def test_fused_groupnorm_statistics_plain_and_rejections():
+    """A launch with no other epilogue feature still produces statistics (it leaves the PLAIN instantiation);
+    GEGLU / fp32 output / fp16 column blocks are rejected loudly."""
+    from stableanimator_b200 import ops
+    from stableanimator_b200._lib import SaKernelError
+    a, w = rnd(512, 128, seed=41), rnd(256, 128, scale=128 ** -0.5, seed=42)
+    st = torch.empty((4, 32, 2), device="cuda", dtype=torch.float64)
+    out = ops.gemm_tap(a, w, gn_stats=st, gn_rows_per_stat=128)
+    v = out.double().reshape(4, 128, 32, 8)
+    assert torch.allclose(st[..., 0], v.sum(dim=(1, 3)), rtol=2e-6, atol=1e-5)
+    with pytest.raises(SaKernelError):
+        ops.gemm_tap(a, w, geglu=True, gn_stats=torch.empty((4, 32, 2), device="cuda", dtype=torch.float64),
+                     gn_rows_per_stat=128)
+    with pytest.raises(SaKernelError):
+        ops.gemm_tap(a, w, out_f32=True, gn_stats=st, gn_rows_per_stat=128)

@@ -87,3 +87,28 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", tmp_path / "nope.so")
     with pytest.raises(_lib.SaLibraryError):
         _lib.lib()
+
+
+def test_unet_fused_groupnorm_statistics_option():
+    """SA_GN_FUSE / UNetB200.fuse_gn_stats: GroupNorm statistics accumulated by the producing convolution's epilogue
+    (sa_gemm_args.gn_stats + sa_groupnorm_apply).  Same golden tolerance; B=2 still gives the bits of two B=1 calls
+    (fp64 accumulation makes the statistics independent of how rows fall into tiles)."""
+    c = load_golden("tiny_cond_f4_16x16")
+    m = model(c["cfg"], c["gold"]["seed"])
+    pl = c["pose_latents"].cuda()
+    args = (c["sample"].cuda(), c["t"], c["ehs"].cuda(), c["ati"].cuda())
+    plain = m(*args, pose_latents=pl)[0]
+    m.fuse_gn_stats = True
+    try:
+        fused = m(*args, pose_latents=pl)[0]
+        s2 = torch.cat([c["sample"] * 0.5, c["sample"]], 0).cuda()
+        ehs2 = torch.cat([torch.zeros_like(c["ehs"]), c["ehs"]], 0).cuda()
+        ati2 = torch.cat([c["ati"], c["ati"]], 0).cuda()
+        both = m(s2, c["t"], ehs2, ati2, pose_latents=pl, pose_batch_from=1)[0]
+        a = m(s2[:1], c["t"], ehs2[:1], ati2[:1], pose_latents=None)[0]
+    finally:
+        m.fuse_gn_stats = False
+    ref = c["gold"]["out"].cuda()
+    print(f"fused-statistics UNet vs reference: {rel_l2(fused, ref):.3e} (two-pass: {rel_l2(plain, ref):.3e})")
+    assert rel_l2(fused, ref) <= 1e-2
+    assert torch.equal(both[:1], a) and torch.equal(both[1:], fused)

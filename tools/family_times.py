@@ -36,7 +36,7 @@ def elided(name):
                                    torch.float32 if kw.get("out_f32") else torch.bfloat16)
         return f
     if name == "groupnorm":
-        def f(x0, gamma, beta, eps, rps, *, x1=None, silu=True, stats_ws=None, out=None):
+        def f(x0, gamma, beta, eps, rps, *, x1=None, silu=True, stats_ws=None, out=None, stats_ready=False):
             c = x0.shape[-1] + (0 if x1 is None else x1.shape[-1])
             return out if out is not None else _empty_like_out(x0.numel() // x0.shape[-1], c, x0.device)
         return f
