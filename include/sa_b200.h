@@ -87,6 +87,11 @@ typedef struct sa_gemm_args {
   void* gn_stats;
   int32_t gn_cpg;            /* channels per group (n_out / 32 for nn.GroupNorm(32, n_out)) */
   int32_t gn_rows_per_stat;  /* rows sharing one statistic: h*w (per frame) or F*h*w (whole tile) */
+  /* Strided output grid: element strides of `out` along grid dims 2 and 3 (0 = dense: ldc*d1, ldc*d1*d2).  Lets one */
+  /* launch write every other pixel of a larger image -- the four output phases of Upsample2D (nearest x2 followed   */
+  /* by the 3x3 conv, unet.py:1789-1807) computed as 2x2-tap convolutions on the low-resolution input.  bf16 output, */
+  /* n % tile == 0, no residual / blend_x / gn_stats.                                                                */
+  int64_t ldc2, ldc3;
 } sa_gemm_args;
 
 int sa_gemm_tap(const sa_gemm_args* args, void* stream);

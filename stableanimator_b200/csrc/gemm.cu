@@ -963,7 +963,21 @@ extern "C" int sa_gemm_tap(const sa_gemm_args* a, void* stream_) {
       uint32_t box[4] = {32, static_cast<uint32_t>(s1), static_cast<uint32_t>(s2), static_cast<uint32_t>(s3)};
       return get_tmap_bf16(base, 4, dims, strides, box, 64);
     };
-    const CUtensorMap* tmo = epi_map(a->out, a->ldc);
+    const CUtensorMap* tmo;
+    if (a->ldc2 || a->ldc3) {  // strided output grid (Upsample2D phases)
+      const long long s2_ = a->ldc2 ? a->ldc2 : static_cast<long long>(a->ldc) * a->d1;
+      const long long s3_ = a->ldc3 ? a->ldc3 : s2_ * a->d2;
+      if (a->residual || a->blend_x || a->gn_stats || s2_ % 8 || s3_ % 8 || s2_ < a->ldc || s3_ < s2_)
+        return fail(SA_ERR_INVALID, "sa_gemm_tap: strided output (ldc2/ldc3) excludes residual / blend_x / gn_stats");
+      uint64_t dims[4] = {static_cast<uint64_t>(n_out), static_cast<uint64_t>(a->d1),
+                          static_cast<uint64_t>(a->d2), static_cast<uint64_t>(a->d3)};
+      uint64_t strides[3] = {static_cast<uint64_t>(a->ldc) * 2, static_cast<uint64_t>(s2_) * 2,
+                             static_cast<uint64_t>(s3_) * 2};
+      uint32_t box[4] = {32, static_cast<uint32_t>(s1), static_cast<uint32_t>(s2), static_cast<uint32_t>(s3)};
+      tmo = get_tmap_bf16(a->out, 4, dims, strides, box, 64);
+    } else {
+      tmo = epi_map(a->out, a->ldc);
+    }
     const CUtensorMap* tmr = a->residual ? epi_map(a->residual, a->ldr) : tmo;
     const CUtensorMap* tmx = a->blend_x ? epi_map(a->blend_x, a->ldx) : tmo;
     if (!tmo || !tmr || !tmx) return SA_ERR_TMA;
@@ -987,6 +1001,8 @@ extern "C" int sa_gemm_tap(const sa_gemm_args* a, void* stream_) {
   }
   if (a->f16_from_col > 0)
     return fail(SA_ERR_INVALID, "sa_gemm_tap: f16_from_col needs the persistent bf16 path (n %% tile == 0, tile >= 64)");
+  if (a->ldc2 || a->ldc3)
+    return fail(SA_ERR_INVALID, "sa_gemm_tap: strided output needs the persistent bf16 path (n %% tile == 0, tile >= 64)");
   switch (bn) {
     case 32: return launch<32, 4>(tma[0], tma[1], tmb, p, mt, stream);
     case 64: return launch<64, 4>(tma[0], tma[1], tmb, p, mt, stream);

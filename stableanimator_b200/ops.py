@@ -127,6 +127,11 @@ def gemm_tap(
     args.alpha = float(alpha)
     args.geglu = int(geglu)
     args.out, args.ldc = out.data_ptr(), out.stride(-2)
+    if out.dim() == 4 and not out.is_contiguous():
+        # strided output grid (every other pixel of a larger image): [d3, d2, d1, n_out] view with arbitrary strides
+        if tuple(out.shape[:3]) != (d3, d2, d1) or out.stride(-1) != 1:
+            raise ValueError("a strided `out` must be a [d3, d2, d1, n_out] view")
+        args.ldc2, args.ldc3 = out.stride(1), out.stride(0)
     args.out_f32 = int(out.dtype == torch.float32)
     args.tile_n = tile_n
     args.out_scale = float(out_scale)
@@ -138,6 +143,33 @@ def gemm_tap(
             raise ValueError("gn_stats must be a contiguous fp64 [rows / gn_rows_per_stat, 32, 2] tensor")
         args.gn_stats, args.gn_cpg, args.gn_rows_per_stat = gn_stats.data_ptr(), n_out // 32, int(gn_rows_per_stat)
     check(lib().sa_gemm_tap(C.byref(args), _stream()), "sa_gemm_tap")
+    return out
+
+
+# (py, px, taps) of the four output phases of nearest-x2 + conv3x3, in the order upsample_conv_phases() packs them
+UPSAMPLE_PHASE_TAPS = tuple((py, px, tuple((px - 1 + tx, py - 1 + ty, 0) for ty in (0, 1) for tx in (0, 1)))
+                            for py in (0, 1) for px in (0, 1))
+
+
+def upsample_conv_phases(w_oihw: torch.Tensor):
+    """Upsample2D = nearest x2 then Conv2d 3x3 pad 1 (unet.py:1789-1807) as four 2x2-tap convolutions on the
+    LOW-resolution input, one per output phase (py, px): out[2y + py, 2x + px] = sum over (ty, tx) in {0,1}^2 of
+    Wp[ty, tx] . in[y + py - 1 + ty, x + px - 1 + tx], where Wp sums the original taps that read the same input pixel
+    (py = 0: rows {ky0} | {ky1 + ky2}; py = 1: rows {ky0 + ky1} | {ky2}; same along x).  4/9 of the multiply-adds and
+    no upsampled tensor.  Returns [(py, px, taps, weight fp32 [O, (ty, tx, ci)])]; the zero padding of the upsampled
+    image maps onto the zero padding of the low-resolution one."""
+    w = w_oihw.float()
+    rows = {0: ([0], [1, 2]), 1: ([0, 1], [2])}
+    out = []
+    for py in (0, 1):
+        for px in (0, 1):
+            blocks, taps = [], []
+            for ty in (0, 1):
+                for tx in (0, 1):
+                    acc = sum(w[:, :, ky, kx] for ky in rows[py][ty] for kx in rows[px][tx])   # [O, I]
+                    blocks.append(acc)
+                    taps.append((px - 1 + tx, py - 1 + ty, 0))
+            out.append((py, px, tuple(taps), torch.cat(blocks, dim=1).contiguous()))
     return out
 
 

@@ -60,6 +60,8 @@ class UNetB200:
         # (tools/unet_ab.py: the statistics pass re-reads a tensor that is still L2-resident, the epilogue work is
         # not free) -- off by default, SA_GN_FUSE=1 turns it on
         self.fuse_gn_stats = os.environ.get("SA_GN_FUSE", "0") == "1"
+        # Upsample2D as four phase convolutions (4/9 of the MACs; SA_UP_PHASES=0: upsample2x + 3x3 conv, for A/B)
+        self.upsample_phases = os.environ.get("SA_UP_PHASES", "1") != "0"
         self._pos_cache: Dict[Tuple[str, int, int], torch.Tensor] = {}
         self._pack(state_dict)
 
@@ -152,6 +154,9 @@ class UNetB200:
             for key in (st.downsample, st.upsample):
                 if key:
                     conv3(key)
+            if st.upsample:  # Upsample2D as four 2x2-tap phase convolutions on the low-resolution input
+                for i, (_, _, _, wp) in enumerate(ops.upsample_conv_phases(sd[f"{st.upsample}.weight"])):
+                    w[f"{st.upsample}.ph{i}.w"] = _bf16(wp, dev)
         w["temb_all.w"] = _bf16(torch.cat(temb_w, 0), dev)
         w["temb_all.b"] = _f32(torch.cat(temb_b, 0), dev)
         w["ctx_all.w"] = _bf16(torch.cat(ctx_w, 0), dev)
@@ -386,7 +391,17 @@ class UNetB200:
                         x = self._tst(t, x, ctx, B, F, ch, cw, x_stats=xst)
                     if taps is not None:
                         taps[r.name] = x
-                if st.upsample:
+                if st.upsample and self.upsample_phases:
+                    # nearest x2 + conv3x3 (unet.py:1789-1807): each output phase (py, px) is a 2x2-tap convolution of
+                    # the low-resolution tensor written to every other pixel -- 4/9 of the MACs, no upsampled tensor
+                    xin = x.reshape(B * F, ch, cw, st.cout)
+                    up = torch.empty((B * F, 2 * ch, 2 * cw, st.cout), device=self.dev, dtype=torch.bfloat16)
+                    for i, (py, px, ptaps) in enumerate(ops.UPSAMPLE_PHASE_TAPS):
+                        ops.gemm_tap(xin, w[f"{st.upsample}.ph{i}.w"], grid=(cw, ch, B * F), taps=ptaps,
+                                     bias=w[f"{st.upsample}.b"], out=up[:, py::2, px::2, :])
+                    ch, cw = ch * 2, cw * 2
+                    x = up.reshape(-1, st.cout)
+                elif st.upsample:
                     up = ops.upsample2x(x.reshape(B * F, ch, cw, st.cout))
                     ch, cw = ch * 2, cw * 2
                     x = ops.gemm_tap(up, w[f"{st.upsample}.w"], grid=(cw, ch, B * F), taps=ops.TAPS_3X3,

@@ -13,7 +13,7 @@ channel-innermost bf16 layout:
     ``S = Q K^T`` (fp32 out), ``sa_softmax_rows``, ``O = P V`` with ``V^T`` produced directly by a GEMM with the
     roles of weights and activations swapped; the value bias is added after the product (rows of P sum to 1);
   * conv_in (4 input channels): ``sa_conv_direct``; conv_out (3 channels, fp32): ``sa_gemm_tap``;
-    ``time_conv_out``: ``sa_time_conv_out``; nearest x2: ``sa_upsample2x``.
+    ``time_conv_out``: ``sa_time_conv_out``; nearest x2 + conv3x3: four phase convolutions (``ops.upsample_conv_phases``).
 """
 from __future__ import annotations
 
@@ -85,8 +85,10 @@ class TemporalDecoderB200:
                 norm(f"{t_}.norm1"); convt(f"{t_}.conv1"); norm(f"{t_}.norm2"); convt(f"{t_}.conv2")
                 # AlphaBlender (vae.py:957-965): weight of the temporal branch = sigmoid(mix_factor)
                 w[f"{name}.s"] = float(torch.sigmoid(sd[f"{name}.time_mixer.mix_factor"].float()).item())
-            if up:
-                conv3(up)
+            if up:  # Upsample2D (vae.py: nearest x2 + conv3x3) as four 2x2-tap phase convolutions, see ops.upsample_conv_phases
+                w[f"{up}.b"] = _f32(sd[f"{up}.bias"], dev)
+                for i, (_, _, _, wp) in enumerate(ops.upsample_conv_phases(sd[f"{up}.weight"])):
+                    w[f"{up}.ph{i}.w"] = _bf16(wp, dev)
         a = "mid_block.attentions.0"
         norm(f"{a}.group_norm")
         for n in ("to_q", "to_k", "to_v", "to_out.0"):
@@ -173,9 +175,13 @@ class TemporalDecoderB200:
                 x = self._res_block(rname, ci, co, x, B, F, h, wd)
             if up:
                 co = res[-1][2]
-                xu = ops.upsample2x(x.reshape(BF, h, wd, co))
+                xin = x.reshape(BF, h, wd, co)
+                xu = torch.empty((BF, 2 * h, 2 * wd, co), device=self.dev, dtype=torch.bfloat16)
+                for i, (py, px, ptaps) in enumerate(ops.UPSAMPLE_PHASE_TAPS):
+                    ops.gemm_tap(xin, w[f"{up}.ph{i}.w"], grid=(wd, h, BF), taps=ptaps, bias=w[f"{up}.b"],
+                                 out=xu[:, py::2, px::2, :])
                 h, wd = 2 * h, 2 * wd
-                x = ops.gemm_tap(xu, w[f"{up}.w"], grid=(wd, h, BF), taps=ops.TAPS_3X3, bias=w[f"{up}.b"])
+                x = xu.reshape(-1, co)
         n = ops.groupnorm(x, w["conv_norm_out.g"], w["conv_norm_out.b"], 1e-6, h * wd, silu=True)
         y = ops.gemm_tap(n, w["conv_out.w"], grid=(wd, h, BF), taps=ops.TAPS_3X3, bias=w["conv_out.b"], out_f32=True)
         out = torch.empty((BF, cfg.out_channels, h, wd), device=self.dev, dtype=torch.float32)

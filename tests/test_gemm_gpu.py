@@ -4,7 +4,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from util import assert_close
+from util import assert_close, rel_l2
 
 pytestmark = pytest.mark.gpu
 
@@ -228,3 +228,23 @@ def test_fused_groupnorm_statistics_plain_and_rejections():
                      gn_rows_per_stat=128)
     with pytest.raises(SaKernelError):
         ops.gemm_tap(a, w, out_f32=True, gn_stats=st, gn_rows_per_stat=128)
+
+
+@pytest.mark.parametrize("f,h,w_,c,cout", [(2, 8, 8, 64, 64), (3, 16, 12, 128, 64), (2, 9, 18, 64, 128), (16, 32, 32, 640, 640)])
+def test_upsample_conv_as_phase_convolutions(f, h, w_, c, cout):
+    """Upsample2D (nearest x2 + conv3x3, unet.py:1789-1807) as four 2x2-tap launches writing every other pixel
+    (strided output grid, sa_gemm_args.ldc2 / ldc3) vs conv2d(interpolate(x)) and vs the upsample2x + 3x3 path."""
+    from stableanimator_b200 import ops
+    x = rnd(f, h, w_, c, seed=51)
+    wt = rnd(cout, c, 3, 3, scale=(9 * c) ** -0.5, seed=52)
+    bias = torch.randn(cout, device="cuda")
+    out = torch.full((f, 2 * h, 2 * w_, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    for (py, px, taps), (_, _, taps2, wp) in zip(ops.UPSAMPLE_PHASE_TAPS, ops.upsample_conv_phases(wt)):
+        assert taps == taps2
+        ops.gemm_tap(x, wp.bfloat16(), grid=(w_, h, f), taps=taps, bias=bias, out=out[:, py::2, px::2, :])
+    up = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest")
+    ref = F.conv2d(up, wt.float(), bias, padding=1).permute(0, 2, 3, 1)
+    assert_close(out, ref)
+    wp9 = wt.permute(0, 2, 3, 1).reshape(cout, 9 * c).contiguous()
+    old = ops.gemm_tap(ops.upsample2x(x), wp9, grid=(2 * w_, 2 * h, f), taps=ops.TAPS_3X3, bias=bias)
+    assert rel_l2(out.float(), old.reshape(out.shape).float()) <= 2.0 ** -8
