@@ -50,14 +50,18 @@ class _GraphedUNet:
                 self._run()
             self.graph = g
 
-    def refresh_context(self, ctx) -> None:
-        """New conditioning for the same shapes: overwrite the static buffers the graph reads."""
+    def refresh_context(self, ctx) -> bool:
+        """New conditioning for the same shapes: overwrite the static buffers the graph reads.  Returns False when
+        the captured control flow does not fit the new conditioning (a different zero-context prefix)."""
         if ctx is self.ctx:
-            return
+            return True
+        if ctx.zero_prefix != self.ctx.zero_prefix:
+            return False
         self.ctx.all.copy_(ctx.all)
         for k in self.ctx.wv:
             self.ctx.wv[k].copy_(ctx.wv[k])
             self.ctx.tconst[k].copy_(ctx.tconst[k])
+        return True
 
     def _run(self):
         self.out = self.unet.forward_nhwc(self.x_in, self.t, self.ctx, self.ati, self.B, self.T, self.h, self.w,
@@ -131,10 +135,12 @@ class AnimationSampler:
         if key in plan["runners"]:
             if key not in plan["fresh"]:  # first use in this video: conditioning may have changed
                 run = plan["runners"][key]
-                run.refresh_context(self.unet.prepare_context(ehs[rows]))
-                run.ati.copy_(ati[rows])
-                plan["fresh"].add(key)
-        else:
+                if run.refresh_context(self.unet.prepare_context(ehs[rows])):
+                    run.ati.copy_(ati[rows])
+                    plan["fresh"].add(key)
+                else:  # e.g. an all-zero context became non-zero: capture a new graph
+                    del plan["runners"][key]
+        if key not in plan["runners"]:
             plan["fresh"].add(key)
             ctx = self.unet.prepare_context(ehs[rows])
             with_pose = has_pose and (1 in branches)

@@ -36,7 +36,7 @@ def _f32(t: torch.Tensor, dev) -> torch.Tensor:
 
 class _Ctx:
     """Per-call context-derived tensors (they depend on encoder_hidden_states only)."""
-    __slots__ = ("all", "wv", "tconst", "b")
+    __slots__ = ("all", "wv", "tconst", "b", "zero_prefix")
 
 
 class UNetB200:
@@ -60,6 +60,8 @@ class UNetB200:
         # (tools/unet_ab.py: the statistics pass re-reads a tensor that is still L2-resident, the epilogue work is
         # not free) -- off by default, SA_GN_FUSE=1 turns it on
         self.fuse_gn_stats = os.environ.get("SA_GN_FUSE", "0") == "1"
+        # zero-context (unconditional CFG branch) shortcut of the ID cross-attention; SA_SKIP_ZERO_CTX=0 for A/B
+        self.skip_zero_context = os.environ.get("SA_SKIP_ZERO_CTX", "1") != "0"
         # Upsample2D as four phase convolutions (4/9 of the MACs; SA_UP_PHASES=0: upsample2x + 3x3 conv, for A/B)
         self.upsample_phases = os.environ.get("SA_UP_PHASES", "1") != "0"
         self._pos_cache: Dict[Tuple[str, int, int], torch.Tensor] = {}
@@ -196,6 +198,12 @@ class UNetB200:
                              f"{self.cfg.cross_attention_dim}], got {tuple(ehs.shape)}")
         ctx = _Ctx()
         ctx.b = B
+        # leading batch elements whose conditioning is exactly zero (the unconditional CFG branch,
+        # inference_pipeline_animation.py:232-241, :526-533): for them the ID cross-attention is the constant to_out bias
+        # (k = v = 0 -> both attention branches and all four alignment statistics are 0, unet.py:1999-2024), so
+        # _tst skips norm2 / to_q / attention / to_out on their rows.  One host read per video, none per step.
+        nz = (ehs.abs().amax(dim=(1, 2)) > 0).tolist()
+        ctx.zero_prefix = next((i for i, v in enumerate(nz) if v), B) if self.skip_zero_context else 0
         ctx.all = ops.small_linear(ehs.reshape(B * L, D), w["ctx_all.w"]).reshape(B, L, self.n_ctx)
         ctx.wv, ctx.tconst = {}, {}
         for st in self.stages:
@@ -281,21 +289,31 @@ class UNetB200:
         qkv = ops.gemm_tap(a, w[f"{b}.attn1.qkv"], f16_from_col=2 * c)  # v block in fp16 for the P V MMA
         o = ops.attn_spatial(qkv, BF, S, heads)
         y1 = ops.gemm_tap(o, w[f"{b}.attn1.to_out.0.w"], bias=w[f"{b}.attn1.to_out.0.b"], residual=y)
-        a = ops.layernorm(y1, w[f"{b}.norm2.g"], w[f"{b}.norm2.b"])
-        q = ops.gemm_tap(a, w[f"{b}.attn2.to_q.w"])
+        # attn2 (ID cross-attention) on the batch elements with a non-zero context; for the zero-context prefix
+        # (rows [0, mz)) the block adds the constant to_out bias, fused into norm3 below
+        zb = ctx.zero_prefix
+        mz, bn = zb * F * S, B - zb
         off = self.ctx_off[t.name]
         nt = self.cfg.num_tokens
-        ik = ctx.all[:, 1:1 + nt, off + c:off + 2 * c]
-        iv = ctx.all[:, 1:1 + nt, off + 2 * c:off + 3 * c]
-        stats = torch.empty((BF, 2), device=self.dev, dtype=torch.float64)
-        ip = ops.attn_id(q, ik, iv, B, F, S, heads, stats)
-        rs = torch.empty((BF,), device=self.dev, dtype=torch.float32)
-        rb = torch.empty((BF, c), device=self.dev, dtype=torch.float32)
-        ops.attn_id_finalize(stats, ctx.all[:, 0, off:off + c], ctx.wv[t.name], w[f"{b}.attn2.rowsum"],
-                             w[f"{b}.attn2.to_out.0.b"], B, F, S, c, rs, rb)
-        y2 = ops.gemm_tap(ip, w[f"{b}.attn2.to_out.0.w"], row_scale=rs, row_bias=rb, rows_per_group=S,
-                          residual=y1)
-        a = ops.layernorm(y2, w[f"{b}.norm3.g"], w[f"{b}.norm3.b"])
+        y2 = torch.empty_like(y1)
+        a = torch.empty_like(y1)
+        if bn > 0:
+            an = ops.layernorm(y1[mz:], w[f"{b}.norm2.g"], w[f"{b}.norm2.b"])
+            q = ops.gemm_tap(an, w[f"{b}.attn2.to_q.w"])
+            ik = ctx.all[zb:, 1:1 + nt, off + c:off + 2 * c]
+            iv = ctx.all[zb:, 1:1 + nt, off + 2 * c:off + 3 * c]
+            stats = torch.empty((bn * F, 2), device=self.dev, dtype=torch.float64)
+            ip = ops.attn_id(q, ik, iv, bn, F, S, heads, stats)
+            rs = torch.empty((bn * F,), device=self.dev, dtype=torch.float32)
+            rb = torch.empty((bn * F, c), device=self.dev, dtype=torch.float32)
+            ops.attn_id_finalize(stats, ctx.all[zb:, 0, off:off + c], ctx.wv[t.name][zb:], w[f"{b}.attn2.rowsum"],
+                                 w[f"{b}.attn2.to_out.0.b"], bn, F, S, c, rs, rb)
+            ops.gemm_tap(ip, w[f"{b}.attn2.to_out.0.w"], row_scale=rs, row_bias=rb, rows_per_group=S,
+                         residual=y1[mz:], out=y2[mz:])
+            ops.layernorm(y2[mz:], w[f"{b}.norm3.g"], w[f"{b}.norm3.b"], out=a[mz:])
+        if zb > 0:  # y2 = y1 + to_out.bias, a = norm3(y2) in one pass
+            ops.layernorm(y1[:mz], w[f"{b}.norm3.g"], w[f"{b}.norm3.b"], addv=w[f"{b}.attn2.to_out.0.b"].reshape(1, c),
+                          rows_per_group=mz, x_out=y2[:mz], out=a[:mz])
         g = ops.gemm_tap(a, w[f"{b}.ff.w1"], bias=w[f"{b}.ff.b1"], geglu=True)
         y3 = ops.gemm_tap(g, w[f"{b}.ff.w2"], bias=w[f"{b}.ff.b2"], residual=y2)
         # --- TemporalBasicTransformerBlock (unet.py:919-958) on hidden + frame-position embedding (:686)

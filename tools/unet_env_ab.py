@@ -1,5 +1,5 @@
 """A/B of env-selected UNet options in ONE process (graphs replayed alternately): python tools/unet_env_ab.py ATTR
-where ATTR is a boolean attribute of UNetB200 (upsample_phases, fuse_gn_stats)."""
+where ATTR is a boolean attribute of UNetB200 (upsample_phases, fuse_gn_stats, skip_zero_context)."""
 import sys
 from pathlib import Path
 
@@ -17,13 +17,13 @@ cfg = UNetConfig.full()
 unet = UNetB200(cfg, synth_unet_state_dict(cfg), "cuda")
 B, F = 2, 16
 inp = synth_inputs(cfg, F, h, w)
-ctx = unet.prepare_context(inp["encoder_hidden_states"][:B].cuda())
 ati = inp["added_time_ids"][:B].cuda()
 x = torch.randn(B * F, h, w, 8, device="cuda").bfloat16()
 t = torch.tensor(1.0, device="cuda")
-graphs, outs = {}, {}
+graphs, outs, ctxs = {}, {}, {}   # ctxs: the graphs read these buffers, keep them alive
 for val in (True, False):
     setattr(unet, attr, val)
+    ctx = ctxs[val] = unet.prepare_context(inp["encoder_hidden_states"][:B].cuda())
     unet.forward_nhwc(x, t, ctx, ati, B, F, h, w)
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
