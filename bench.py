@@ -116,8 +116,9 @@ def cpu_reference_sample(frames: int, hw: int, cfg_name: str = "full", w: int = 
     torch.set_num_threads(cores)
     cfg = UNetConfig.full() if cfg_name == "full" else UNetConfig.tiny()
     sd = synth_unet_state_dict(cfg)
-    inp = synth_inputs(cfg, frames, lh, lw)
-    sample = torch.cat([inp["latents"].expand(1, frames, 4, hw, hw), inp["image_latents"][:1]], dim=2)
+    w = w or hw
+    inp = synth_inputs(cfg, frames, hw, w)
+    sample = torch.cat([inp["latents"].expand(1, frames, 4, hw, w), inp["image_latents"][:1]], dim=2)
     t0 = time.perf_counter()
     O.unet_forward(sd, cfg, sample, torch.tensor(1.0), inp["encoder_hidden_states"][:1], inp["added_time_ids"][:1])
     dt = time.perf_counter() - t0
@@ -134,7 +135,7 @@ def run_reference(args):
     sample_frames = 16 if cores >= 32 else 4
     times = []
     for i in range(args.warmup + args.steps):
-        dt, cores = cpu_reference_sample(sample_frames, 64)
+        dt, cores = cpu_reference_sample(sample_frames, 64, args.size)
         if i >= args.warmup:
             times.append(dt)
         if sum(times) > 150:
