@@ -48,8 +48,8 @@ CONFIGS = {
 }
 # average DRAM bytes (read + write) per sa_gemm_tap launch in one B=2 UNet call at 64x64x16, from the ncu pass
 # `--metrics dram__bytes_read.sum,dram__bytes_write.sum` over all 334 launches of the family
-# (profiles/r1_v5_launches_unet_b2_64x64x16.csv, summary next to it: read 98.2 MB + write 42.6 MB)
-GEMM_DRAM_BYTES_PER_LAUNCH = 140.7e6
+# (profiles/r1_v8_launches_unet_b2_64x64x16.csv, summary next to it)
+GEMM_DRAM_BYTES_PER_LAUNCH = 132.2e6
 
 
 def peaks():
