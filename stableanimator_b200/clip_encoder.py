@@ -108,7 +108,7 @@ class ClipImageEncoderB200:
             kk = int(max(2.0 * 2 * sg, 3))
             sig.append(sg)
             ks.append(kk + 1 if kk % 2 == 0 else kk)
-        cur, bufs = x, [torch.empty_like(x), torch.empty_like(x)]   # never written: the caller's tensor
+        cur, bufs = x, [torch.empty_like(x), torch.empty_like(x)]   # x may be the caller's tensor: it is only read
         # columns first, then rows (:93-94); `image * 2.0 - 1.0` (:208) is applied to the values the first pass reads
         for axis, sg, kk, a0, c0 in ((1, sig[1], ks[1], 2.0, -1.0), (0, sig[0], ks[0], 1.0, 0.0)):
             taps = self._gauss_taps(kk, sg).to(self.dev)
