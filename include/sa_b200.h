@@ -92,6 +92,10 @@ typedef struct sa_gemm_args {
   /* by the 3x3 conv, unet.py:1789-1807) computed as 2x2-tap convolutions on the low-resolution input.  bf16 output, */
   /* n % tile == 0, no residual / blend_x / gn_stats.                                                                */
   int64_t ldc2, ldc3;
+  /* Strided input grid: 2 = the sources are sampled at every 2nd position along grid dims 1 and 2 (their extents are */
+  /* 2*d1 x 2*d2 x d3; tap offsets are in INPUT positions): the stride-2 3x3 conv of Downsample2D (unet.py:1459-1483) */
+  /* straight from the full-resolution tensor through TMA element strides, no im2col.  0 / 1 = dense.                */
+  int32_t in_stride;
 } sa_gemm_args;
 
 int sa_gemm_tap(const sa_gemm_args* args, void* stream);

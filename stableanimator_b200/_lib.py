@@ -45,6 +45,7 @@ class GemmArgs(C.Structure):
         ("f16_from_col", C.c_int32),
         ("gn_stats", C.c_void_p), ("gn_cpg", C.c_int32), ("gn_rows_per_stat", C.c_int32),
         ("ldc2", C.c_int64), ("ldc3", C.c_int64),
+        ("in_stride", C.c_int32),
     ]
 
 

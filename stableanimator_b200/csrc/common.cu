@@ -41,7 +41,7 @@ static EncodeTiledFn encode_fn() {
 }
 
 struct TmapKey {
-  uint64_t w[17];
+  uint64_t w[18];
   bool operator==(const TmapKey& o) const { return memcmp(w, o.w, sizeof(w)) == 0; }
 };
 struct TmapHash {
@@ -56,7 +56,8 @@ struct TmapHash {
 };
 
 const CUtensorMap* get_tmap_bf16(const void* base, int rank, const uint64_t* dims,
-                                 const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
+                                 const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes,
+                                 const uint32_t* elem_strides) {
   static std::mutex mu;
   static std::unordered_map<TmapKey, CUtensorMap*, TmapHash> cache;
   TmapKey key;
@@ -67,6 +68,7 @@ const CUtensorMap* get_tmap_bf16(const void* base, int rank, const uint64_t* dim
     key.w[2 + i] = dims[i];
     key.w[7 + i] = (i == 0) ? 0 : strides_bytes[i - 1];
     key.w[12 + i] = box[i];
+    if (elem_strides) key.w[17] |= static_cast<uint64_t>(elem_strides[i]) << (8 * i);
   }
   std::lock_guard<std::mutex> lock(mu);
   auto it = cache.find(key);
@@ -84,6 +86,8 @@ const CUtensorMap* get_tmap_bf16(const void* base, int rank, const uint64_t* dim
     return nullptr;
   }
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  if (elem_strides)
+    for (int i = 0; i < rank; ++i) estr[i] = elem_strides[i];
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank),
                   const_cast<void*>(base), dims, strides_bytes, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE,

@@ -21,11 +21,12 @@ int fail(int code, const char* fmt, ...);
 
 // bf16 tensor map of rank `rank` (<= 5), SWIZZLE_128B (or 64B), zero OOB fill, cached by content.
 // dims/strides follow cuTensorMapEncodeTiled (dim 0 innermost; strides in BYTES for dims 1..).
+// elem_strides (optional, per dim): traversal stride -- box[i] elements are traversed, every elem_strides[i]-th loaded.
 // Returns nullptr (and sets the error text) on failure.  The returned pointer stays valid for the
 // life of the process (the cache never evicts).
 const CUtensorMap* get_tmap_bf16(const void* base, int rank, const uint64_t* dims,
                                  const uint64_t* strides_bytes, const uint32_t* box,
-                                 int swizzle_bytes = 128);
+                                 int swizzle_bytes = 128, const uint32_t* elem_strides = nullptr);
 
 int num_sms();
 

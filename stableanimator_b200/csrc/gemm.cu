@@ -53,6 +53,7 @@ struct GemmKParams {
   int n_tiles_n, total_tiles;
   float out_scale;  // v = (acc*rs + bias + row_bias [geglu]) * out_scale + residual ...
   int f16_from;     // > 0: output columns >= f16_from are stored as fp16 instead of bf16
+  int cs;           // coordinate scale of the source grid along dims 1, 2 (2 = stride-2 convolution)
   double* gn_stats; // fused GroupNorm statistics of the output: fp64 [M / rows_per_stat, n_out / cpg, 2] or null
   int gn_groups;    // n_out / cpg
   FastDiv fd_ntn, fd_t1, fd_t2, fd_rpg, fd_gcpg, fd_grps;
@@ -118,9 +119,9 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         const int o1 = p.tap_off[tap * 3 + 0], o2 = p.tap_off[tap * 3 + 1],
                   o3 = p.tap_off[tap * 3 + 2];
         if (ch < p.kc0)
-          tma_load_4d(sa_, &tmA0, &full_bar[s], ch * 64, q1 + o1, q2 + o2, q3 + o3);
+          tma_load_4d(sa_, &tmA0, &full_bar[s], ch * 64, q1 * p.cs + o1, q2 * p.cs + o2, q3 + o3);
         else
-          tma_load_4d(sa_, &tmA1, &full_bar[s], (ch - p.kc0) * 64, q1 + o1, q2 + o2, q3 + o3);
+          tma_load_4d(sa_, &tmA1, &full_bar[s], (ch - p.kc0) * 64, q1 * p.cs + o1, q2 * p.cs + o2, q3 + o3);
         tma_load_2d(sa_ + A_BYTES, &tmB, &full_bar[s], kb * 64, n0);
         if (++ch == p.kcpt) {
           ch = 0;
@@ -393,9 +394,9 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
           uint8_t* sa_ = smem + s * STAGE_BYTES;
           const int o1 = p.tap_off[tap * 3 + 0], o2 = p.tap_off[tap * 3 + 1], o3 = p.tap_off[tap * 3 + 2];
           if (ch < p.kc0)
-            tma_load_4d(sa_, &tmA0, &full_bar[s], ch * 64, q1 + o1, q2 + o2, q3 + o3);
+            tma_load_4d(sa_, &tmA0, &full_bar[s], ch * 64, q1 * p.cs + o1, q2 * p.cs + o2, q3 + o3);
           else
-            tma_load_4d(sa_, &tmA1, &full_bar[s], (ch - p.kc0) * 64, q1 + o1, q2 + o2, q3 + o3);
+            tma_load_4d(sa_, &tmA1, &full_bar[s], (ch - p.kc0) * 64, q1 * p.cs + o1, q2 * p.cs + o2, q3 + o3);
           tma_load_2d(sa_ + A_BYTES, &tmB, &full_bar[s], kb * 64, n0);
           if (++ch == p.kcpt) {
             ch = 0;
@@ -881,6 +882,8 @@ extern "C" int sa_gemm_tap(const sa_gemm_args* a, void* stream_) {
   p.d2 = a->d2;
   p.d3 = a->d3;
   pick_box(a->d1, a->d2, a->d3, &p.b1, &p.b2, &p.b3);
+  p.cs = a->in_stride > 1 ? a->in_stride : 1;
+  if (p.cs > 2) return fail(SA_ERR_INVALID, "sa_gemm_tap: in_stride must be 0, 1 or 2");
   p.t1 = (a->d1 + p.b1 - 1) / p.b1;
   p.t2 = (a->d2 + p.b2 - 1) / p.b2;
   const int t3 = (a->d3 + p.b3 - 1) / p.b3;
@@ -916,13 +919,15 @@ extern "C" int sa_gemm_tap(const sa_gemm_args* a, void* stream_) {
       tma[1] = tma[0];
       break;
     }
-    uint64_t dims[4] = {static_cast<uint64_t>(c), static_cast<uint64_t>(a->d1),
-                        static_cast<uint64_t>(a->d2), static_cast<uint64_t>(a->d3)};
-    uint64_t strides[3] = {static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(ld) * 2 * a->d1,
-                           static_cast<uint64_t>(ld) * 2 * a->d1 * a->d2};
-    uint32_t box[4] = {64, static_cast<uint32_t>(p.b1), static_cast<uint32_t>(p.b2),
+    // source grid: (d1, d2, d3) positions, or (cs*d1, cs*d2, d3) sampled with TMA element strides (cs, cs)
+    const uint64_t e1 = static_cast<uint64_t>(a->d1) * p.cs, e2 = static_cast<uint64_t>(a->d2) * p.cs;
+    uint64_t dims[4] = {static_cast<uint64_t>(c), e1, e2, static_cast<uint64_t>(a->d3)};
+    uint64_t strides[3] = {static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(ld) * 2 * e1,
+                           static_cast<uint64_t>(ld) * 2 * e1 * e2};
+    uint32_t box[4] = {64, static_cast<uint32_t>(p.b1 * p.cs), static_cast<uint32_t>(p.b2 * p.cs),
                        static_cast<uint32_t>(p.b3)};
-    tma[s] = get_tmap_bf16(base, 4, dims, strides, box);
+    uint32_t estr[4] = {1, static_cast<uint32_t>(p.cs), static_cast<uint32_t>(p.cs), 1};
+    tma[s] = get_tmap_bf16(base, 4, dims, strides, box, 128, p.cs > 1 ? estr : nullptr);
     if (!tma[s]) return SA_ERR_TMA;
   }
   const long long ktot = static_cast<long long>(a->ntaps) * (a->c0 + a->c1);

@@ -70,6 +70,7 @@ def gemm_tap(
     f16_from_col: int = 0,
     gn_stats: Optional[torch.Tensor] = None,
     gn_rows_per_stat: int = 0,
+    in_stride: int = 1,
 ) -> torch.Tensor:
     """``out = epilogue(sum_taps A(shifted) @ W^T)`` -- see ``sa_gemm_tap`` in include/sa_b200.h.
 
@@ -81,13 +82,16 @@ def gemm_tap(
     _chk_bf16(w, "w")
     c0 = a0.shape[-1]
     lda0 = a0.stride(-2) if a0.dim() >= 2 else c0
-    rows = a0.numel() // c0
+    src_rows = a0.numel() // c0
+    if in_stride not in (1, 2) or (in_stride == 2 and (grid is None or src_rows != 4 * grid[0] * grid[1] * grid[2])):
+        raise ValueError("in_stride=2 needs an explicit grid (d1, d2, d3) and sources of 2*d1 x 2*d2 x d3 positions")
+    rows = src_rows // (in_stride * in_stride)   # output positions
     c1, lda1 = 0, 0
     if a1 is not None:
         _chk_bf16(a1, "a1")
         c1 = a1.shape[-1]
         lda1 = a1.stride(-2)
-        if a1.numel() // c1 != rows:
+        if a1.numel() // c1 != src_rows:
             raise ValueError("a0 and a1 must cover the same positions")
     if grid is None:
         grid = (rows, 1, 1)
@@ -136,6 +140,7 @@ def gemm_tap(
     args.tile_n = tile_n
     args.out_scale = float(out_scale)
     args.f16_from_col = int(f16_from_col)
+    args.in_stride = int(in_stride)
     if gn_stats is not None:
         # fused statistics of the output for the GroupNorm(32) that consumes it: fp64 [rows / rows_per_stat, 32, 2]
         if gn_stats.dtype != torch.float64 or not gn_stats.is_contiguous() or n_out % 32 or \

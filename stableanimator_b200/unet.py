@@ -62,6 +62,8 @@ class UNetB200:
         self.fuse_gn_stats = os.environ.get("SA_GN_FUSE", "0") == "1"
         # zero-context (unconditional CFG branch) shortcut of the ID cross-attention; SA_SKIP_ZERO_CTX=0 for A/B
         self.skip_zero_context = os.environ.get("SA_SKIP_ZERO_CTX", "1") != "0"
+        # stride-2 Downsample2D through TMA element strides (SA_STRIDED_DOWN=0: im2col_s2 + GEMM, for A/B)
+        self.strided_downsample = os.environ.get("SA_STRIDED_DOWN", "1") != "0"
         # Upsample2D as four phase convolutions (4/9 of the MACs; SA_UP_PHASES=0: upsample2x + 3x3 conv, for A/B)
         self.upsample_phases = os.environ.get("SA_UP_PHASES", "1") != "0"
         self._pos_cache: Dict[Tuple[str, int, int], torch.Tensor] = {}
@@ -389,7 +391,15 @@ class UNetB200:
                         if taps is not None:
                             taps[t.name] = x
                     skips.append(x)
-                if st.downsample:
+                if st.downsample and self.strided_downsample:
+                    # Downsample2D (unet.py:1459-1483): the stride-2 taps come straight from the full-resolution
+                    # tensor through TMA element strides -- no im2col buffer
+                    x = ops.gemm_tap(x.reshape(B * F, ch, cw, st.cout), w[f"{st.downsample}.w"],
+                                     grid=(cw // 2, ch // 2, B * F), taps=ops.TAPS_3X3, in_stride=2,
+                                     bias=w[f"{st.downsample}.b"])
+                    ch, cw = ch // 2, cw // 2
+                    skips.append(x)
+                elif st.downsample:
                     cols = ops.im2col_s2(x.reshape(B * F, ch, cw, st.cout))
                     x = ops.gemm_tap(cols, w[f"{st.downsample}.w"], bias=w[f"{st.downsample}.b"])
                     ch, cw = ch // 2, cw // 2

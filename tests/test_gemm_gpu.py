@@ -248,3 +248,21 @@ def test_upsample_conv_as_phase_convolutions(f, h, w_, c, cout):
     wp9 = wt.permute(0, 2, 3, 1).reshape(cout, 9 * c).contiguous()
     old = ops.gemm_tap(ops.upsample2x(x), wp9, grid=(2 * w_, 2 * h, f), taps=ops.TAPS_3X3, bias=bias)
     assert rel_l2(out.float(), old.reshape(out.shape).float()) <= 2.0 ** -8
+
+
+@pytest.mark.parametrize("f,h,w_,c,cout", [(2, 8, 8, 64, 64), (3, 16, 24, 128, 64), (2, 18, 36, 64, 128), (16, 64, 64, 320, 320)])
+def test_stride2_conv_through_tma_element_strides(f, h, w_, c, cout):
+    """Downsample2D (Conv2d 3x3, stride 2, pad 1; unet.py:1459-1483) straight from the full-resolution tensor
+    (sa_gemm_args.in_stride = 2) vs F.conv2d and vs the im2col_s2 + GEMM path (same operands -> same bits)."""
+    from stableanimator_b200 import ops
+    x = rnd(f, h, w_, c, seed=61)
+    wt = rnd(cout, c, 3, 3, scale=(9 * c) ** -0.5, seed=62)
+    bias = torch.randn(cout, device="cuda")
+    wp = wt.permute(0, 2, 3, 1).reshape(cout, 9 * c).contiguous()
+    out = ops.gemm_tap(x, wp, grid=(w_ // 2, h // 2, f), taps=ops.TAPS_3X3, in_stride=2, bias=bias)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, stride=2, padding=1).permute(0, 2, 3, 1)
+    assert_close(out.reshape(f, h // 2, w_ // 2, cout), ref)
+    old = ops.gemm_tap(ops.im2col_s2(x), wp, bias=bias)
+    assert rel_l2(out.float(), old.float()) <= 1e-3
+    with pytest.raises(ValueError):
+        ops.gemm_tap(x, wp, taps=ops.TAPS_3X3, in_stride=2, bias=bias)      # grid is mandatory
