@@ -169,7 +169,7 @@ def gemm_family_time(unet, ctx, ati, B, F, h, w, reps=5):
     flops = []
 
     def elided(a0, w_, **kw):
-        rows = a0.numel() // a0.shape[-1]
+        rows = a0.numel() // a0.shape[-1] // (kw.get("in_stride", 1) ** 2)   # output positions
         n = kw.get("n") or w_.shape[0]
         flops.append(2.0 * rows * w_.shape[1] * n)
         if kw.get("out") is not None:

@@ -83,3 +83,35 @@ def test_second_video_reuses_graph_with_new_conditioning():
     b = s(args[0], args[1], ehs2, args[3], args[4]).clone()
     c = s(*args).clone()
     assert torch.equal(a, c) and not torch.equal(a, b)
+
+
+def test_bench_gemm_flop_accounting_matches_the_launches():
+    """bench.py's roofline leg elides the GEMM launches and counts 2*M*N*K per launch from the ARGUMENTS; check it
+    against a pass-through wrapper that counts from the tensors the real launches return (strided inputs, phase
+    convolutions and the zero-context row split included), and that the elided graph keeps every shape."""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+    import bench
+    from stableanimator_b200 import ops
+    cfg, inp, unet, pose, _, _ = setup(4, 16, 16, 4)
+    ctx = unet.prepare_context(inp["encoder_hidden_states"].cuda())
+    ati = inp["added_time_ids"].cuda()
+    flops, g_ms, n_launch, full_ms = bench.gemm_family_time(unet, ctx, ati, 2, 4, 16, 16, reps=2)
+    true = []
+    orig = ops.gemm_tap
+
+    def counting(a0, w_, **kw):
+        out = orig(a0, w_, **kw)
+        true.append(2.0 * (out.numel() // out.shape[-1]) * w_.shape[1] * (kw.get("n") or w_.shape[0]))
+        return out
+
+    ops.gemm_tap = counting
+    try:
+        x_in = torch.zeros((2 * 4, 16, 16, cfg.in_channels), device="cuda", dtype=torch.bfloat16)
+        unet.forward_nhwc(x_in, torch.tensor(1.0, device="cuda"), ctx, ati, 2, 4, 16, 16)
+    finally:
+        ops.gemm_tap = orig
+    assert n_launch == len(true)
+    assert abs(flops - sum(true)) <= 1e-9 * sum(true), (flops, sum(true))
+    assert g_ms > 0 and full_ms > g_ms

@@ -28,7 +28,7 @@ def _empty_like_out(rows, cols, dev, dtype=torch.bfloat16):
 def elided(name):
     if name == "gemm_tap":
         def f(a0, w_, **kw):
-            rows = a0.numel() // a0.shape[-1]
+            rows = a0.numel() // a0.shape[-1] // (kw.get("in_stride", 1) ** 2)   # output positions
             n = kw.get("n") or w_.shape[0]
             if kw.get("out") is not None:
                 return kw["out"]
