@@ -301,15 +301,19 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
 // =====================================================================================================
 constexpr int EPI_CHUNK = 32;             // output columns per chunk
 constexpr int EPI_TILE_BYTES = 32 * 64;   // per-warp staging tile: [32 rows][32 bf16]
-constexpr int EPI_RO_SLOTS = 3, EPI_X_SLOTS = 2;
-constexpr int EPI_WARP_BYTES = (EPI_RO_SLOTS + EPI_X_SLOTS) * EPI_TILE_BYTES;
+// Staging slots per epilogue warp: 3 output / residual slots (the residual sub-box is prefetched two chunks ahead) and
+// 2 blend-operand slots.  SLIM (the GEGLU instantiations, which never carry a residual or a blend operand): 2 output
+// slots only -- the 48 KB this frees with eight epilogue warps buy two more pipeline stages, which the short-K GEGLU
+// GEMMs need to cover the TMA latency (4 stages x 32 KB in flight against ~125 B/clk of operand traffic per SM).
+template <bool SLIM> struct EpiSlots { static constexpr int RO = SLIM ? 2 : 3, X = SLIM ? 0 : 2; };
 
-template <int BN, int STAGES, int EW>
+template <int BN, int STAGES, int EW, bool SLIM = false>
 struct Gemm2Smem {
+  static constexpr int EPI_WARP_BYTES = (EpiSlots<SLIM>::RO + EpiSlots<SLIM>::X) * EPI_TILE_BYTES;
   static constexpr int STAGE_BYTES = 128 * 128 + BN * 128;
   static constexpr int EPI_OFF = STAGES * STAGE_BYTES;
   static constexpr int BAR_OFF = EPI_OFF + EW * EPI_WARP_BYTES;
-  static constexpr int NBARS = 2 * STAGES + 4 + EW * (EPI_RO_SLOTS + EPI_X_SLOTS);
+  static constexpr int NBARS = 2 * STAGES + 4 + EW * (EpiSlots<SLIM>::RO + EpiSlots<SLIM>::X);
   static constexpr int TOTAL = BAR_OFF + NBARS * 8 + 16 + 1024;  // + tmem slot + alignment slack
 };
 
@@ -325,7 +329,10 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
                         const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
                         const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmBld,
                         const GemmKParams p) {
-  using L = Gemm2Smem<BN, STAGES, EW>;
+  constexpr bool SLIM = GEGLU || PLAIN;   // neither ever carries a residual / blend operand
+  using L = Gemm2Smem<BN, STAGES, EW, SLIM>;
+  constexpr int EPI_RO_SLOTS = EpiSlots<SLIM>::RO, EPI_X_SLOTS = EpiSlots<SLIM>::X;
+  constexpr int EPI_WARP_BYTES = L::EPI_WARP_BYTES;
   constexpr int CSTRIDE = EW / 4;  // chunk stride of one epilogue warp
   constexpr int A_BYTES = 128 * 128;
   constexpr int STAGE_BYTES = L::STAGE_BYTES;
@@ -476,10 +483,12 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
       } else {
         mbar_arrive(&ro_ready[slot]);
       }
-      if (p.blend_x) {
-        const int xs = nx_g % EPI_X_SLOTS;
-        mbar_expect_tx(&x_ready[xs], EPI_TILE_BYTES);
-        tma_load_4d(sX + xs * EPI_TILE_BYTES, &tmBld, &x_ready[xs], col, nx_q1 + w1, nx_q2 + w2, nx_q3 + w3);
+      if constexpr (EPI_X_SLOTS > 0) {
+        if (p.blend_x) {
+          const int xs = nx_g % EPI_X_SLOTS;
+          mbar_expect_tx(&x_ready[xs], EPI_TILE_BYTES);
+          tma_load_4d(sX + xs * EPI_TILE_BYTES, &tmBld, &x_ready[xs], col, nx_q1 + w1, nx_q2 + w2, nx_q3 + w3);
+        }
       }
       ++nx_g;
       nx_c += CSTRIDE;
@@ -493,7 +502,7 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
     // as the store issued from it two chunks ago has read it (wait_group.read below), so the whole
     // issue_next / ro_ready machinery (two div/mod chains and a barrier round trip per chunk -- the short-K
     // GEMMs are issue-bound) is skipped.
-    const bool staged = !PLAIN && ((p.residual != nullptr) || (p.blend_x != nullptr));
+    const bool staged = !SLIM && ((p.residual != nullptr) || (p.blend_x != nullptr));
     if (lane == 0 && staged) {
       issue_next();
       issue_next();
@@ -631,7 +640,7 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
         const int slot = gc % EPI_RO_SLOTS;
         if (staged) mbar_wait(&ro_ready[slot], (gc / EPI_RO_SLOTS) & 1);
         uint8_t* ro = my_ro + slot * EPI_TILE_BYTES;
-        if (!PLAIN && p.residual) {
+        if (!SLIM && p.residual) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint4 q = *reinterpret_cast<const uint4*>(ro + ((j ^ sw) << 4));
@@ -641,7 +650,7 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
             v2[4 * j + 3] = add2(v2[4 * j + 3], bf16x2_to_f32x2(q.w));
           }
         }
-        if (!PLAIN && p.blend_x) {
+        if constexpr (!PLAIN && EPI_X_SLOTS > 0) if (p.blend_x) {
           const int xs = gc % EPI_X_SLOTS;
           mbar_wait(&x_ready[xs], (gc / EPI_X_SLOTS) & 1);
           const uint8_t* xr = my_x + xs * EPI_TILE_BYTES;
@@ -771,13 +780,18 @@ template <int BN, int STAGES, bool GEGLU, int EW>
 static int launch_persist(const CUtensorMap* a0, const CUtensorMap* a1, const CUtensorMap* b,
                           const CUtensorMap* o, const CUtensorMap* r, const CUtensorMap* x, GemmKParams p,
                           int m_tiles, cudaStream_t stream) {
-  using L = Gemm2Smem<BN, STAGES, EW>;
+  // the PLAIN instantiation has the slim staging layout: spend the shared memory it frees on pipeline stages
+  constexpr int SLIM_MAX = (232448 - 2048 - EW * 2 * EPI_TILE_BYTES) / (128 * 128 + BN * 128);
+  constexpr int STP = GEGLU ? STAGES : (SLIM_MAX < STAGES ? STAGES : (SLIM_MAX > 8 ? 8 : SLIM_MAX));
+  using L = Gemm2Smem<BN, STAGES, EW, GEGLU>;
+  using LP = Gemm2Smem<BN, STP, EW, true>;
+  static_assert(L::TOTAL <= 232448 && LP::TOTAL <= 232448, "shared memory budget");
   static bool configured = false;
   if (!configured) {
     SA_CUDA_CHECK(cudaFuncSetAttribute(gemm_tap_persist_kernel<BN, STAGES, GEGLU, EW, false>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    SA_CUDA_CHECK(cudaFuncSetAttribute(gemm_tap_persist_kernel<BN, STAGES, GEGLU, EW, true>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    SA_CUDA_CHECK(cudaFuncSetAttribute(gemm_tap_persist_kernel<BN, STP, GEGLU, EW, true>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, LP::TOTAL));
     configured = true;
   }
   p.n_tiles_n = p.N / BN;
@@ -791,7 +805,7 @@ static int launch_persist(const CUtensorMap* a0, const CUtensorMap* a1, const CU
   const bool plain = !p.row_scale && !p.row_bias && p.out_scale == 1.0f && !p.residual && !p.blend_x && p.f16_from == 0 &&
                      !p.gn_stats;
   if (plain)
-    gemm_tap_persist_kernel<BN, STAGES, GEGLU, EW, true><<<grid, 64 + 32 * EW, L::TOTAL, stream>>>(*a0, *a1, *b, *o, *r, *x, p);
+    gemm_tap_persist_kernel<BN, STP, GEGLU, EW, true><<<grid, 64 + 32 * EW, LP::TOTAL, stream>>>(*a0, *a1, *b, *o, *r, *x, p);
   else
     gemm_tap_persist_kernel<BN, STAGES, GEGLU, EW, false><<<grid, 64 + 32 * EW, L::TOTAL, stream>>>(*a0, *a1, *b, *o, *r, *x, p);
   SA_CUDA_CHECK(cudaGetLastError());
@@ -908,6 +922,8 @@ extern "C" int sa_gemm_tap(const sa_gemm_args* a, void* stream_) {
   const long long ktot_pick = static_cast<long long>(a->ntaps) * (a->c0 + a->c1);
   int bn = a->tile_n ? a->tile_n : pick_tile(p.M, p.N, p.geglu, ktot_pick);
   if (p.geglu && bn != 128 && bn != 256) return fail(SA_ERR_INVALID, "sa_gemm_tap: geglu tile must be 128/256");
+  if (p.geglu && (a->residual || a->blend_x))
+    return fail(SA_ERR_INVALID, "sa_gemm_tap: the geglu epilogue takes no residual / blend_x operand");
 
   // tensor maps: A sources as rank-4 (C, d1, d2, d3); W as rank-2 (K, N)
   const CUtensorMap* tma[2] = {nullptr, nullptr};
@@ -990,8 +1006,8 @@ extern "C" int sa_gemm_tap(const sa_gemm_args* a, void* stream_) {
 #define SA_LP(BN_, ST_, G_, EW_) return launch_persist<BN_, ST_, G_, EW_>(tma[0], tma[1], tmb, tmo, tmr, tmx, p, mt, stream)
     if (p.geglu) {
       switch (bn) {
-        case 128: if (long_k) SA_LP(128, 5, true, 4); else SA_LP(128, 4, true, 8);
-        case 256: SA_LP(256, 3, true, 8);
+        case 128: if (long_k) SA_LP(128, 6, true, 4); else SA_LP(128, 6, true, 8);
+        case 256: SA_LP(256, 4, true, 8);
         default: break;
       }
     } else
