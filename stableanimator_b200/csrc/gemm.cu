@@ -1002,7 +1002,9 @@ extern "C" int sa_gemm_tap(const sa_gemm_args* a, void* stream_) {
     const CUtensorMap* tmr = a->residual ? epi_map(a->residual, a->ldr) : tmo;
     const CUtensorMap* tmx = a->blend_x ? epi_map(a->blend_x, a->ldx) : tmo;
     if (!tmo || !tmr || !tmx) return SA_ERR_TMA;
-    const bool long_k = ktot >= 1280;  // long main loop: 4 epilogue warps, one more pipeline stage
+    // long main loop: 4 epilogue warps, one more pipeline stage (SA_GEMM_LONGK=<k> moves the threshold, for A/B runs)
+    static const long long long_k_min = getenv("SA_GEMM_LONGK") ? atoll(getenv("SA_GEMM_LONGK")) : 1280;
+    const bool long_k = ktot >= long_k_min;
 #define SA_LP(BN_, ST_, G_, EW_) return launch_persist<BN_, ST_, G_, EW_>(tma[0], tma[1], tmb, tmo, tmr, tmx, p, mt, stream)
     if (p.geglu) {
       switch (bn) {
