@@ -38,6 +38,7 @@ class _GraphedUNet:
                      if with_pose else None)
         self.out = None
         self.graph = None
+        self.pose_tile = None  # (tile index, video serial) of the PoseNet output currently held by self.pose
         from . import _lib
         n0 = _lib.launch_count
         self._run()  # warm-up: configures kernels, fills tensor-map + constant caches
@@ -99,6 +100,7 @@ class AnimationSampler:
         self.timesteps = sch.timesteps(self.sigmas)
         self.dev = unet.dev
         self._plans: Dict[tuple, dict] = {}
+        self._video_serial = 0
         self.rank, self.world = 0, 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.rank, self.world = torch.distributed.get_rank(), torch.distributed.get_world_size()
@@ -168,6 +170,7 @@ class AnimationSampler:
         has_pose = pose is not None and self.pose_net is not None
         plan = self._plan(F, h, w, has_pose)
         plan["fresh"] = set()
+        self._video_serial += 1
         # :586-597 scale by init_noise_sigma and repeat the tile of noise along frames
         lat = (lat0 * sch.init_noise_sigma(self.sigmas)).repeat(1, F // T + 1, 1, 1, 1)[0, :F].contiguous()
         noise = torch.empty((2, F, 4, h, w), device=dev, dtype=torch.float32)
@@ -190,8 +193,9 @@ class AnimationSampler:
                     ops.sampler_prepare(lat, img, idx, 2, 0, F, hw, sigma, run.x_in)
                 else:
                     ops.sampler_prepare(lat, img, idx, 1, branches[0], F, hw, sigma, run.x_in)
-                if run.pose is not None:
-                    run.pose.copy_(pose_nhwc[ti])
+                if run.pose is not None and run.pose_tile != (ti, self._video_serial):
+                    run.pose.copy_(pose_nhwc[ti])  # once per video for a single tile; per step when tiles share a runner
+                    run.pose_tile = (ti, self._video_serial)
                 out = run()
                 ops.sampler_accumulate(out, idx, plan["weight"], len(branches), branches[0], F, hw, noise)
             if self.world > 1:
