@@ -81,6 +81,41 @@ def test_unet_full_config_golden():
     torch.cuda.empty_cache()
 
 
+def test_baseline_config0_one_cfg_step_full_width():
+    """BASELINE.json configs[0]: one CFG denoising step of the full-width UNet at 256x256 (32x32 latent), 8 frames,
+    synthetic pose + face tokens -- the reference's own CPU-runnable case.  Ours: one fused B=2 call (pose on the cond
+    element); oracle: PoseNet + two B=1 fp32 calls on the host cores (inference_pipeline_animation.py:661-685)."""
+    from oracle import unet_oracle as O
+    from stableanimator_b200.arch import UNetConfig
+    from stableanimator_b200.pose_net import PoseNetB200
+    from stableanimator_b200.synth import synth_inputs, synth_posenet_state_dict, synth_unet_state_dict
+    from stableanimator_b200.unet import UNetB200
+    cfg = UNetConfig.full()
+    frames, h, w = 8, 32, 32
+    sd, psd = synth_unet_state_dict(cfg), synth_posenet_state_dict(cfg.block_out_channels[0])
+    inp = synth_inputs(cfg, frames, h, w)
+    t = torch.tensor(1.637770)                                   # 0.25 ln(700): the first Euler step
+    lat = inp["latents"] * 700.0 / (700.0 ** 2 + 1) ** 0.5        # scale_model_input at sigma_max
+    sample = torch.cat([torch.cat([lat, lat], 0), inp["image_latents"]], dim=2)       # [2, F, 8, h, w]
+    unet = UNetB200(cfg, sd, "cuda")
+    pose = PoseNetB200(psd, cfg.block_out_channels[0], "cuda")
+    pl = pose(inp["pose"].cuda())
+    out = unet(sample.cuda(), t, inp["encoder_hidden_states"].cuda(), inp["added_time_ids"].cuda(), pose_latents=pl,
+               pose_batch_from=1)[0].float().cpu()
+    pl_ref = O.pose_net(psd, inp["pose"])
+    ref_u = O.unet_forward(sd, cfg, sample[:1], t, inp["encoder_hidden_states"][:1], inp["added_time_ids"][:1], None)
+    ref_c = O.unet_forward(sd, cfg, sample[1:], t, inp["encoder_hidden_states"][1:], inp["added_time_ids"][1:], pl_ref)
+    eu, ec = rel_l2(out[:1], ref_u), rel_l2(out[1:], ref_c)
+    g = 3.0
+    e_cfg = rel_l2(out[:1] + g * (out[1:] - out[:1]), ref_u + g * (ref_c - ref_u))
+    print(f"configs[0] (full width, 32x32 latent, 8 frames): uncond {eu:.3e}, cond {ec:.3e}, CFG-combined {e_cfg:.3e}")
+    assert torch.isfinite(out).all()
+    assert eu <= 1e-2 and ec <= 1e-2
+    assert e_cfg <= 3e-2        # guidance 3 extrapolates the difference of two bf16 results
+    del unet
+    torch.cuda.empty_cache()
+
+
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     from stableanimator_b200 import _lib
     monkeypatch.setattr(_lib, "_lib", None)
