@@ -137,3 +137,31 @@ def test_clip_blur_geometry_of_the_baseline_resolutions():
     assert clip_oracle.blur_geometry((224, 224), (224, 224)) == ((0.001, 0.001), (3, 3))
     t = clip_oracle.gaussian_taps(7, 1.7857)
     assert abs(t.sum().item() - 1.0) < 1e-6 and torch.equal(t, t.flip(0))
+
+
+def test_pipeline_oracle_chain_runs_and_is_deterministic():
+    """oracle/pipeline_oracle.py (inference_pipeline_animation.py:494-706 as a chain of the pinned stage oracles):
+    shapes, value ranges, the zero unconditional rows and determinism on the debug-size configs."""
+    import dataclasses
+    from oracle import pipeline_oracle
+    from stableanimator_b200 import synth
+    from stableanimator_b200.arch import ClipVisionConfig, UNetConfig, VaeDecoderConfig
+    ucfg, vcfg = UNetConfig.tiny(), VaeDecoderConfig.tiny()
+    ccfg = dataclasses.replace(ClipVisionConfig.tiny(), projection_dim=ucfg.cross_attention_dim)
+    sd = dict(unet=synth.synth_unet_state_dict(ucfg), pose=synth.synth_posenet_state_dict(ucfg.block_out_channels[0]),
+              face=synth.synth_face_state_dict(), clip=synth.synth_clip_vision_state_dict(ccfg),
+              venc=synth.synth_vae_encoder_state_dict(vcfg), vdec=synth.synth_vae_decoder_state_dict(vcfg))
+    frames, tile, H, W = 4, 4, 64, 64
+    image01 = (synth.synth_image(H, W) + 1.0) / 2.0
+    inp = synth.synth_inputs(ucfg, frames, H // 8, W // 8)
+    ide = torch.randn(512, generator=torch.Generator().manual_seed(1))
+    noise = torch.randn(1, 3, H, W, generator=torch.Generator().manual_seed(2))
+    run = lambda: pipeline_oracle.animation_pipeline(  # noqa: E731
+        sd, (ucfg, vcfg, ccfg), image01, inp["pose"], ide, inp["latents"][:, :tile].contiguous(), noise,
+        num_frames=frames, tile_size=tile, tile_overlap=1, num_inference_steps=2, decode_chunk_size=4)
+    ehs, il, lat, video = run()
+    assert ehs.shape == (2, 5, 1024) and not ehs[0].any() and ehs[1].abs().max() > 0
+    assert il.shape == (2, frames, 4, H // 8, W // 8) and not il[0].any()
+    assert lat.shape == (1, frames, 4, H // 8, W // 8) and torch.isfinite(lat).all()
+    assert video.shape == (frames, 3, H, W) and video.min() >= 0 and video.max() <= 1
+    assert torch.equal(run()[3], video)

@@ -34,25 +34,6 @@ def build(seed=23123134):
     return pipe, sd, (ucfg, vcfg, ccfg)
 
 
-def oracle_pipeline(sd, cfgs, image01, pose, ide, lat0, img_noise, *, frames, tile, overlap, steps, aug, fps, bucket,
-                    gmin, gmax, chunk):
-    """inference_pipeline_animation.py:494-706 as a chain of the fp32 oracles."""
-    from oracle import clip_oracle, face_oracle, sampler_oracle as SO, unet_oracle as O, vae_oracle
-    ucfg, vcfg, ccfg = cfgs
-    emb = clip_oracle.encode_image(sd["clip"], ccfg, image01)                                   # :505
-    face = face_oracle.fusion_face_id(sd["face"], ide.reshape(1, -1), emb[1:])                  # :509-524
-    ehs = torch.cat([torch.cat([emb[:1], torch.zeros_like(face)], 1), torch.cat([emb[1:], face], 1)])   # :526-540
-    img = (2.0 * image01 - 1.0) + aug * img_noise                                               # :542-545
-    il = vae_oracle.vae_encode_mode(sd["venc"], vcfg, img)                                      # :552-557
-    image_latents = torch.cat([torch.zeros_like(il), il]).unsqueeze(1).repeat(1, frames, 1, 1, 1)   # :565
-    ati = torch.tensor([[fps - 1, bucket, aug]] * 2, dtype=torch.float32)                       # :567-577
-    lat = SO.denoise_loop(lambda s, t, e, a, pl: O.unet_forward(sd["unet"], ucfg, s, t, e, a, pl),
-                          lambda p: O.pose_net(sd["pose"], p), lat0, image_latents, ehs, ati, pose, num_steps=steps,
-                          tile_size=tile, tile_overlap=overlap, min_guidance=gmin, max_guidance=gmax)
-    frames_out = vae_oracle.decode_latents(sd["vdec"], vcfg, lat, frames, chunk)                # :702
-    return ehs, image_latents, lat, frames_out
-
-
 def test_pipeline_matches_oracle_chain():
     from stableanimator_b200.synth import _gen, bf16_round, synth_image, synth_inputs
     pipe, sd, cfgs = build()
@@ -64,9 +45,11 @@ def test_pipeline_matches_oracle_chain():
     img_noise = torch.randn(1, 3, H, W, generator=_gen("input.image_noise", 1))
     kw = dict(tile_size=tile, tile_overlap=overlap, num_inference_steps=steps, min_guidance_scale=1.0,
               max_guidance_scale=3.0, fps=7, motion_bucket_id=127, noise_aug_strength=0.02, decode_chunk_size=4)
-    ehs_r, il_r, lat_r, frames_r = oracle_pipeline(sd, cfgs, image01, inp["pose"], ide, lat0, img_noise, frames=frames,
-                                                   tile=tile, overlap=overlap, steps=steps, aug=0.02, fps=7, bucket=127,
-                                                   gmin=1.0, gmax=3.0, chunk=4)
+    from oracle import pipeline_oracle
+    ehs_r, il_r, lat_r, ref = pipeline_oracle.animation_pipeline(
+        sd, cfgs, image01, inp["pose"], ide, lat0, img_noise, num_frames=frames, tile_size=tile, tile_overlap=overlap,
+        num_inference_steps=steps, min_guidance_scale=1.0, max_guidance_scale=3.0, fps=7, motion_bucket_id=127,
+        noise_aug_strength=0.02, decode_chunk_size=4)
     ehs = pipe.encode_conditioning(image01.cuda(), ide.numpy())
     assert ehs.shape == ehs_r.shape == (2, 5, 1024) and not ehs[0].any()
     e_ctx = rel_l2(ehs.cpu(), ehs_r)
@@ -83,7 +66,6 @@ def test_pipeline_matches_oracle_chain():
     out = pipe(image01, inp["pose"], height=H, width=W, num_frames=frames, latents=lat0, image_noise=img_noise,
                reference_image_id_ante_embedding=ide.numpy(), output_type="pt", **kw)
     assert len(out) == 1 and out[0].shape == (frames, 3, H, W)
-    ref = (frames_r[0].permute(1, 0, 2, 3) / 2 + 0.5).clamp(0, 1)
     e_frames = rel_l2(out[0].cpu(), ref)
     print(f"pipeline vs oracle chain: conditioning {e_ctx:.2e}, image latents {e_il:.2e}, loop on oracle inputs "
           f"{e_loop:.2e}, end-to-end latents after {steps} steps {e_lat:.2e}, decoded frames {e_frames:.2e}")
