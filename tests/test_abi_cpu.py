@@ -64,3 +64,30 @@ def test_missing_library_raises(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", tmp_path / "libsa_b200.so")
     with pytest.raises(_lib.SaLibraryError):
         _lib.lib()
+
+
+def test_ctypes_signatures_match_header_prototypes():
+    """Every entry of _lib.SIGNATURES has the argument count and kinds (pointer / int32 / int64 / float) of the
+    prototype in include/sa_b200.h -- a drifting ctypes table would corrupt arguments silently."""
+    from stableanimator_b200 import _lib
+    hdr = (ROOT / "include" / "sa_b200.h").read_text()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    protos = dict(re.findall(r"\bint\s+(sa_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", hdr))
+    kinds = {C.c_void_p: "ptr", C.c_int32: "i32", C.c_int64: "i64", C.c_float: "f32"}
+    for name, argtypes in _lib.SIGNATURES.items():
+        assert name in protos, name
+        params = [p.strip() for p in protos[name].split(",") if p.strip() and p.strip() != "void"]
+        want = []
+        for p in params:
+            if "*" in p:
+                want.append("ptr")
+            elif p.startswith("int64_t"):
+                want.append("i64")
+            elif p.startswith("int32_t"):
+                want.append("i32")
+            elif p.startswith("float"):
+                want.append("f32")
+            else:
+                raise AssertionError(f"{name}: unhandled parameter {p!r}")
+        got = [kinds.get(t, "ptr") for t in argtypes]   # POINTER(...) types count as pointers
+        assert got == want, f"{name}: ctypes {got} vs header {want}"
