@@ -298,11 +298,12 @@ extern "C" int sa_attn_spatial(const void* qkv, int32_t ld, int32_t frames, int3
   uint32_t box[3] = {64, 128, 1};
   const CUtensorMap* tm = get_tmap_bf16(qkv, 3, dims, strides, box);
   if (!tm) return SA_ERR_TMA;
-  static bool configured = false;
-  if (!configured) {
-    SA_CUDA_CHECK(cudaFuncSetAttribute(attn_flash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA3_SMEM));
-    configured = true;
-  }
+  static DeviceOnce once;
+  if (int rc = once.run([&]() -> int {
+        SA_CUDA_CHECK(cudaFuncSetAttribute(attn_flash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA3_SMEM));
+        return SA_OK;
+      }))
+    return rc;
   dim3 grid((S + 2 * FA_BM - 1) / (2 * FA_BM), heads, frames);
   attn_flash_kernel<<<grid, 320, FA3_SMEM, stream>>>(*tm, S, C, static_cast<__nv_bfloat16*>(out), ldo);
   SA_CUDA_CHECK(cudaGetLastError());

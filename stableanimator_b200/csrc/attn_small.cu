@@ -395,12 +395,12 @@ extern "C" int sa_attn_id(const void* q, int32_t ldq, const float* ik, const flo
   if (num_tokens != 4) return fail(SA_ERR_INVALID, "sa_attn_id: num_tokens must be 4");
   if (C != heads * 64 || ldq % 8 || ldo % 8) return fail(SA_ERR_INVALID, "sa_attn_id: head_dim must be 64");
   const size_t smem = sizeof(float) * 2 * 4 * C;
-  static bool configured = false;
-  if (!configured) {
-    SA_CUDA_CHECK(cudaFuncSetAttribute(attn_id_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       96 * 1024));
-    configured = true;
-  }
+  static DeviceOnce once;
+  if (int rc = once.run([&]() -> int {
+        SA_CUDA_CHECK(cudaFuncSetAttribute(attn_id_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        return SA_OK;
+      }))
+    return rc;
   SA_CUDA_CHECK(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * B * F, stream));
   dim3 grid((S + 31) / 32, B * F, 1);
   attn_id_kernel<4><<<grid, 256, smem, stream>>>(static_cast<const __nv_bfloat16*>(q), ldq, ik, iv,

@@ -237,12 +237,13 @@ extern "C" int sa_attn_tokens(const void* qkv, int32_t ld, int32_t b, int32_t n,
   size_t smem = static_cast<size_t>(n) * (d / 2 + 1) * 4 + (static_cast<size_t>(n) * d + (static_cast<size_t>(n) * d & 1)) * 2 +
                 static_cast<size_t>(AT_WARPS) * (n + d) * 4;
   if (smem > 227 * 1024) return fail(SA_ERR_INVALID, "sa_attn_tokens: %d tokens x head_dim %d do not fit shared memory", n, d);
-  static size_t configured = 0;
-  if (smem > configured) {
-    SA_CUDA_CHECK(cudaFuncSetAttribute(attn_tokens_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem)));
-    configured = smem;
-  }
+  // the whole opt-in range once per device (the requested size varies with the token count)
+  static DeviceOnce once;
+  if (int rc = once.run([&]() -> int {
+        SA_CUDA_CHECK(cudaFuncSetAttribute(attn_tokens_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        return SA_OK;
+      }))
+    return rc;
   dim3 grid(heads, b, (n + AT_QB - 1) / AT_QB);
   attn_tokens_kernel<<<grid, AT_WARPS * 32, smem, stream>>>(static_cast<const __nv_bfloat16*>(qkv), ld, n, heads, d,
                                                             scale, static_cast<__nv_bfloat16*>(out), ldo);

@@ -3,6 +3,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <list>
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -58,8 +59,14 @@ struct TmapHash {
 const CUtensorMap* get_tmap_bf16(const void* base, int rank, const uint64_t* dims,
                                  const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes,
                                  const uint32_t* elem_strides) {
+  // bounded LRU: `lru` front = most recently used; the map points at list nodes (key, storage)
+  struct Node {
+    TmapKey key;
+    CUtensorMap* tm;
+  };
   static std::mutex mu;
-  static std::unordered_map<TmapKey, CUtensorMap*, TmapHash> cache;
+  static std::list<Node> lru;
+  static std::unordered_map<TmapKey, std::list<Node>::iterator, TmapHash> cache;
   TmapKey key;
   memset(&key, 0, sizeof(key));
   key.w[0] = reinterpret_cast<uint64_t>(base);
@@ -72,16 +79,24 @@ const CUtensorMap* get_tmap_bf16(const void* base, int rank, const uint64_t* dim
   }
   std::lock_guard<std::mutex> lock(mu);
   auto it = cache.find(key);
-  if (it != cache.end()) return it->second;
+  if (it != cache.end()) {
+    lru.splice(lru.begin(), lru, it->second);
+    return it->second->tm;
+  }
 
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     fail(SA_ERR_TMA, "cuTensorMapEncodeTiled entry point not available");
     return nullptr;
   }
-  // 64-byte aligned storage as the driver requires
+  // 64-byte aligned storage as the driver requires; at capacity the least recently used entry's storage is recycled
+  // (eager callers whose activation addresses churn would otherwise grow the cache without bound)
   CUtensorMap* tm = nullptr;
-  if (posix_memalign(reinterpret_cast<void**>(&tm), 64, sizeof(CUtensorMap)) != 0 || !tm) {
+  if (cache.size() >= static_cast<size_t>(SA_TMAP_CACHE_CAP)) {
+    tm = lru.back().tm;
+    cache.erase(lru.back().key);
+    lru.pop_back();
+  } else if (posix_memalign(reinterpret_cast<void**>(&tm), 64, sizeof(CUtensorMap)) != 0 || !tm) {
     fail(SA_ERR_TMA, "out of host memory for a tensor map");
     return nullptr;
   }
@@ -107,17 +122,20 @@ const CUtensorMap* get_tmap_bf16(const void* base, int rank, const uint64_t* dim
     free(tm);
     return nullptr;
   }
-  cache.emplace(key, tm);
+  lru.push_front(Node{key, tm});
+  cache.emplace(key, lru.begin());
   return tm;
 }
 
 int num_sms() {
-  static int n = 0;
+  static std::atomic<int> cache[64];  // zero-initialised; per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int n = cache[dev & 63].load(std::memory_order_relaxed);
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
+    cache[dev & 63].store(n, std::memory_order_relaxed);
   }
   return n;
 }

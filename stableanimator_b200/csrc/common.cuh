@@ -4,6 +4,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+#include <mutex>
+
 #include "../../include/sa_b200.h"
 
 namespace sa {
@@ -22,12 +25,35 @@ int fail(int code, const char* fmt, ...);
 // bf16 tensor map of rank `rank` (<= 5), SWIZZLE_128B (or 64B), zero OOB fill, cached by content.
 // dims/strides follow cuTensorMapEncodeTiled (dim 0 innermost; strides in BYTES for dims 1..).
 // elem_strides (optional, per dim): traversal stride -- box[i] elements are traversed, every elem_strides[i]-th loaded.
-// Returns nullptr (and sets the error text) on failure.  The returned pointer stays valid for the
-// life of the process (the cache never evicts).
+// Returns nullptr (and sets the error text) on failure.  The cache is a bounded LRU (SA_TMAP_CACHE_CAP entries):
+// a returned pointer stays valid until that many OTHER maps have been requested after it -- entry points copy the
+// map into the kernel's parameter space (__grid_constant__) at launch, a handful of requests later.
 const CUtensorMap* get_tmap_bf16(const void* base, int rank, const uint64_t* dims,
                                  const uint64_t* strides_bytes, const uint32_t* box,
                                  int swizzle_bytes = 128, const uint32_t* elem_strides = nullptr);
 
+constexpr int SA_TMAP_CACHE_CAP = 8192;
+
+// SM count of the CURRENT device (cached per device)
 int num_sms();
+
+// One-time, per-DEVICE kernel configuration (cudaFuncSetAttribute applies to the current device only), safe under
+// concurrent callers: `static DeviceOnce once; if (int rc = once.run([&]() -> int { ...; return SA_OK; })) return rc;`
+struct DeviceOnce {
+  std::atomic<uint64_t> done{0};  // bit d = device d configured
+  std::mutex mu;
+  template <class F>
+  int run(F&& f) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return fail(SA_ERR_CUDA, "cudaGetDevice failed");
+    const uint64_t bit = 1ull << (dev & 63);
+    if (done.load(std::memory_order_acquire) & bit) return SA_OK;
+    std::lock_guard<std::mutex> lock(mu);
+    if (done.load(std::memory_order_relaxed) & bit) return SA_OK;
+    const int rc = f();
+    if (rc == SA_OK) done.fetch_or(bit, std::memory_order_release);
+    return rc;
+  }
+};
 
 }  // namespace sa

@@ -764,12 +764,12 @@ template <int BN, int STAGES>
 static int launch(const CUtensorMap* a0, const CUtensorMap* a1, const CUtensorMap* b,
                   const GemmKParams& p, int m_tiles, cudaStream_t stream) {
   constexpr int SMEM = STAGES * (128 * 128 + BN * 128) + 1024 + 256;
-  static bool configured = false;
-  if (!configured) {
-    SA_CUDA_CHECK(cudaFuncSetAttribute(gemm_tap_kernel<BN, STAGES>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    configured = true;
-  }
+  static DeviceOnce once;
+  if (int rc = once.run([&]() -> int {
+        SA_CUDA_CHECK(cudaFuncSetAttribute(gemm_tap_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        return SA_OK;
+      }))
+    return rc;
   dim3 grid((p.N + BN - 1) / BN, m_tiles, 1);
   gemm_tap_kernel<BN, STAGES><<<grid, 128, SMEM, stream>>>(*a0, *a1, *b, p);
   SA_CUDA_CHECK(cudaGetLastError());
@@ -786,14 +786,15 @@ static int launch_persist(const CUtensorMap* a0, const CUtensorMap* a1, const CU
   using L = Gemm2Smem<BN, STAGES, EW, GEGLU>;
   using LP = Gemm2Smem<BN, STP, EW, true>;
   static_assert(L::TOTAL <= 232448 && LP::TOTAL <= 232448, "shared memory budget");
-  static bool configured = false;
-  if (!configured) {
-    SA_CUDA_CHECK(cudaFuncSetAttribute(gemm_tap_persist_kernel<BN, STAGES, GEGLU, EW, false>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    SA_CUDA_CHECK(cudaFuncSetAttribute(gemm_tap_persist_kernel<BN, STP, GEGLU, EW, true>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, LP::TOTAL));
-    configured = true;
-  }
+  static DeviceOnce once;
+  if (int rc = once.run([&]() -> int {
+        SA_CUDA_CHECK(cudaFuncSetAttribute(gemm_tap_persist_kernel<BN, STAGES, GEGLU, EW, false>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        SA_CUDA_CHECK(cudaFuncSetAttribute(gemm_tap_persist_kernel<BN, STP, GEGLU, EW, true>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, LP::TOTAL));
+        return SA_OK;
+      }))
+    return rc;
   p.n_tiles_n = p.N / BN;
   p.total_tiles = m_tiles * p.n_tiles_n;
   p.fd_ntn.init(p.n_tiles_n);

@@ -683,12 +683,13 @@ static int groupnorm_impl(const void* x0, const void* x1, int32_t c0, int32_t c1
       const int tile = R * C * 2;
       const int smem_stats = GN_ST * tile + 2 * GN_ST * 8 + 64 * 8 + 128;
       const int smem_apply = GN_ST * tile * (c1 > 0 ? 2 : 1) + 2 * GN_ST * 8 + 64 * 8 + 128;
-      static bool cfgd = false;
-      if (!cfgd) {
-        SA_CUDA_CHECK(cudaFuncSetAttribute(gn_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        SA_CUDA_CHECK(cudaFuncSetAttribute(gn_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        cfgd = true;
-      }
+      static DeviceOnce once;
+      if (int rc = once.run([&]() -> int {
+            SA_CUDA_CHECK(cudaFuncSetAttribute(gn_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            SA_CUDA_CHECK(cudaFuncSetAttribute(gn_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            return SA_OK;
+          }))
+        return rc;
       const int sms = num_sms();
       long long g1 = static_cast<long long>(sms) * (smem_stats <= 110 * 1024 ? 2 : 1);
       long long g2 = static_cast<long long>(sms) * (smem_apply <= 110 * 1024 ? 2 : 1);
@@ -758,16 +759,17 @@ extern "C" int sa_layernorm(const void* x, int32_t ldx, int64_t rows, int32_t c,
   __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(y);
   const bool dense = ldx == c && ldy == c && (!x_out || ldxo == c) && (x_out == nullptr || addv != nullptr) &&
                      rows * c * 2 >= (8ll << 20) && getenv("SA_LN_REG") == nullptr;
-  static int n_sm = num_sms();
+  const int n_sm = num_sms();
 #define SA_LN_STREAM(LPR, OPL, XO)                                                                        \
   do {                                                                                                    \
     using L = LnStream<LPR, OPL, XO>;                                                                     \
-    static bool cfgd = false;                                                                             \
-    if (!cfgd) {                                                                                          \
-      SA_CUDA_CHECK(cudaFuncSetAttribute(layernorm_stream_kernel<LPR, OPL, XO>,                           \
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM));          \
-      cfgd = true;                                                                                        \
-    }                                                                                                     \
+    static DeviceOnce once;                                                                               \
+    if (int rc = once.run([&]() -> int {                                                                  \
+          SA_CUDA_CHECK(cudaFuncSetAttribute(layernorm_stream_kernel<LPR, OPL, XO>,                       \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM));      \
+          return SA_OK;                                                                                   \
+        }))                                                                                               \
+      return rc;                                                                                          \
     const long long nt = (rows + L::TILE_ROWS - 1) / L::TILE_ROWS;                                        \
     long long g = static_cast<long long>(n_sm) * (L::SMEM <= 110 * 1024 ? 2 : 1);                         \
     if (g > nt) g = nt;                                                                                   \

@@ -6,7 +6,10 @@ PyTorch is used for device memory and streams only -- every arithmetic op below 
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
+import functools
+import os
 from typing import Optional, Sequence
 
 import torch
@@ -23,6 +26,39 @@ TAPS_T3 = ((0, -1, 0), (0, 0, 0), (0, 1, 0))
 
 def _stream() -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def device_of(t: torch.Tensor):
+    """Context that makes ``t``'s device current for a launch (kernels run on the CURRENT device's stream, and
+    ``cudaFuncSetAttribute`` / the SM count are per device): free when it already is, so a model built on ``cuda:1``
+    works while ``cuda:0`` is current instead of faulting on foreign pointers."""
+    if not t.is_cuda:
+        raise ValueError(f"expected a CUDA tensor, got one on {t.device} (the hot path has no CPU fallback)")
+    if t.device.index == torch.cuda.current_device():
+        return contextlib.nullcontext()
+    return torch.cuda.device(t.device)
+
+
+# NVTX range per kernel family (SURVEY section 5, tracing): SA_NVTX=1, e.g. under `nsys` / `ncu --nvtx`
+_NVTX = os.environ.get("SA_NVTX", "0") == "1"
+
+
+def _launcher(family: str):
+    """Wrap a launcher: first tensor argument's device becomes current; optional NVTX range named after the family."""
+    def deco(fn):
+        @functools.wraps(fn)
+        def wrapped(t0, *args, **kwargs):
+            with device_of(t0):
+                if not _NVTX:
+                    return fn(t0, *args, **kwargs)
+                torch.cuda.nvtx.range_push(family)
+                try:
+                    return fn(t0, *args, **kwargs)
+                finally:
+                    torch.cuda.nvtx.range_pop()
+        wrapped.family = family
+        return wrapped
+    return deco
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -47,6 +83,7 @@ def pick_tile(m: int, n: int, geglu: bool = False) -> int:
     return lib().sa_gemm_pick_tile(m, n, int(geglu))
 
 
+@_launcher("gemm_tap")
 def gemm_tap(
     a0: torch.Tensor,
     w: torch.Tensor,
@@ -100,8 +137,12 @@ def gemm_tap(
         raise ValueError(f"grid {grid} does not match {rows} positions")
     ntaps = len(taps)
     n_mma = int(n) if n is not None else w.shape[0]
-    if w.shape[1] != ntaps * (c0 + c1):
-        raise ValueError(f"w has K={w.shape[1]}, expected {ntaps}*({c0}+{c1})")
+    if w.dim() != 2 or w.shape[1] != ntaps * (c0 + c1):
+        raise ValueError(f"w must be [N, K] with K={ntaps}*({c0}+{c1}), got {tuple(w.shape)}")
+    if w.stride(0) != w.shape[1]:   # the W tensor map is built with a row pitch of K elements
+        raise ValueError("w must have dense rows (stride(0) == K); pass .contiguous() for a sliced / padded weight")
+    if geglu and tile_n and n_mma % tile_n:
+        raise ValueError("tile_n must divide n for GEGLU-interleaved weights")
     n_out = n_mma // 2 if geglu else n_mma
     if out is None:
         out = torch.empty((rows, n_out), device=a0.device,
@@ -189,6 +230,7 @@ def interleave_geglu(w: torch.Tensor, b: Optional[torch.Tensor]):
 
 
 # ----------------------------------------------------------------------------- attention
+@_launcher("attn_spatial")
 def attn_spatial(qkv: torch.Tensor, frames: int, s: int, heads: int,
                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """softmax(q k^T / 8) v per (frame, head); qkv 16-bit [frames*s, 3C] -> bf16 [frames*s, C].
@@ -210,6 +252,7 @@ def v_block_to_f16_(qkv: torch.Tensor, c: int) -> torch.Tensor:
     return qkv
 
 
+@_launcher("attn_temporal")
 def attn_temporal(qkv: torch.Tensor, b: int, f: int, s: int, heads: int,
                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _chk_bf16(qkv, "qkv")
@@ -221,6 +264,7 @@ def attn_temporal(qkv: torch.Tensor, b: int, f: int, s: int, heads: int,
     return out
 
 
+@_launcher("attn_id")
 def attn_id(q: torch.Tensor, ik: torch.Tensor, iv: torch.Tensor, b: int, f: int, s: int, heads: int,
             stats: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """ip = softmax(q ik^T / 8) iv over the 4 face tokens; stats (fp64 [b*f, 2]) gets Sum, Sum^2.
@@ -240,6 +284,7 @@ def attn_id(q: torch.Tensor, ik: torch.Tensor, iv: torch.Tensor, b: int, f: int,
     return out
 
 
+@_launcher("attn_id")
 def attn_id_finalize(stats, vclip, wv, w_rowsum, bias, b, f, s, c, row_scale, row_bias) -> None:
     """vclip: fp32 view [b, C] (any batch stride); the rest contiguous fp32."""
     for t, nm in ((wv, "wv"), (w_rowsum, "w_rowsum"), (bias, "bias"),
@@ -253,6 +298,7 @@ def attn_id_finalize(stats, vclip, wv, w_rowsum, bias, b, f, s, c, row_scale, ro
 
 
 # ----------------------------------------------------------------------------- normalisation
+@_launcher("groupnorm")
 def groupnorm(x0: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, rows_per_stat: int,
               *, x1: Optional[torch.Tensor] = None, silu: bool = True, stats_ws: Optional[torch.Tensor] = None,
               out: Optional[torch.Tensor] = None, stats_ready: bool = False) -> torch.Tensor:
@@ -283,6 +329,7 @@ def groupnorm(x0: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: fl
     return out
 
 
+@_launcher("layernorm")
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, addv: Optional[torch.Tensor] = None,
               rows_per_group: int = 1, x_out: Optional[torch.Tensor] = None,
               out: Optional[torch.Tensor] = None, eps: float = 1e-5) -> torch.Tensor:
@@ -299,6 +346,7 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, addv:
 
 
 # ----------------------------------------------------------------------------- small / memory-bound ops
+@_launcher("embedding")
 def small_linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
                  silu_in: bool = False, silu_out: bool = False, accumulate: bool = False,
                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -316,6 +364,7 @@ def small_linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] 
     return out
 
 
+@_launcher("embedding")
 def sinusoid(t: torch.Tensor, dim: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _chk_f32(t, "t")
     n = t.numel()
@@ -325,6 +374,7 @@ def sinusoid(t: torch.Tensor, dim: int, out: Optional[torch.Tensor] = None) -> t
     return out
 
 
+@_launcher("conv_direct")
 def conv_direct(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor], cout: int, ksz: int,
                 stride: int, pad: int, *, silu: bool = False, scale: float = 1.0,
                 add: Optional[torch.Tensor] = None, add_from: int = 0,
@@ -342,6 +392,7 @@ def conv_direct(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor],
     return out
 
 
+@_launcher("layout")
 def upsample2x(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _chk_bf16(x, "x")
     n, h, w, c = x.shape
@@ -351,6 +402,7 @@ def upsample2x(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Ten
     return out
 
 
+@_launcher("layout")
 def im2col_s2(x: torch.Tensor, out: Optional[torch.Tensor] = None, pad: int = 1) -> torch.Tensor:
     """3x3 stride-2 gather: pad=1 symmetric (UNet), pad=0 = F.pad(x, (0, 1, 0, 1)) (VAE encoder)."""
     _chk_bf16(x, "x")
@@ -364,6 +416,7 @@ def im2col_s2(x: torch.Tensor, out: Optional[torch.Tensor] = None, pad: int = 1)
     return out
 
 
+@_launcher("layout")
 def im2col3x3_c8(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """conv_in gather: x bf16 [n, h, w, 8] -> bf16 [n*h*w, 128] (72 values (ky, kx, ci) + zero padding)."""
     _chk_bf16(x, "x")
@@ -376,6 +429,7 @@ def im2col3x3_c8(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.T
     return out
 
 
+@_launcher("layout")
 def nchw_to_nhwc(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """[n, c, h, w] fp32/bf16 contiguous -> bf16 [n, h, w, c]."""
     if not x.is_contiguous() or x.dtype not in (torch.float32, torch.bfloat16):
@@ -388,6 +442,7 @@ def nchw_to_nhwc(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.T
     return out
 
 
+@_launcher("layout")
 def nhwc_to_nchw_f32(x: torch.Tensor, n: int, c: int, hw: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """fp32 [n*hw, ld] (first c columns) -> fp32 [n, c, hw]."""
     if x.dtype != torch.float32:
@@ -399,18 +454,21 @@ def nhwc_to_nchw_f32(x: torch.Tensor, n: int, c: int, hw: int, out: Optional[tor
     return out
 
 
+@_launcher("sampler")
 def sampler_prepare(latents, image_latents, idx, nb, b0, f, hw, sigma, out) -> None:
     check(lib().sa_sampler_prepare(latents.data_ptr(), image_latents.data_ptr(), idx.data_ptr(), nb, b0,
                                    idx.numel(), f, hw, float(sigma), out.data_ptr(), _stream()),
           "sa_sampler_prepare")
 
 
+@_launcher("sampler")
 def sampler_accumulate(unet_out, idx, weight, nb, b0, f, hw, noise) -> None:
     check(lib().sa_sampler_accumulate(unet_out.data_ptr(), unet_out.stride(-2), idx.data_ptr(),
                                       weight.data_ptr(), nb, b0, idx.numel(), f, hw, noise.data_ptr(),
                                       _stream()), "sa_sampler_accumulate")
 
 
+@_launcher("sampler")
 def sampler_step(noise, cnt, guidance, f, chw, sigma, sigma_next, latents) -> None:
     check(lib().sa_sampler_step(noise.data_ptr(), cnt.data_ptr(), guidance.data_ptr(), f, chw, float(sigma),
                                 float(sigma_next), latents.data_ptr(), _stream()), "sa_sampler_step")

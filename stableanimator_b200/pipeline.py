@@ -101,7 +101,7 @@ class AnimationPipelineB200:
                  motion_bucket_id: int = 127, noise_aug_strength: float = 0.02, image_only_indicator: bool = False,
                  decode_chunk_size: Optional[int] = None, num_videos_per_prompt: int = 1,
                  generator: Optional[torch.Generator] = None, latents: Optional[torch.Tensor] = None,
-                 reference_image_id_ante_embedding=None, output_type: str = "pt", return_dict: bool = True,
+                 reference_image_id_ante_embedding=None, output_type: str = "pil", return_dict: bool = True,
                  image_noise: Optional[torch.Tensor] = None):
         if num_videos_per_prompt != 1:
             raise ValueError("num_videos_per_prompt must be 1 (as in the reference)")

@@ -18,6 +18,9 @@ class PoseNetB200:
         self.dev = torch.device(device)
         self.cout = noise_latent_channels
         shapes = posenet_param_shapes(noise_latent_channels)
+        extra = [k for k in state_dict if k not in shapes]
+        if extra:  # strict=True semantics of the reference loader (inference_basic.py:449-471)
+            raise KeyError(f"pose_net state_dict: unexpected keys {extra[:5]}")
         for k, s in shapes.items():
             if k not in state_dict or tuple(state_dict[k].shape) != tuple(s):
                 raise KeyError(f"pose_net state_dict: bad or missing {k}")

@@ -181,7 +181,9 @@ class AnimationSampler:
             for ti, branches in plan["work"]:
                 if 1 in branches:
                     pose_nhwc[ti] = self.pose_net.forward_nhwc(pose_d[plan["tiles"][ti]])
-        n_steps = self.steps if steps_to_run is None else steps_to_run
+        n_steps = self.steps if steps_to_run is None else int(steps_to_run)
+        if not 0 < n_steps <= self.steps:
+            raise ValueError(f"steps_to_run must be in 1..{self.steps} (num_inference_steps), got {steps_to_run}")
         for i in range(n_steps):
             sigma, sigma_next = self.sigmas[i], self.sigmas[i + 1]
             noise.zero_()
