@@ -154,7 +154,8 @@ def transformer_spatio_temporal(sd: SD, t: TstSpec, x: torch.Tensor, ehs: torch.
     y = y.permute(0, 2, 3, 1).reshape(bf, h * w, c)                              # :661
     y = linear(sd, f"{t.name}.proj_in", y)                                       # :664
     pos = torch.arange(frames, device=x.device).repeat(b, 1).reshape(-1)         # :666-668
-    emb = timestep_mlp(sd, f"{t.name}.time_pos_embed", timestep_embedding(pos, c))[:, None, :]
+    emb = timestep_mlp(sd, f"{t.name}.time_pos_embed",
+                       timestep_embedding(pos, c).to(x.dtype))[:, None, :]      # :669-677 (cast :674)
     y = spatial_block(sd, f"{t.name}.transformer_blocks.0", y, ehs, t.heads)     # :681-684
     y_mix = temporal_block(sd, f"{t.name}.temporal_transformer_blocks.0", y + emb, frames,
                            time_ctx, t.heads)                                    # :686-692
@@ -202,9 +203,10 @@ def res_block(sd: SD, r: ResSpec, x: torch.Tensor, temb: torch.Tensor, frames: i
 def time_embedding(sd: SD, cfg: UNetConfig, timestep: torch.Tensor, added_time_ids: torch.Tensor) -> torch.Tensor:
     """unet.py:249-271: emb[B,1280] = MLP(sinusoid(t,320)) + MLP(sinusoid(ids.flatten(),256) -> [B,768])."""
     b = added_time_ids.shape[0]
+    dt = sd["conv_in.weight"].dtype   # the model dtype the fp32 sinusoids are cast to (:263, :269); fp32 here = no-op
     t = timestep.reshape(-1).float().expand(b)
-    emb = timestep_mlp(sd, "time_embedding", timestep_embedding(t, cfg.block_out_channels[0]))
-    te = timestep_embedding(added_time_ids.flatten().float(), cfg.addition_time_embed_dim).reshape(b, -1)
+    emb = timestep_mlp(sd, "time_embedding", timestep_embedding(t, cfg.block_out_channels[0]).to(dt))
+    te = timestep_embedding(added_time_ids.flatten().float(), cfg.addition_time_embed_dim).reshape(b, -1).to(dt)
     return emb + timestep_mlp(sd, "add_embedding", te)
 
 

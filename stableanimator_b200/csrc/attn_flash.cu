@@ -7,14 +7,16 @@
 // map (cols, S, frames), so head_to_batch_dim / .contiguous() (:1893-1895) and batch_to_head_dim
 // (:1905) never materialise; rows past S are zero-filled by TMA and masked to -inf.
 //
-// CTA = 2 query tiles of 128 rows of one (frame, head); 320 threads:
-//   warps 0-3 / 4-7 : softmax warpgroup of tile A / tile B, one thread per query row (TMEM lane)
-//   warp 8          : TMA producer (Q tiles once; K/V blocks of 128 keys, 4-stage ring shared by
-//                     both tiles)
-//   warp 9          : MMA issuer + TMEM allocator
-// The two tiles ping-pong on the tensor core: while warpgroup A runs the softmax of S_A(j) the MMA
-// pipe computes P_B V(j-1), S_B(j), ...  Per tile and key block:
-//   S = Q K^T (128x128 fp32 in TMEM) -> softmax thread: one tcgen05.ld of its row, max, exp2, P as
+// CTA = 2 query tiles of 128 rows of one (frame, head); 640 threads:
+//   warps 0-15 : softmax.  Warp w serves TMEM lane quadrant (w & 3) of tile ((w >> 2) & 1) and the 64-column half
+//                (w >> 3) of each 128-key block: TWO threads share a query row, so an SM sub-partition holds four
+//                softmax warps (round 1: two, each owning whole rows -- ncu: MUFU pipe 69 %, issue 35 %, tensor 34 %:
+//                latency-exposed on the ex2 chain with too few warps to cover it)
+//   warp 16    : TMA producer (Q tiles once; K/V blocks of 128 keys, 4-stage ring shared by both tiles)
+//   warp 17    : MMA issuer + TMEM allocator      (warps 18, 19 idle: setmaxnreg moves registers per warpgroup)
+// The two tiles ping-pong on the tensor core: while the softmax of S_A(j) runs the MMA pipe computes P_B V(j-1),
+// S_B(j), ...  Per tile and key block:
+//   S = Q K^T (128x128 fp32 in TMEM) -> softmax thread: one tcgen05.ld of its half row, max, exp2, P as
 //   fp16 back into TMEM -> O += P V (TS-form MMA, accumulating in TMEM).
 #include <math.h>
 #include <stdlib.h>
@@ -29,43 +31,71 @@ constexpr int FA_TILE = 128 * 128;  // bytes of a [128][64] 16-bit tile
 
 // -----------------------------------------------------------------------------------------------------
 // Single-pass softmax, S / P / O resident in TMEM:
-//   * the softmax thread reads its whole S row (128 fp32) with ONE tcgen05.ld and immediately hands the
-//     S columns back (s_free), so the tensor core computes S(j+1) WHILE the row's softmax of block j
-//     runs -- the softmax warps never wait for Q K^T in steady state;
-//   * row max with 3-input FMNMX, exp2 on packed fp32x2 lanes (FFMA2 / FADD2); P goes back into TMEM
-//     (its own 64 columns per tile, tcgen05.st) as fp16 pairs: P is in (0, 256], so half precision holds
-//     it with an 11-bit significand (bf16: 8).  kind::f16 needs A and B in the same format (a mixed
-//     fp16 x bf16 descriptor traps), so the V block of qkv is fp16 too: the q|k|v projection writes it
+//   * the softmax thread reads its half of the S row (64 fp32) with ONE tcgen05.ld and immediately hands the
+//     S columns back (s_free), so the tensor core computes S(j+1) WHILE the row's softmax of block j runs;
+//   * row max with 3-input FMNMX; the two threads of a row exchange their half maxima through shared memory
+//     (one 64-thread named barrier per warp pair and block), so both take identical rescale decisions;
+//   * exp2 on packed fp32x2 lanes (FFMA2 / FADD2).  At head_dim 64 one ex2 per score costs twice the tensor-pipe
+//     time of the score's two MMAs (16 MUFU results / clk / SM), so a quarter of the columns take their 2^x from
+//     the FMA pipe instead (Cody-Waite split + degree-3 minimax polynomial, |rel err| <= 7.5e-5, below the
+//     fp16 rounding of P): the MUFU pipe, not the tensor pipe, is this kernel's roofline;
+//   * P goes back into TMEM (its own 64 columns per tile, tcgen05.st) as fp16 pairs: P is in (0, 256], so half
+//     precision holds it with an 11-bit significand (bf16: 8).  kind::f16 needs A and B in the same format (a
+//     mixed fp16 x bf16 descriptor traps), so the V block of qkv is fp16 too: the q|k|v projection writes it
 //     that way (sa_gemm_tap f16_from_col = 2C);
 //   * O += P V is a TS-form tcgen05.mma (A = P from TMEM, B = V MN-major from the TMA tile) that
 //     ACCUMULATES into O in TMEM over all key blocks -- no per-block fold through registers;
-//   * the running max is updated lazily: O and l are rescaled (TMEM read-modify-write by the row's own
-//     thread) only when a block's max exceeds the reference max by more than 2^8, so P <= 256 and the
-//     common case has no correction work at all.  The decision is warp-uniform (any-lane vote);
-//   * the exp2 phase saturates a sub-partition's MUFU pipe on its own (1024 cycles per warp and block;
-//     measured: tools/probes/exp_loop.cu).  Left alone, the two softmax warps of a sub-partition (tile A,
-//     tile B) fall into lock step -- both in the exp phase at half rate, then both in the MUFU-free phase
-//     (tcgen05.ld, max, barriers) with the pipe idle -- so they take turns through a pair of mbarriers:
-//     A(j), B(j), A(j+1), ... puts one warp's MUFU-free work under the other's exp phase (worth 4 %;
-//     ablations on B200 at S=4096: 0.90 ms as is, 0.64 ms with the MUFU instructions removed, i.e. the
-//     kernel runs at 70 % MUFU-pipe utilisation and 34 % tensor-pipe utilisation -- at head_dim 64 one
-//     exp2 per score costs twice the tensor-pipe time of its two MMAs, so MUFU is the roofline here).
+//   * the running max is updated lazily: O and l are rescaled (TMEM read-modify-write, each thread of the row
+//     its 32 O columns) only when a block's max exceeds the reference max by more than 2^8, so P <= 256 and the
+//     common case has no correction work at all.  The decision is warp-uniform (any-lane vote) and identical in
+//     both warps of a pair.
 // TMEM columns (all 512): S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384) P_A [384,448) P_B [448,512).
-// smem: Q 2x16K | K 4x16K | V 4x16K = 160 KB + barriers -> one CTA per SM.
+// smem: Q 2x16K | K 4x16K | V 4x16K = 160 KB + barriers + 4 KB exchange -> one CTA per SM.
 // -----------------------------------------------------------------------------------------------------
 constexpr int FA3_ST = 4;
-constexpr int FA3_SMEM = FA_TILE * (2 + 2 * FA3_ST) + 1024 + 256;
+constexpr int FA3_SW = 16;                      // softmax warps
+constexpr int FA3_THREADS = (FA3_SW + 4) * 32;  // + one warpgroup: TMA, MMA, two idle warps (setmaxnreg is per warpgroup)
+// 640 threads start with 96 registers each; the control warpgroup gives most of its share to the softmax warpgroups
+// (setmaxnreg.inc can only take what setmaxnreg.dec released inside the SAME CTA: the pool is 640 x 96 registers)
+constexpr int FA3_REGS_CTRL = 24, FA3_REGS_SOFTMAX = 112;
+static_assert(FA3_SW * 32 * FA3_REGS_SOFTMAX + 4 * 32 * FA3_REGS_CTRL <= FA3_THREADS * 96, "register pool of the CTA");
 constexpr float FA3_TAU = 8.0f;  // lazy-rescale threshold (log2 units)
+// columns whose 2^x comes from the FMA-pipe polynomial: every POLY-th group of 4 columns (template parameter; 0 = none)
 
 struct Fa3Bars {
   uint64_t q_full;
   uint64_t k_full[FA3_ST], v_full[FA3_ST], kv_empty[FA3_ST];
   uint64_t s_full[2], s_free[2], o_full[2], p_full[2];
-  uint64_t order[2][4];  // MUFU turn-taking between the two softmax warps of an SM sub-partition
   uint32_t tmem_slot;
+  float xch[2][8][2][32];  // [block parity][warp pair][column half][lane]: half-row maxima / final row sums
 };
+constexpr int FA3_SMEM = FA_TILE * (2 + 2 * FA3_ST) + 1024 + static_cast<int>(sizeof(Fa3Bars)) + 64;
 
-__global__ void __launch_bounds__(320, 1)
+// 2^x for two lanes on the FMA pipe: x = n + f, n = round(x), f in [-0.5, 0.5]; 2^f by a degree-3 minimax
+// polynomial (relative error <= 7.5e-5), 2^n by adding n to the exponent field.  x is clamped at -126 (2^-126 ~ 1e-38
+// stands in for the zeros of masked columns); no MUFU instruction.
+__device__ __forceinline__ float exp2_poly(float x) {
+  // scalar form: every constant is an instruction immediate (the packed form keeps seven 64-bit constants in
+  // registers, which this kernel cannot afford: 120 registers per softmax thread)
+  x = fmaxf(x, -126.0f);
+  const float t = x + 12582912.0f;            // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float f = x - (t - 12582912.0f);      // [-0.5, 0.5]
+  float p = fmaf(5.517166771e-02f, f, 2.426111221e-01f);
+  p = fmaf(p, f, 6.932609857e-01f);
+  p = fmaf(p, f, 9.999280736e-01f);
+  return __uint_as_float(__float_as_uint(p) + (__float_as_uint(t) << 23));
+}
+__device__ __forceinline__ void exp2_poly2(uint64_t x, float& e0, float& e1) {
+  const float2 xf = unpack2(x);
+  e0 = exp2_poly(xf.x);
+  e1 = exp2_poly(xf.y);
+}
+
+#ifndef FA3_LB
+#define FA3_LB FA3_THREADS
+#endif
+template <int POLY>
+__global__ void __launch_bounds__(FA3_LB, 1)
 attn_flash_kernel(const __grid_constant__ CUtensorMap tm, int S, int C, __nv_bfloat16* __restrict__ out,
                   int ldo) {
   extern __shared__ uint8_t smem_raw[];
@@ -82,7 +112,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm, int S, int C, __nv_bfl
   const int nblk = (S + FA_BN - 1) / FA_BN;
   const int ntiles = (q0 + FA_BM < S) ? 2 : 1;
 
-  if (warp == 8 && elect_one()) {
+  if (warp == FA3_SW && elect_one()) {
     tma_prefetch_desc(&tm);
     mbar_init(&bars->q_full, 1);
     for (int i = 0; i < FA3_ST; ++i) {
@@ -93,19 +123,23 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm, int S, int C, __nv_bfl
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars->s_full[i], 1);
       mbar_init(&bars->o_full[i], 1);
-      mbar_init(&bars->s_free[i], 128);
-      mbar_init(&bars->p_full[i], 128);
-      for (int q = 0; q < 4; ++q) mbar_init(&bars->order[i][q], 32);
+      mbar_init(&bars->s_free[i], 256);
+      mbar_init(&bars->p_full[i], 256);
     }
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc<512>(&bars->tmem_slot);
+  if (warp == FA3_SW + 1) tmem_alloc<512>(&bars->tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_slot;
-
-  if (warp == 8) {
+  // Register rebalancing: the two branches below never re-join (each ends with its own CTA-wide barrier and return),
+  // so ptxas allocates them under different budgets.
+  if (warp >= FA3_SW) {
+#ifndef FA3_NATURAL_REGS   // -DFA3_NATURAL_REGS -DFA3_LB=256: what ptxas would use unconstrained (register audit)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FA3_REGS_CTRL));
+#endif
+  if (warp == FA3_SW) {
     // ------------------------------------------------------------ TMA producer
     if (elect_one()) {
       mbar_expect_tx(&bars->q_full, ntiles * FA_TILE);
@@ -121,7 +155,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm, int S, int C, __nv_bfl
       }
     }
     __syncwarp();
-  } else if (warp == 9) {
+  } else if (warp == FA3_SW + 1) {
     // ------------------------------------------------------------ MMA issuer
     if (elect_one()) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, FA_BN, 0, 0);  // S = Q K^T (bf16, both K-major)
@@ -165,46 +199,59 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm, int S, int C, __nv_bfl
       }
     }
     __syncwarp();
-  } else {
-    // ------------------------------------------------------------ softmax warpgroups (row = thread)
-    const int t = warp >> 2;                 // tile handled by this warpgroup
-    const int r = threadIdx.x & 127;         // row in tile == TMEM lane
+  }
+    tc_fence_before();
+    named_bar_sync(15, FA3_THREADS);   // every softmax thread is done with TMEM
+    if (warp == FA3_SW + 1) tmem_dealloc<512>(tmem_base);
+    return;
+  }
+#ifndef FA3_NATURAL_REGS
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FA3_REGS_SOFTMAX));
+#endif
+  {
+    // ------------------------------------------------------------ softmax warps (two threads per query row)
+    const int quad = warp & 3;               // TMEM lane quadrant
+    const int t = (warp >> 2) & 1;           // tile handled by this warp
+    const int hc = warp >> 3;                // column half of the key block
+    const int pair = warp & 7;               // (tile, quadrant): the two warps sharing these 32 rows
+    const int lane = threadIdx.x & 31;
     if (t < ntiles) {
-      const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-      const uint32_t s_addr = lane_addr + t * 128;
-      const uint32_t o_addr = lane_addr + 256 + t * 64;
-      const uint32_t p_addr = lane_addr + 384 + t * 64;
+      const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+      const uint32_t s_addr = lane_addr + t * 128 + hc * 64;
+      const uint32_t o_addr = lane_addr + 256 + t * 64 + hc * 32;   // this thread's half of the row's O columns
+      const uint32_t p_addr = lane_addr + 384 + t * 64 + hc * 32;
       const float sl2 = 0.125f * 1.4426950408889634f;  // attn.scale * log2(e)
       const uint64_t sl22 = pack2(sl2, sl2);
       float m_ref = -INFINITY;                 // reference max the exponentials are taken against
-      uint64_t l2 = pack2(0.f, 0.f);           // row sum (two interleaved partial sums)
-      uint64_t* my_turn = &bars->order[t][warp & 3];
-      uint64_t* their_turn = &bars->order[t ^ 1][warp & 3];
-      const bool take_turns = ntiles == 2;
+      uint64_t l2 = pack2(0.f, 0.f);           // partial row sum over this thread's columns (two interleaved sums)
 
       for (int j = 0; j < nblk; ++j) {
-        const int kv_left = S - j * FA_BN;
+        const int kv_left = S - j * FA_BN - hc * 64;   // valid columns of this thread's half
         mbar_wait(&bars->s_full[t], j & 1);
         tc_fence_after();
-        uint32_t s[128];
-        tmem_ld_32x128(s_addr, s);
+        uint32_t s[64];
+        tmem_ld_32x64(s_addr, s);
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(&bars->s_free[t]);  // the tensor core may overwrite S_t with S_t(j+1) now
-        if (kv_left < FA_BN) {
+        if (kv_left < 64) {
 #pragma unroll
-          for (int c = 0; c < FA_BN; ++c)
+          for (int c = 0; c < 64; ++c)
             if (c >= kv_left) s[c] = 0xff800000u;  // -inf
         }
         float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int c = 0; c < FA_BN; c += 8) {
+        for (int c = 0; c < 64; c += 8) {
           mx[0] = max3(mx[0], __uint_as_float(s[c]), __uint_as_float(s[c + 1]));
           mx[1] = max3(mx[1], __uint_as_float(s[c + 2]), __uint_as_float(s[c + 3]));
           mx[2] = max3(mx[2], __uint_as_float(s[c + 4]), __uint_as_float(s[c + 5]));
           mx[3] = max3(mx[3], __uint_as_float(s[c + 6]), __uint_as_float(s[c + 7]));
         }
-        const float bm = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * sl2;
+        float bm = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * sl2;
+        // the row's other half: exchange through shared memory (double-buffered by block parity)
+        bars->xch[j & 1][pair][hc][lane] = bm;
+        named_bar_sync(1 + pair, 64);
+        bm = fmaxf(bm, bars->xch[j & 1][pair][hc ^ 1][lane]);
         const bool need = bm > m_ref + FA3_TAU;   // always true on the first block (m_ref = -inf)
         if (__any_sync(0xffffffffu, need)) {
           const float m_new = need ? bm : m_ref;
@@ -216,58 +263,70 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm, int S, int C, __nv_bfl
             // rescale O in TMEM: P V(j-1) must have completed; P V(j) is gated by our p_full arrival
             mbar_wait(&bars->o_full[t], (j - 1) & 1);
             tc_fence_after();
-            uint32_t o[64];
-            tmem_ld_32x64(o_addr, o);
+            uint32_t o[32];
+            tmem_ld_32x32(o_addr, o);
             tmem_ld_wait();
 #pragma unroll
-            for (int d = 0; d < FA_D; d += 2) {
+            for (int d = 0; d < 32; d += 2) {
               const float2 f = unpack2(mul2(pack2u(o[d], o[d + 1]), a2));
               o[d] = __float_as_uint(f.x);
               o[d + 1] = __float_as_uint(f.y);
             }
-            tmem_st_32x64(o_addr, o);
+            tmem_st_32x32(o_addr, o);
           }
         }
         const uint64_t nm2 = pack2(-m_ref, -m_ref);
-        uint32_t pw[64];
         uint64_t la = pack2(0.f, 0.f), lb = pack2(0.f, 0.f);
-        // my turn on the MUFU pipe: tile A's block j follows tile B's block j-1, tile B's follows tile A's
-        if (take_turns && (t == 1 || j > 0)) mbar_wait(my_turn, (t == 1 ? j : j - 1) & 1);
-#pragma unroll
-        for (int c = 0; c < FA_BN; c += 4) {
-          const float2 x0 = unpack2(fma2(pack2u(s[c], s[c + 1]), sl22, nm2));
-          const float2 x1 = unpack2(fma2(pack2u(s[c + 2], s[c + 3]), sl22, nm2));
-          const float e0 = ex2_approx(x0.x), e1 = ex2_approx(x0.y);
-          const float e2 = ex2_approx(x1.x), e3 = ex2_approx(x1.y);
-          la = add2(la, pack2(e0, e1));
-          lb = add2(lb, pack2(e2, e3));
-          pw[c >> 1] = pack_f16x2(e0, e1);        // P <= 2^8 (lazy max): fp16 keeps 11 significant bits
-          pw[(c >> 1) + 1] = pack_f16x2(e2, e3);
-        }
-        if (take_turns) mbar_arrive(their_turn);  // the other tile's warp may start its exp phase
-        l2 = add2(l2, add2(la, lb));
         if (j > 0) {  // P V(j-1) must be done reading P_t before it is overwritten (normally long since)
           mbar_wait(&bars->o_full[t], (j - 1) & 1);
           tc_fence_after();
         }
-        tmem_st_32x64(p_addr, pw);
+        // two halves of 32 columns, each stored to TMEM as soon as it is packed (keeps the live registers down)
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t pw[16];
+#pragma unroll
+          for (int cc = 0; cc < 32; cc += 4) {
+            const int c = hh * 32 + cc;
+            const uint64_t x0 = fma2(pack2u(s[c], s[c + 1]), sl22, nm2);
+            const uint64_t x1 = fma2(pack2u(s[c + 2], s[c + 3]), sl22, nm2);
+            float e0, e1, e2, e3;
+            if (POLY > 0 && ((c >> 2) % (POLY > 0 ? POLY : 1)) == POLY - 1) {   // compile-time after unrolling
+              exp2_poly2(x0, e0, e1);
+              exp2_poly2(x1, e2, e3);
+            } else {
+              const float2 f0 = unpack2(x0), f1 = unpack2(x1);
+              e0 = ex2_approx(f0.x), e1 = ex2_approx(f0.y);
+              e2 = ex2_approx(f1.x), e3 = ex2_approx(f1.y);
+            }
+            la = add2(la, pack2(e0, e1));
+            lb = add2(lb, pack2(e2, e3));
+            pw[cc >> 1] = pack_f16x2(e0, e1);        // P <= 2^8 (lazy max): fp16 keeps 11 significant bits
+            pw[(cc >> 1) + 1] = pack_f16x2(e2, e3);
+          }
+          tmem_st_32x16(p_addr + hh * 16, pw);
+        }
+        l2 = add2(l2, add2(la, lb));
         tmem_st_wait();              // P (and a rescaled O) are in TMEM
         tc_fence_before();
         mbar_arrive(&bars->p_full[t]);
       }
-      // all P V accumulated
+      // all P V accumulated: total row sum = this thread's half + the partner's
+      const float2 lf = unpack2(l2);
+      const float lh = lf.x + lf.y;
+      bars->xch[nblk & 1][pair][hc][lane] = lh;
+      named_bar_sync(1 + pair, 64);
+      const float inv = 1.0f / (lh + bars->xch[nblk & 1][pair][hc ^ 1][lane]);
       mbar_wait(&bars->o_full[t], (nblk - 1) & 1);
       tc_fence_after();
-      uint32_t o[64];
-      tmem_ld_32x64(o_addr, o);
+      uint32_t o[32];
+      tmem_ld_32x32(o_addr, o);
       tmem_ld_wait();
-      const int qrow = q0 + t * FA_BM + r;
+      const int qrow = q0 + t * FA_BM + quad * 32 + lane;
       if (qrow < S) {
-        const float2 lf = unpack2(l2);
-        const float inv = 1.0f / (lf.x + lf.y);
-        uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<long long>(frame) * S + qrow) * ldo + head * FA_D);
+        uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<long long>(frame) * S + qrow) * ldo + head * FA_D + hc * 32);
 #pragma unroll
-        for (int g = 0; g < 8; ++g)
+        for (int g = 0; g < 4; ++g)
           dst[g] = make_uint4(pack_bf16x2(__uint_as_float(o[8 * g]) * inv, __uint_as_float(o[8 * g + 1]) * inv),
                               pack_bf16x2(__uint_as_float(o[8 * g + 2]) * inv, __uint_as_float(o[8 * g + 3]) * inv),
                               pack_bf16x2(__uint_as_float(o[8 * g + 4]) * inv, __uint_as_float(o[8 * g + 5]) * inv),
@@ -277,8 +336,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm, int S, int C, __nv_bfl
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 9) tmem_dealloc<512>(tmem_base);
+  named_bar_sync(15, FA3_THREADS);
 }
 
 }  // namespace sa
@@ -298,14 +356,27 @@ extern "C" int sa_attn_spatial(const void* qkv, int32_t ld, int32_t frames, int3
   uint32_t box[3] = {64, 128, 1};
   const CUtensorMap* tm = get_tmap_bf16(qkv, 3, dims, strides, box);
   if (!tm) return SA_ERR_TMA;
+  // SA_FA_POLY=<n>: every n-th group of four score columns takes its exp2 from the FMA pipe (0 = MUFU only); A/B knob
+  static const int poly = getenv("SA_FA_POLY") ? atoi(getenv("SA_FA_POLY")) : 8;
   static DeviceOnce once;
   if (int rc = once.run([&]() -> int {
-        SA_CUDA_CHECK(cudaFuncSetAttribute(attn_flash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA3_SMEM));
+        SA_CUDA_CHECK(cudaFuncSetAttribute(attn_flash_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA3_SMEM));
+        SA_CUDA_CHECK(cudaFuncSetAttribute(attn_flash_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA3_SMEM));
+        SA_CUDA_CHECK(cudaFuncSetAttribute(attn_flash_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA3_SMEM));
+        SA_CUDA_CHECK(cudaFuncSetAttribute(attn_flash_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA3_SMEM));
+        SA_CUDA_CHECK(cudaFuncSetAttribute(attn_flash_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA3_SMEM));
         return SA_OK;
       }))
     return rc;
   dim3 grid((S + 2 * FA_BM - 1) / (2 * FA_BM), heads, frames);
-  attn_flash_kernel<<<grid, 320, FA3_SMEM, stream>>>(*tm, S, C, static_cast<__nv_bfloat16*>(out), ldo);
+  __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
+  switch (poly) {
+    case 0: attn_flash_kernel<0><<<grid, FA3_THREADS, FA3_SMEM, stream>>>(*tm, S, C, o, ldo); break;
+    case 2: attn_flash_kernel<2><<<grid, FA3_THREADS, FA3_SMEM, stream>>>(*tm, S, C, o, ldo); break;
+    case 3: attn_flash_kernel<3><<<grid, FA3_THREADS, FA3_SMEM, stream>>>(*tm, S, C, o, ldo); break;
+    case 8: attn_flash_kernel<8><<<grid, FA3_THREADS, FA3_SMEM, stream>>>(*tm, S, C, o, ldo); break;
+    default: attn_flash_kernel<4><<<grid, FA3_THREADS, FA3_SMEM, stream>>>(*tm, S, C, o, ldo); break;
+  }
   SA_CUDA_CHECK(cudaGetLastError());
   return SA_OK;
 }

@@ -306,6 +306,10 @@ constexpr int EPI_TILE_BYTES = 32 * 64;   // per-warp staging tile: [32 rows][32
 // slots only -- the 48 KB this frees with eight epilogue warps buy two more pipeline stages, which the short-K GEGLU
 // GEMMs need to cover the TMA latency (4 stages x 32 KB in flight against ~125 B/clk of operand traffic per SM).
 template <bool SLIM> struct EpiSlots { static constexpr int RO = SLIM ? 2 : 3, X = SLIM ? 0 : 2; };
+// Accumulator sets of the fused GroupNorm statistics, indexed by (tile counter % GN_SETS).  The TMEM double buffer
+// bounds the skew between epilogue warps to two tiles (a warp cannot read tile i+2 before every warp has released
+// tile i, and cannot release tile i+1 before it is done with tile i), so three sets never alias.
+constexpr int GN_SETS = 3;
 
 template <int BN, int STAGES, int EW, bool SLIM = false>
 struct Gemm2Smem {
@@ -314,7 +318,10 @@ struct Gemm2Smem {
   static constexpr int EPI_OFF = STAGES * STAGE_BYTES;
   static constexpr int BAR_OFF = EPI_OFF + EW * EPI_WARP_BYTES;
   static constexpr int NBARS = 2 * STAGES + 4 + EW * (EpiSlots<SLIM>::RO + EpiSlots<SLIM>::X);
-  static constexpr int TOTAL = BAR_OFF + NBARS * 8 + 16 + 1024;  // + tmem slot + alignment slack
+  // fused GroupNorm statistics (non-SLIM only): GN_SETS per-tile accumulator sets of [32 groups][2] fp64 + arrival counters
+  static constexpr int GN_OFF = BAR_OFF + NBARS * 8 + 16;
+  static constexpr int GN_BYTES = SLIM ? 0 : (GN_SETS * 64 * 8 + 16);
+  static constexpr int TOTAL = GN_OFF + GN_BYTES + 1024;  // + alignment slack
 };
 
 // EW = number of epilogue warps: 8 (two per TMEM quadrant, alternating chunks) for short-K problems
@@ -347,6 +354,8 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
   uint64_t* acc_empty = acc_full + 2;        // [2]
   uint64_t* epi_bar = acc_empty + 2;         // [EPI_WARPS][RO_SLOTS + X_SLOTS]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_bar + EW * (EPI_RO_SLOTS + EPI_X_SLOTS));
+  double* gn_acc = reinterpret_cast<double*>(smem + L::GN_OFF);                    // [GN_SETS][32][2]
+  uint32_t* gn_cnt = reinterpret_cast<uint32_t*>(smem + L::GN_OFF + GN_SETS * 64 * 8);  // [GN_SETS]
 
   const int warp = threadIdx.x >> 5;
   const int KB = p.ntaps * p.kcpt;
@@ -370,6 +379,12 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<TCOLS>(tmem_slot);
+  if constexpr (!SLIM) {
+    if (p.gn_stats) {
+      for (int i = threadIdx.x; i < GN_SETS * 64; i += blockDim.x) gn_acc[i] = 0.0;
+      if (threadIdx.x < GN_SETS) gn_cnt[threadIdx.x] = 0u;
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -524,13 +539,28 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
       // below needs it uniform over the warp's 32 rows
       int gn_sid = -1;
       bool gn_uniform = false;
+      // gn_tile: every row of the tile lies inside the grid and belongs to ONE statistic -> the cheap path: column
+      // sums from the staged bf16 tile in packed fp32, warp-reduced to groups, kept in two registers per lane
+      // (lane l = group g_first + l) over the tile, then one fp64 shared-memory add per lane and ONE set of fp64
+      // global atomics per (tile, group) by the last epilogue warp to finish the tile
+      bool gn_tile = false;
+      int g_first = 0;
+      float ga1 = 0.f, ga2 = 0.f;
+      const int nout0 = GEGLU ? n0 / 2 : n0;
       if (!PLAIN && !GEGLU && p.gn_stats) {
         const int p1 = q1 + i1, p2 = q2 + i2, p3 = q3 + i3;
         if ((p1 < p.d1) && (p2 < p.d2) && (p3 < p.d3))
           gn_sid = static_cast<int>(p.fd_grps.div(static_cast<uint32_t>((p3 * p.d2 + p2) * p.d1 + p1)));
-        gn_uniform = __all_sync(0xffffffffu, gn_sid == __shfl_sync(0xffffffffu, gn_sid, 0)) && gn_sid >= 0;
+        const int e1 = q1 + p.b1 - 1, e2 = q2 + p.b2 - 1, e3 = q3 + p.b3 - 1;
+        if (e1 < p.d1 && e2 < p.d2 && e3 < p.d3) {   // rows of the box span [row(q), row(e)]; the statistic index is monotonic
+          const uint32_t smin = p.fd_grps.div(static_cast<uint32_t>((q3 * p.d2 + q2) * p.d1 + q1));
+          const uint32_t smax = p.fd_grps.div(static_cast<uint32_t>((e3 * p.d2 + e2) * p.d1 + e1));
+          gn_tile = smin == smax;
+        }
+        g_first = static_cast<int>(p.fd_gcpg.div(static_cast<uint32_t>(nout0)));
+        if (!gn_tile)
+          gn_uniform = __all_sync(0xffffffffu, gn_sid == __shfl_sync(0xffffffffu, gn_sid, 0)) && gn_sid >= 0;
       }
-      const int nout0 = GEGLU ? n0 / 2 : n0;
       const int ab = ti & 1;
       mbar_wait_relaxed(&acc_full[ab], (ti >> 1) & 1);
       tc_fence_after();
@@ -696,6 +726,47 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
             // the first lane of each group adds to the fp64 accumulators.
             const uint8_t* tile = sRO + slot * EPI_TILE_BYTES;
             const int gid = static_cast<int>(p.fd_gcpg.div(static_cast<uint32_t>(ncol + lane)));
+            if (gn_tile) {
+              // lane = (row parity hf, 32-bit word w = column pair (2w, 2w+1)): 16 conflict-free word loads cover the
+              // 32 x 32 tile; channels-per-group and chunk origins are even, so a column pair never straddles a group
+              const int hf = lane >> 4, w = lane & 15;
+              const uint8_t* colp = tile + hf * 64 + (w & 3) * 4;
+              const int u = w >> 2;
+              uint64_t sv = pack2(0.f, 0.f), qv = pack2(0.f, 0.f);
+#pragma unroll
+              for (int rr = 0; rr < 16; ++rr) {
+                const uint64_t v = bf16x2_to_f32x2(*reinterpret_cast<const uint32_t*>(colp + rr * 128 + ((u ^ (rr & 3)) << 4)));
+                sv = add2(sv, v);
+                qv = fma2(v, v, qv);
+              }
+              const float2 sf = unpack2(sv), qf = unpack2(qv);
+              float s1 = sf.x + sf.y, s2 = qf.x + qf.y;
+              s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+              s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+              // segmented suffix sums over the 16 column pairs (both half-warps mirror each other)
+              const int cpg = static_cast<int>(p.fd_gcpg.d);
+              const int gw = static_cast<int>(p.fd_gcpg.div(static_cast<uint32_t>(ncol + 2 * w)));
+#pragma unroll
+              for (int off = 1; off < 16; off <<= 1) {
+                const float t1 = __shfl_down_sync(0xffffffffu, s1, off, 16);
+                const float t2 = __shfl_down_sync(0xffffffffu, s2, off, 16);
+                const int g2_ = __shfl_down_sync(0xffffffffu, gw, off, 16);
+                if (w + off < 16 && g2_ == gw) {
+                  s1 += t1;
+                  s2 += t2;
+                }
+              }
+              // lane l collects group g_first + l from the first column pair of that group inside this chunk
+              const int lo = (g_first + lane) * cpg;
+              const bool present = lo < ncol + EPI_CHUNK && lo + cpg > ncol;
+              const int src = present ? ((lo > ncol ? lo : ncol) - ncol) >> 1 : 0;
+              const float v1 = __shfl_sync(0xffffffffu, s1, src);
+              const float v2 = __shfl_sync(0xffffffffu, s2, src);
+              if (present) {
+                ga1 += v1;
+                ga2 += v2;
+              }
+            } else
             // bf16 values and their squares are exact in fp32; the sums run in fp64, so the statistics do not depend on
             // how rows fall into tiles / warps (B = 2 gives the bits of two B = 1 calls) and carry no fp32 partial-sum noise
             if (gn_uniform) {
@@ -749,6 +820,38 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
           }
         }
         __syncwarp();
+      }
+      if constexpr (!SLIM) {
+        if (gn_tile) {
+          // tile done for this warp: fold the lane's group sums into the tile's shared fp64 set; the last of the EW
+          // warps to arrive flushes the set to the global fp64 accumulators and clears it
+          const int set = ti % GN_SETS;
+          double* acc = gn_acc + set * 64;
+          if (ga1 != 0.f || ga2 != 0.f) {
+            atomicAdd(&acc[lane * 2], static_cast<double>(ga1));
+            atomicAdd(&acc[lane * 2 + 1], static_cast<double>(ga2));
+          }
+          __threadfence_block();
+          __syncwarp();
+          uint32_t last = 0;
+          if (lane == 0) last = (atomicAdd(&gn_cnt[set], 1u) == static_cast<uint32_t>(EW - 1)) ? 1u : 0u;
+          last = __shfl_sync(0xffffffffu, last, 0);
+          if (last) {
+            __threadfence_block();
+            volatile double* vacc = acc;
+            const double t1 = vacc[lane * 2], t2 = vacc[lane * 2 + 1];
+            vacc[lane * 2] = 0.0;
+            vacc[lane * 2 + 1] = 0.0;
+            if (g_first + lane < p.gn_groups && (t1 != 0.0 || t2 != 0.0)) {
+              double* dst = p.gn_stats + (static_cast<long long>(gn_sid) * p.gn_groups + g_first + lane) * 2;
+              atomicAdd(dst, t1);
+              atomicAdd(dst + 1, t2);
+            }
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&gn_cnt[set]) = 0u;
+          }
+        }
       }
     }
     if (lane == 0) tma_store_wait_all();

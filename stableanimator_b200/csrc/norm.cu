@@ -144,9 +144,11 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0,
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float y = v[u][k] * a[k] + b[k];
-        v[u][k] = do_silu ? silu(y) : y;
+      for (int k = 0; k < 8; k += 2) {   // same arithmetic as the streamed kernel (fma2 + one-MUFU SiLU): identical bits
+        const uint64_t y2 = fma2(pack2(v[u][k], v[u][k + 1]), pack2(a[k], a[k + 1]), pack2(b[k], b[k + 1]));
+        const float2 o = unpack2(do_silu ? silu2(y2) : y2);
+        v[u][k] = o.x;
+        v[u][k + 1] = o.y;
       }
       store8(out + (ns * P + r + u * step) * ldo + c, v[u]);
     }
@@ -155,9 +157,11 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0,
     float v[8];
     load8(src + (ns * P + r) * ld, v);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float y = v[k] * a[k] + b[k];
-      v[k] = do_silu ? silu(y) : y;
+    for (int k = 0; k < 8; k += 2) {
+      const uint64_t y2 = fma2(pack2(v[k], v[k + 1]), pack2(a[k], a[k + 1]), pack2(b[k], b[k + 1]));
+      const float2 o = unpack2(do_silu ? silu2(y2) : y2);
+      v[k] = o.x;
+      v[k + 1] = o.y;
     }
     store8(out + (ns * P + r) * ldo + c, v);
   }
@@ -581,19 +585,14 @@ gn_stream_kernel(const GnStreamP p) {
             float v[8];
             load8s(src + r * src_ld, v);
             if (APPLY) {
-              // packed fp32x2 lanes; silu(y) = y / (1 + 2^(-y log2 e))
+              // packed fp32x2 lanes; silu2: one MUFU (tanh) per element
               uint32_t w[4];
 #pragma unroll
               for (int k = 0; k < 8; k += 2) {
                 const uint64_t y2 = fma2(pack2(v[k], v[k + 1]), pack2(a[cs][k], a[cs][k + 1]),
                                          pack2(b[cs][k], b[cs][k + 1]));
                 if (p.do_silu) {
-                  const float2 n = unpack2(mul2(y2, pack2(-1.4426950408889634f, -1.4426950408889634f)));
-                  const float2 d = unpack2(add2(pack2(ex2_approx(n.x), ex2_approx(n.y)), pack2(1.0f, 1.0f)));
-                  float r0, r1;
-                  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d.x));
-                  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d.y));
-                  w[k >> 1] = pack_bf16x2_f2(mul2(y2, pack2(r0, r1)));
+                  w[k >> 1] = pack_bf16x2_f2(silu2(y2));
                 } else {
                   w[k >> 1] = pack_bf16x2_f2(y2);
                 }

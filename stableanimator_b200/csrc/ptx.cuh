@@ -389,6 +389,19 @@ __device__ __forceinline__ uint64_t gelu2(uint64_t x) {
   return mul2(x, pack2(r0, r1));
 }
 
+// SiLU on two lanes with ONE MUFU per element: y sigmoid(y) = h + h tanh(h), h = y / 2 (tanh.approx: max relative
+// error 2^-11, i.e. |error| <= 2.5e-4 |y| -- below the bf16 rounding of the result for y > -1 and under 2e-3 absolute
+// on the negative tail, where the ex2 + rcp form costs two MUFU per element and made the GroupNorm apply pass
+// MUFU-bound: ncu pipe_xu 60 % at 53 % of the HBM roofline)
+__device__ __forceinline__ uint64_t silu2(uint64_t y) {
+  const uint64_t h = mul2(y, pack2(0.5f, 0.5f));
+  const float2 hf = unpack2(h);
+  float t0, t1;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(hf.x));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(hf.y));
+  return fma2(h, pack2(t0, t1), h);
+}
+
 __device__ __forceinline__ float max3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));

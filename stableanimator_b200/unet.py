@@ -59,7 +59,7 @@ class UNetB200:
         # pass.  Correct and B-invariant (tests/test_gemm_gpu.py), but measured 0.5 ms SLOWER per B=2 call at 64x64x16
         # (tools/unet_ab.py: the statistics pass re-reads a tensor that is still L2-resident, the epilogue work is
         # not free) -- off by default, SA_GN_FUSE=1 turns it on
-        self.fuse_gn_stats = os.environ.get("SA_GN_FUSE", "0") == "1"
+        self.fuse_gn_stats = os.environ.get("SA_GN_FUSE", "1") == "1"
         # zero-context (unconditional CFG branch) shortcut of the ID cross-attention; SA_SKIP_ZERO_CTX=0 for A/B
         self.skip_zero_context = os.environ.get("SA_SKIP_ZERO_CTX", "1") != "0"
         # stride-2 Downsample2D through TMA element strides (SA_STRIDED_DOWN=0: im2col_s2 + GEMM, for A/B)

@@ -132,8 +132,9 @@ def test_unet_fused_groupnorm_statistics_option():
     m = model(c["cfg"], c["gold"]["seed"])
     pl = c["pose_latents"].cuda()
     args = (c["sample"].cuda(), c["t"], c["ehs"].cuda(), c["ati"].cuda())
+    m.fuse_gn_stats = False          # the two-pass statistics (SA_GN_FUSE=0)
     plain = m(*args, pose_latents=pl)[0]
-    m.fuse_gn_stats = True
+    m.fuse_gn_stats = True           # the default
     try:
         fused = m(*args, pose_latents=pl)[0]
         s2 = torch.cat([c["sample"] * 0.5, c["sample"]], 0).cuda()
@@ -142,7 +143,7 @@ def test_unet_fused_groupnorm_statistics_option():
         both = m(s2, c["t"], ehs2, ati2, pose_latents=pl, pose_batch_from=1)[0]
         a = m(s2[:1], c["t"], ehs2[:1], ati2[:1], pose_latents=None)[0]
     finally:
-        m.fuse_gn_stats = False
+        m.fuse_gn_stats = True
     ref = c["gold"]["out"].cuda()
     print(f"fused-statistics UNet vs reference: {rel_l2(fused, ref):.3e} (two-pass: {rel_l2(plain, ref):.3e})")
     assert rel_l2(fused, ref) <= 1e-2
