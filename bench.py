@@ -5,6 +5,11 @@
   python bench.py [--gpus N] [--steps K] [--warmup W]          our arm (B200 kernels)
   python bench.py --impl reference [...]                       the reference's own CPU path (oracle port)
 
+Our line also carries: ``roofline`` (dominant kernel family, live CUDA-event measurement, plus ``memory_bound`` GB/s of
+the GroupNorm / LayerNorm / CFG+Euler kernels), ``gpu_eager_baseline`` (N = 1: the reference graph in eager bf16 PyTorch
+on the same GPU -- the north star's >= 8x denominator), ``cpu_baseline`` (N = 1: one CFG step of BASELINE configs[0] on the
+host cores) and ``long_video`` (BASELINE configs[4], 576x1024x128f, strong scaling over the N ranks).
+
 A "step" is one full 25-step denoise of the workload through ``AnimationSampler``.  N=1: BASELINE
 configs[1] (512x512 -> 64x64 latent, 16 frames, one tile, CFG cond/uncond fused in one B=2 batch).
 N>1 (torchrun): weak scaling of the long-video sampler -- N frame tiles of 16 frames (overlap 4,
@@ -106,52 +111,120 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------- reference / CPU leg
+# reference-graph FLOPs of one B=1 UNet call at the CPU sample's shape (BASELINE.md section 3, configs[0])
+FLOPS_PER_CALL_32x32x8 = 2.364e12
+
+
+class CpuCfgStep:
+    """BASELINE.md section 4 / BASELINE.json configs[0]: ONE full CFG step of the reference's loop on the host cores --
+    two B=1 fp32 UNet calls (uncond, cond), PoseNet, the CFG combine and the Euler update
+    (inference_pipeline_animation.py:641-699 restated in oracle/sampler_oracle.py) -- at 256x256 (32x32 latent), 8 frames,
+    full-width UNet, ``torch.set_num_threads(os.cpu_count())``.  The reference module itself cannot travel to the GPU
+    box (Python + absent dependencies), so the arithmetic is the oracle port that is pinned to it (kind = "port")."""
+
+    def __init__(self, size: str = "full", frames: int = 8, hw: int = 32, w: int = 0):
+        from oracle import sampler_oracle as SO
+        from oracle import unet_oracle as O
+        from stableanimator_b200.arch import UNetConfig
+        from stableanimator_b200.synth import synth_inputs, synth_posenet_state_dict, synth_unet_state_dict
+        self.cores = os.cpu_count() or 1
+        torch.set_num_threads(self.cores)
+        cfg = UNetConfig.full() if size == "full" else UNetConfig.tiny()
+        self.frames, self.h, self.w = frames, hw, (w or hw)
+        sd = synth_unet_state_dict(cfg)
+        psd = synth_posenet_state_dict(cfg.block_out_channels[0])
+        inp = synth_inputs(cfg, frames, self.h, self.w)
+        unet_fn = lambda x, t, e, a, pl: O.unet_forward(sd, cfg, x, t, e, a, pl)  # noqa: E731
+        pose_fn = lambda pm: O.pose_net(psd, pm)  # noqa: E731
+        self._step = lambda: SO.denoise_loop(unet_fn, pose_fn, inp["latents"], inp["image_latents"],  # noqa: E731
+                                             inp["encoder_hidden_states"], inp["added_time_ids"], inp["pose"],
+                                             num_steps=25, tile_size=frames, tile_overlap=min(4, frames - 1), steps_to_run=1)
+
+    def seconds(self) -> float:
+        t0 = time.perf_counter()
+        self._step()
+        return time.perf_counter() - t0
+
+    def to_metric(self, sec_per_cfg_step: float) -> float:
+        """frames/s of the metric's workload (512x512x16f, 25 steps) extrapolated from the sample by the reference
+        graph's algorithmic FLOPs (20.311 TFLOP per B=1 call at 64x64x16 vs 2.364 at 32x32x8)."""
+        if (self.frames, self.h, self.w) == (8, 32, 32):
+            scale = FLOPS_PER_CALL_64x64x16 / FLOPS_PER_CALL_32x32x8
+        else:   # debug shapes: tokens (the quadratic attention term is ignored)
+            scale = (16 * 64 * 64) / (self.frames * self.h * self.w)
+        return 16.0 / (sec_per_cfg_step * scale * 25)
+
+    def describe(self) -> str:
+        return (f"one CFG step (2 B=1 fp32 UNet calls + PoseNet + CFG + Euler) of the oracle port at {self.w * 8}x{self.h * 8}, "
+                f"{self.frames} frames (BASELINE configs[0]); scaled to 512x512x16f x 25 steps by the reference-graph FLOP "
+                f"ratio 20.311 / 2.364 per call")
+
+
 def cpu_reference_sample(frames: int, hw: int, cfg_name: str = "full", w: int = 0):
-    """Time ONE B=1 UNet call of the oracle port (fp32, all host cores) at the workload's shape and
-    extrapolate to the 50 calls (25 steps x 2 CFG branches) of a 16-frame denoise."""
-    from oracle import unet_oracle as O
-    from stableanimator_b200.arch import UNetConfig
-    from stableanimator_b200.synth import synth_inputs, synth_unet_state_dict
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    cfg = UNetConfig.full() if cfg_name == "full" else UNetConfig.tiny()
-    sd = synth_unet_state_dict(cfg)
-    w = w or hw
-    inp = synth_inputs(cfg, frames, hw, w)
-    sample = torch.cat([inp["latents"].expand(1, frames, 4, hw, w), inp["image_latents"][:1]], dim=2)
-    t0 = time.perf_counter()
-    O.unet_forward(sd, cfg, sample, torch.tensor(1.0), inp["encoder_hidden_states"][:1], inp["added_time_ids"][:1])
-    dt = time.perf_counter() - t0
-    return dt, cores
+    """Seconds of one CFG step of the oracle port at an arbitrary (debug) shape, and the threads used."""
+    leg = CpuCfgStep(cfg_name, frames, hw, w)
+    return leg.seconds(), leg.cores
 
 
 def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port), every bench step = one bounded
+    sample (a full CFG step at BASELINE configs[0]); exactly --warmup untimed and --steps timed samples."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    frames = 16
-    cores = os.cpu_count() or 1
-    # bounded sample: full 16-frame call when the host has enough cores, else 4 frames (scaled x4)
-    sample_frames = 16 if cores >= 32 else 4
-    times = []
-    for i in range(args.warmup + args.steps):
-        dt, cores = cpu_reference_sample(sample_frames, 64, args.size)
-        if i >= args.warmup:
-            times.append(dt)
-        if sum(times) > 150:
-            break
-    per_call = sum(times) / len(times) * (frames / sample_frames)
-    sec_per_video = per_call * 50  # 25 steps x (uncond + cond), inference_pipeline_animation.py:663-685
-    v = frames / sec_per_video
-    sample = (f"1 B=1 fp32 UNet call of the oracle port, F={sample_frames}, 64x64 latent, scaled x{frames // sample_frames} "
-              f"to F=16 and x50 calls (25 steps x 2 CFG branches)")
+    leg = CpuCfgStep(args.size) if args.size == "full" else CpuCfgStep("tiny", 4, 16)
+    for _ in range(args.warmup):
+        leg.seconds()
+    times = [leg.seconds() for _ in range(max(args.steps, 1))]
+    sec = sum(times) / len(times)
+    v = leg.to_metric(sec)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": len(times), "warmup": args.warmup, "ms_per_step": sec_per_video * 1e3,
+            "steps": len(times), "warmup": args.warmup, "ms_per_step": sec * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": {"workload": "512x512x16f, 25 Euler steps, CFG (BASELINE configs[1])"},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": leg.cores, "kind": "port", "sample": leg.describe(),
+                             "sec_per_cfg_step": sec, "frames_per_cfg_step_second": leg.frames / sec},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------- GPU eager leg
+def gpu_eager_baseline(dev, lh, lw, frames, euler_steps, size):
+    """The north star's >= 8x denominator: the reference graph in eager PyTorch on the SAME GPU in bf16 -- the
+    fp32-pinned oracle restatement with weights and activations in bfloat16 (what ``.to('cuda', torch.bfloat16)`` does to
+    the reference modules, inference_basic.py:486-503; cuDNN / cuBLAS / SDPA kernels picked by torch), driven exactly
+    like inference_pipeline_animation.py:641-699: per Euler step two B=1 UNet calls (uncond, cond), PoseNet, CFG, Euler.
+    The reference modules themselves cannot travel to the GPU box, hence kind = "port".  Timed with CUDA events:
+    one warm-up step, then the full loop."""
+    from oracle import sampler_oracle as SO
+    from oracle import unet_oracle as O
+    from stableanimator_b200.arch import UNetConfig
+    from stableanimator_b200.synth import synth_inputs, synth_posenet_state_dict, synth_unet_state_dict
+    cfg = UNetConfig.full() if size == "full" else UNetConfig.tiny()
+    bf = torch.bfloat16
+    sd = {k: v.to(dev, bf) for k, v in synth_unet_state_dict(cfg).items()}
+    psd = {k: v.to(dev, bf) for k, v in synth_posenet_state_dict(cfg.block_out_channels[0]).items()}
+    inp = {k: v.to(dev) for k, v in synth_inputs(cfg, frames, lh, lw).items()}
+    unet_fn = lambda x, t, e, a, pl: O.unet_forward(sd, cfg, x.to(bf), t.to(dev), e.to(bf), a.to(bf),  # noqa: E731
+                                                    None if pl is None else pl.to(bf)).float()
+    pose_fn = lambda pm: O.pose_net(psd, pm.to(bf))  # noqa: E731
+
+    def loop(n):
+        return SO.denoise_loop(unet_fn, pose_fn, inp["latents"], inp["image_latents"], inp["encoder_hidden_states"],
+                               inp["added_time_ids"], inp["pose"], num_steps=euler_steps, tile_size=16, tile_overlap=4,
+                               steps_to_run=n)
+    with torch.no_grad():
+        loop(1)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        loop(euler_steps)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    del sd, psd, inp
+    torch.cuda.empty_cache()
+    return ms
 
 
 # ----------------------------------------------------------------------------------------- our arm
@@ -161,48 +234,63 @@ def gemm_family_time(unet, ctx, ati, B, F, h, w, reps=5):
     the same call with the GEMM launches elided (all other kernels still run, on whatever the output
     buffers contain -- none of them has data-dependent control flow); the difference is the in-situ
     GEMM time, with the real cache state and launch overlap of the step.
-    Returns (algorithmic flops of the family, family ms, launches, full-call ms)."""
-    from stableanimator_b200 import ops
+    Returns (algorithmic flops of the family, family ms, launches, full-call ms, {family: ms})."""
+    from stableanimator_b200 import profiling
     x_in = torch.zeros((B * F, h, w, unet.cfg.in_channels), device=unet.dev, dtype=torch.bfloat16)
     t = torch.tensor(1.0, device=unet.dev)
-    orig = ops.gemm_tap
     flops = []
-
-    def elided(a0, w_, **kw):
-        rows = a0.numel() // a0.shape[-1] // (kw.get("in_stride", 1) ** 2)   # output positions
-        n = kw.get("n") or w_.shape[0]
-        flops.append(2.0 * rows * w_.shape[1] * n)
-        if kw.get("out") is not None:
-            return kw["out"]
-        n_out = n // 2 if kw.get("geglu") else n
-        return torch.empty((rows, n_out), device=a0.device,
-                           dtype=torch.float32 if kw.get("out_f32") else torch.bfloat16)
-
-    def graph_ms(fn):
-        fn()
-        torch.cuda.synchronize()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            fn()
-        g.replay()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
-            g.replay()
-        e1.record()
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / reps
-
     run = lambda: unet.forward_nhwc(x_in, t, ctx, ati, B, F, h, w)  # noqa: E731
-    full = graph_ms(run)
-    ops.gemm_tap = elided
-    try:
-        rest = graph_ms(run)
-    finally:
-        ops.gemm_tap = orig
+    res = profiling.family_times(run, ("gemm_tap", "groupnorm", "layernorm", "attn_spatial"), reps, flops)
     n_launch = len(flops) // 2  # the elided function ran twice (warm-up + capture)
-    return sum(flops) / 2, full - rest, n_launch, full
+    return sum(flops) / 2, res["gemm_tap"], n_launch, res["full_ms"], res
+
+
+def long_video_record(unet, pose_net, dev, world, rank, euler_steps, size):
+    """BASELINE configs[4] -- 576x1024 (w x h), 128 frames, tile 16 / overlap 4: 11 frame tiles x 2 CFG branches = 22
+    UNet units per Euler step spread over the ranks (strong scaling; the north star's >= 0.8 @ 8 GPUs claim).  One
+    warm-up Euler step (captures the per-unit CUDA graphs), then ONE full denoise, CUDA-event timed, max over ranks."""
+    import torch.distributed as dist
+    from stableanimator_b200 import scheduler as sch
+    from stableanimator_b200.arch import UNetConfig
+    from stableanimator_b200.sampler import AnimationSampler
+    from stableanimator_b200.synth import synth_inputs
+    cfg = UNetConfig.full() if size == "full" else UNetConfig.tiny()
+    lh, lw, frames = (128, 72, 128) if size == "full" else (16, 8, 40)
+    inp = synth_inputs(cfg, frames, lh, lw)
+    src = {k: inp[k].to(dev) for k in ("image_latents", "encoder_hidden_states", "added_time_ids", "pose")}
+    src["latents"] = inp["latents"][:, :16].contiguous().to(dev)
+    sampler = AnimationSampler(unet, pose_net, num_inference_steps=euler_steps, tile_size=16, tile_overlap=4)
+    call = lambda n: sampler(src["latents"], src["image_latents"], src["encoder_hidden_states"],  # noqa: E731
+                             src["added_time_ids"], src["pose"], steps_to_run=n)
+    call(1)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    call(euler_steps)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        tt = torch.tensor([ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = tt.item()
+    n_tiles = len(sch.tile_indices(frames, 16, 4))
+    units = 2 * n_tiles
+    rounds = -(-units // world)
+    rec = {"workload": f"{lw * 8}x{lh * 8}x{frames}f, {euler_steps} Euler steps, tile 16 / overlap 4 (BASELINE configs[4])",
+           "scaling": "strong", "n_gpus": world, "ms_per_denoise": ms, "video_frames_per_s": frames / (ms / 1e3),
+           "units_per_step": units, "partition_ceiling": units / (rounds * world),
+           "timed": "1 full denoise after a 1-step warm-up, CUDA events, max over ranks"}
+    if size == "full":
+        rec["whole_step_tflops_reference_graph_per_gpu"] = (euler_steps * units * FLOPS_PER_CALL_128x72x16 / (ms * 1e-3)
+                                                            / 1e12 / world)
+    del sampler, src
+    torch.cuda.empty_cache()
+    return rec
 
 
 def run_ours(args):
@@ -293,6 +381,11 @@ def run_ours(args):
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     d2h = out_host.numel() * out_host.element_size()
 
+    # ---- BASELINE configs[4] next to the metric's line at every N (strong scaling of the long-video sampler)
+    long_video = None
+    if args.config == 1 and args.latent == 64 and not args.no_long_video:
+        long_video = long_video_record(unet, pose_net, dev, world, rank, args.euler_steps, args.size)
+
     if rank == 0:
         sustained, burst, hbm, src = peaks()
         # weak: frames denoised per bench step by all ranks (N=1: the 16-frame video); strong: the video's frames
@@ -301,7 +394,7 @@ def run_ours(args):
         e2e = tile_frames / (e2e_ms / 1e3)
         # roofline of the dominant kernel family (tcgen05 tapped GEMM): live CUDA-event pass
         ctx = unet.prepare_context(devt["encoder_hidden_states"])
-        g_flops, g_ms, g_n, call_ms = gemm_family_time(unet, ctx, devt["added_time_ids"], 2, tile, lh, lw)
+        g_flops, g_ms, g_n, call_ms, fam = gemm_family_time(unet, ctx, devt["added_time_ids"], 2, tile, lh, lw)
         achieved = g_flops / (g_ms * 1e-3) / 1e12
         from stableanimator_b200 import scheduler as sch
         n_tiles = len(sch.tile_indices(frames, tile, 4))
@@ -339,13 +432,34 @@ def run_ours(args):
                          "whole_step_tflops_reference_graph_per_gpu": step_tflops,
                          "whole_step_frac": None if step_tflops is None else step_tflops / sustained},
         }
+        line["roofline"]["family_ms_per_unet_call_all"] = {k: v for k, v in fam.items() if k != "full_ms"}
+        if long_video is not None:
+            line["long_video"] = long_video
+        if world == 1 and args.size == "full" and (lh, lw) == (64, 64):
+            # memory-bound kernels as HBM GB/s (north star): standalone launches at the L0 shape of a B=2 call, inputs
+            # rotating over > 126 MB; plus the in-situ family times against SURVEY 8d's algorithmic bytes per call
+            from stableanimator_b200 import profiling
+            mb = profiling.memory_bound_gbs(dev, hbm_gbs=hbm)
+            for name, gb in (("groupnorm", 2 * 4.42), ("layernorm", 2 * 5.17)):   # GB per B=2 call, unfused
+                mb[f"{name}_in_situ"] = {"ms_per_unet_call": fam[name], "algorithmic_GB_per_call": gb,
+                                         "GB/s": gb / fam[name] * 1e3, "frac": gb / fam[name] * 1e3 / hbm}
+            line["roofline"]["memory_bound"] = mb
+        if world == 1 and not args.no_eager:
+            eager_ms = gpu_eager_baseline(dev, lh, lw, frames, args.euler_steps, args.size)
+            line["gpu_eager_baseline"] = {
+                "value": frames / (eager_ms / 1e3), "unit": UNIT, "ms_per_denoise": eager_ms, "dtype": "bf16",
+                "kind": "port", "what": "oracle/unet_oracle.py + oracle/sampler_oracle.py in eager PyTorch on this GPU, bf16 "
+                                        "weights and activations, two B=1 UNet calls + PoseNet per Euler step "
+                                        "(inference_pipeline_animation.py:641-699)",
+                "speedup": value / (frames / (eager_ms / 1e3)), "speedup_e2e": e2e / (frames / (eager_ms / 1e3)),
+                "ms_per_cfg_step_eager": eager_ms / args.euler_steps, "ms_per_cfg_step_ours": ms / args.euler_steps}
         if world == 1 and not args.no_cpu:
-            sample_frames = 16 if (os.cpu_count() or 1) >= 32 else 4
-            dt, cores = cpu_reference_sample(sample_frames, lh, args.size, lw)
-            sec = dt * (16 / sample_frames) * 50
-            line["cpu_baseline"] = {"value": 16 / sec, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"1 B=1 fp32 oracle UNet call, F={sample_frames}, {lh}x{lw} latent, "
-                                              f"scaled to F=16 and x50 calls"}
+            leg = CpuCfgStep(args.size) if args.size == "full" else CpuCfgStep("tiny", 4, 16)
+            leg.seconds()                                     # 1 warm-up
+            ts = sorted(leg.seconds() for _ in range(3))      # median of 3
+            line["cpu_baseline"] = {"value": leg.to_metric(ts[1]), "unit": UNIT, "cores": leg.cores, "kind": "port",
+                                    "sample": leg.describe() + "; median of 3 after 1 warm-up",
+                                    "sec_per_cfg_step": ts[1], "frames_per_cfg_step_second": leg.frames / ts[1]}
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
@@ -368,6 +482,8 @@ def main():
     ap.add_argument("--euler-steps", type=int, default=25)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-eager", action="store_true", help="skip the gpu_eager_baseline leg (N = 1)")
+    ap.add_argument("--no-long-video", action="store_true", help="skip the BASELINE configs[4] long_video sub-record")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -88,16 +88,17 @@ def denoise_loop(unet_fn: Callable, pose_fn: Optional[Callable], latents: torch.
     ts = timesteps_from_sigmas(sig)
     lat = latents.float() * init_noise_sigma(sig)
     lat = lat.repeat(1, num_frames // tile_size + 1, 1, 1, 1)[:, :num_frames]                # :597
-    g = torch.linspace(min_guidance, max_guidance, num_frames).reshape(1, num_frames, 1, 1, 1)  # :604-607
+    dev = image_latents.device   # CPU in the tests; cuda for bench.py's eager-GPU baseline leg
+    g = torch.linspace(min_guidance, max_guidance, num_frames).reshape(1, num_frames, 1, 1, 1).to(dev)  # :604-607
     indices = tile_indices(num_frames, tile_size, tile_overlap)
-    weight = tile_weights(tile_size)
+    weight = tile_weights(tile_size).to(dev)
     n = num_steps if steps_to_run is None else steps_to_run
     for i in range(n):
         sigma, sigma_next = float(sig[i]), float(sig[i + 1])
         x = scale_model_input(torch.cat([lat] * 2), sigma)                                     # :644-647
         x = torch.cat([x, image_latents.float()], dim=2)                                       # :650
         noise = torch.zeros_like(image_latents, dtype=torch.float32)
-        cnt = torch.zeros(num_frames)
+        cnt = torch.zeros(num_frames, device=dev)
         for idx in indices:                                                                    # :659
             pl = pose_fn(pose[idx].float()) if (pose_fn is not None and pose is not None) else None
             eu = unet_fn(x[:1, idx], ts[i], encoder_hidden_states[:1], added_time_ids[:1], None)

@@ -21,53 +21,7 @@ from stableanimator_b200.synth import synth_inputs, synth_unet_state_dict  # noq
 from stableanimator_b200.unet import UNetB200  # noqa: E402
 
 
-def _empty_like_out(rows, cols, dev, dtype=torch.bfloat16):
-    return torch.empty((rows, cols), device=dev, dtype=dtype)
-
-
-def elided(name):
-    if name == "gemm_tap":
-        def f(a0, w_, **kw):
-            rows = a0.numel() // a0.shape[-1] // (kw.get("in_stride", 1) ** 2)   # output positions
-            n = kw.get("n") or w_.shape[0]
-            if kw.get("out") is not None:
-                return kw["out"]
-            return _empty_like_out(rows, n // 2 if kw.get("geglu") else n, a0.device,
-                                   torch.float32 if kw.get("out_f32") else torch.bfloat16)
-        return f
-    if name == "groupnorm":
-        def f(x0, gamma, beta, eps, rps, *, x1=None, silu=True, stats_ws=None, out=None, stats_ready=False):
-            c = x0.shape[-1] + (0 if x1 is None else x1.shape[-1])
-            return out if out is not None else _empty_like_out(x0.numel() // x0.shape[-1], c, x0.device)
-        return f
-    if name == "layernorm":
-        def f(x, gamma, beta, *, addv=None, rows_per_group=1, x_out=None, out=None, eps=1e-5):
-            return out if out is not None else torch.empty_like(x)
-        return f
-    if name == "attn_spatial":
-        return lambda qkv, frames, s, heads, out=None: _empty_like_out(frames * s, heads * 64, qkv.device)
-    if name == "attn_temporal":
-        return lambda qkv, b, f, s, heads, out=None: _empty_like_out(b * f * s, heads * 64, qkv.device)
-    if name == "attn_id":
-        return lambda q, ik, iv, b, f, s, heads, stats, out=None: _empty_like_out(b * f * s, heads * 64, q.device)
-    raise KeyError(name)
-
-
-def graph_ms(fn, reps):
-    fn()
-    torch.cuda.synchronize()
-    g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g):
-        fn()
-    g.replay()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        g.replay()
-    e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / reps
+from stableanimator_b200.profiling import elided, graph_ms  # noqa: E402
 
 
 def main():
