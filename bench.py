@@ -425,10 +425,10 @@ def run_ours(args):
                          "traffic": GEMM_DRAM_BYTES_PER_LAUNCH if (args.size == "full" and (lh, lw) == (64, 64)) else None,
                          "traffic_unit": "bytes of DRAM read+write per launch (ncu, family average)",
                          "peak_source": src,
-                         "kernel": "gemm_tap_kernel (tcgen05 tapped implicit GEMM, all instantiations)",
+                         "kernel": "gemm_tap_persist_kernel + ff_fused_kernel (tcgen05 tapped implicit GEMM family, all instantiations)",
                          "launches_per_unet_call": g_n, "family_ms_per_unet_call": g_ms,
                          "unet_call_ms": call_ms, "family_share_of_call": g_ms / call_ms,
-                         "how": "CUDA-graph replay of one B=2 UNet call minus the same graph with the GEMM launches elided",
+                         "how": "CUDA-graph replay of one B=2 UNet call minus the same graph with the GEMM-family launches (sa_gemm_tap, sa_ff_fused) elided",
                          "whole_step_tflops_reference_graph_per_gpu": step_tflops,
                          "whole_step_frac": None if step_tflops is None else step_tflops / sustained},
         }

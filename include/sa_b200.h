@@ -103,6 +103,43 @@ int sa_gemm_tap(const sa_gemm_args* args, void* stream);
 int sa_gemm_pick_tile(int32_t m, int32_t n, int32_t geglu);
 
 /* ------------------------------------------------------------------------------------------
+ * Fused transformer feed-forward (one tcgen05 kernel; the [M, 4C] hidden tensor never leaves the SM):
+ *
+ *   xr  = bf16(x + addv[m / rows_per_group])                       (addv optional)
+ *   out = W2 . GEGLU(W1 . LayerNorm(xr) + b1) + b2 + xr            (GEGLU: value * gelu_erf(gate))
+ *   if blend_x: out = alpha * blend_x + (1 - alpha) * out          (AlphaBlender, unet.py:473)
+ *
+ * Replaces nn.LayerNorm -> FeedForward(GEGLU, Linear) -> residual add of BasicTransformerBlock.forward
+ * (unet.py:521-523, :553-555) and TemporalBasicTransformerBlock.forward (:892-897 + :936-940 ff_in; :916-917 +
+ * :949-953 ff; the additive vectors are the frame-position embedding :686 and the constant attn2 output :945-947),
+ * with GEGLU unet.py:859-870, FeedForward :827-857 and the time_mixer blend :693-697, for C in {64, 128, 256, 320}.
+ * w1: bf16 [8C, C], rows interleaved in 64-row blocks [value | gate] (as for sa_gemm_tap geglu), b1: fp32 [8C] in the
+ * same order; w2: bf16 [C, 4C]; b2, gamma, beta: fp32 [C]; x, blend_x, out: bf16 [M, ld*].
+ * ------------------------------------------------------------------------------------------ */
+typedef struct sa_ff_args {
+  const void* x;          /* bf16 [m, ldx]: LayerNorm input and residual */
+  int32_t ldx;
+  int64_t m;              /* rows */
+  int32_t c;              /* channels: 64, 128, 256 or 320 */
+  const float* addv;      /* fp32 [m / rows_per_group, c] added to x before everything else, or NULL */
+  int32_t rows_per_group;
+  const float* gamma;     /* LayerNorm weight / bias / eps */
+  const float* beta;
+  float eps;
+  const void* w1;
+  const float* b1;
+  const void* w2;
+  const float* b2;
+  const void* blend_x;    /* bf16 [m, ldbx] or NULL */
+  int32_t ldbx;
+  float alpha;
+  void* out;              /* bf16 [m, ldc] */
+  int32_t ldc;
+} sa_ff_args;
+
+int sa_ff_fused(const sa_ff_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Spatial self-attention, head_dim 64 (tcgen05 flash attention).
  * Replaces xformers.ops.memory_efficient_attention in AnimationAttnProcessor.__call__
  * (unet.py:1893-1905).  qkv: 16-bit [frames*S, ld], column blocks q | k | v of width C = heads*64

@@ -49,6 +49,19 @@ class GemmArgs(C.Structure):
     ]
 
 
+class FfArgs(C.Structure):
+    """Mirror of ``sa_ff_args`` (include/sa_b200.h)."""
+
+    _fields_ = [
+        ("x", C.c_void_p), ("ldx", C.c_int32), ("m", C.c_int64), ("c", C.c_int32),
+        ("addv", C.c_void_p), ("rows_per_group", C.c_int32),
+        ("gamma", C.c_void_p), ("beta", C.c_void_p), ("eps", C.c_float),
+        ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p),
+        ("blend_x", C.c_void_p), ("ldbx", C.c_int32), ("alpha", C.c_float),
+        ("out", C.c_void_p), ("ldc", C.c_int32),
+    ]
+
+
 _lib = None
 
 
@@ -77,6 +90,7 @@ _P, _I, _F, _L = C.c_void_p, C.c_int32, C.c_float, C.c_int64
 SIGNATURES: dict[str, list] = {
     "sa_gemm_tap": [C.POINTER(GemmArgs), _P],
     "sa_gemm_pick_tile": [_I, _I, _I],
+    "sa_ff_fused": [C.POINTER(FfArgs), _P],
     "sa_attn_spatial": [_P, _I, _I, _I, _I, _I, _P, _I, _P],
     "sa_attn_temporal": [_P, _I, _I, _I, _I, _I, _I, _P, _I, _P],
     "sa_attn_id": [_P, _I, _P, _P, _L, _L, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P],

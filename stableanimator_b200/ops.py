@@ -15,7 +15,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import GemmArgs, check, lib
+from ._lib import FfArgs, GemmArgs, check, lib
 
 TAPS_1 = ((0, 0, 0),)
 # 3x3 conv, pad 1: tap index = ky*3 + kx, offset (dx, dy, 0) = (kx-1, ky-1, 0)
@@ -189,6 +189,43 @@ def gemm_tap(
             raise ValueError("gn_stats must be a contiguous fp64 [rows / gn_rows_per_stat, 32, 2] tensor")
         args.gn_stats, args.gn_cpg, args.gn_rows_per_stat = gn_stats.data_ptr(), n_out // 32, int(gn_rows_per_stat)
     check(lib().sa_gemm_tap(C.byref(args), _stream()), "sa_gemm_tap")
+    return out
+
+
+FF_FUSED_CHANNELS = (64, 128, 256, 320)
+
+
+@_launcher("ff_fused")
+def ff_fused(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor,
+             w2: torch.Tensor, b2: torch.Tensor, *, addv: Optional[torch.Tensor] = None, rows_per_group: int = 1,
+             blend_x: Optional[torch.Tensor] = None, alpha: float = 0.0, eps: float = 1e-5,
+             out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``out = W2 . GEGLU(W1 . LN(x + addv) + b1) + b2 + (x + addv)`` (optionally alpha-blended with ``blend_x``) in ONE
+    kernel -- see ``sa_ff_fused`` in include/sa_b200.h.  ``w1`` / ``b1`` are GEGLU-interleaved (:func:`interleave_geglu`)."""
+    _chk_bf16(x, "x")
+    _chk_bf16(w1, "w1")
+    _chk_bf16(w2, "w2")
+    c = x.shape[-1]
+    rows = x.numel() // c
+    if c not in FF_FUSED_CHANNELS:
+        raise ValueError(f"ff_fused supports C in {FF_FUSED_CHANNELS}, got {c}")
+    if tuple(w1.shape) != (8 * c, c) or tuple(w2.shape) != (c, 4 * c) or not w1.is_contiguous() or not w2.is_contiguous():
+        raise ValueError("w1 must be contiguous [8C, C] (GEGLU-interleaved) and w2 contiguous [C, 4C]")
+    for t, nm in ((gamma, "gamma"), (beta, "beta"), (b1, "b1"), (b2, "b2"), (addv, "addv")):
+        _chk_f32(t, nm)
+    if out is None:
+        out = torch.empty((rows, c), device=x.device, dtype=torch.bfloat16)
+    a = FfArgs()
+    a.x, a.ldx, a.m, a.c = x.data_ptr(), x.stride(-2), rows, c
+    a.addv, a.rows_per_group = _ptr(addv), int(rows_per_group)
+    a.gamma, a.beta, a.eps = gamma.data_ptr(), beta.data_ptr(), float(eps)
+    a.w1, a.b1, a.w2, a.b2 = w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr()
+    if blend_x is not None:
+        _chk_bf16(blend_x, "blend_x")
+        a.blend_x, a.ldbx = blend_x.data_ptr(), blend_x.stride(-2)
+    a.alpha = float(alpha)
+    a.out, a.ldc = out.data_ptr(), out.stride(-2)
+    check(lib().sa_ff_fused(C.byref(a), _stream()), "sa_ff_fused")
     return out
 
 

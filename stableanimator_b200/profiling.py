@@ -16,6 +16,9 @@ import torch
 from . import ops
 
 FAMILIES = ("gemm_tap", "groupnorm", "layernorm", "attn_spatial", "attn_temporal", "attn_id")
+# launchers elided together under one family name: the tensor-core GEMM family is the tapped GEMM plus the fused
+# feed-forward (two chained GEMMs in one kernel)
+MEMBERS = {"gemm_tap": ("gemm_tap", "ff_fused")}
 
 
 def _empty(rows, cols, dev, dtype=torch.bfloat16):
@@ -34,6 +37,14 @@ def elided(name: str, on_call: Callable = None):
                 return kw["out"]
             return _empty(rows, n // 2 if kw.get("geglu") else n, a0.device,
                           torch.float32 if kw.get("out_f32") else torch.bfloat16)
+        return f
+    if name == "ff_fused":
+        def f(x, gamma, beta, w1, b1, w2, b2, **kw):
+            c = x.shape[-1]
+            rows = x.numel() // c
+            if on_call is not None:
+                on_call(2.0 * rows * c * 8 * c + 2.0 * rows * 4 * c * c)
+            return kw["out"] if kw.get("out") is not None else _empty(rows, c, x.device)
         return f
     if name == "groupnorm":
         def f(x0, gamma, beta, eps, rps, *, x1=None, silu=True, stats_ws=None, out=None, stats_ready=False):
@@ -75,12 +86,15 @@ def family_times(run: Callable, families: Iterable[str] = FAMILIES, reps: int = 
     the algorithmic flops of every elided GEMM launch (two passes: warm-up + capture)."""
     res = {"full_ms": graph_ms(run, reps)}
     for fam in families:
-        orig = getattr(ops, fam)
-        setattr(ops, fam, elided(fam, flops.append if (fam == "gemm_tap" and flops is not None) else None))
+        members = MEMBERS.get(fam, (fam,))
+        origs = {m: getattr(ops, m) for m in members}
+        for m in members:
+            setattr(ops, m, elided(m, flops.append if (fam == "gemm_tap" and flops is not None) else None))
         try:
             res[fam] = res["full_ms"] - graph_ms(run, reps)
         finally:
-            setattr(ops, fam, orig)
+            for m in members:
+                setattr(ops, m, origs[m])
     return res
 
 

@@ -62,6 +62,10 @@ class UNetB200:
         self.fuse_gn_stats = os.environ.get("SA_GN_FUSE", "1") == "1"
         # zero-context (unconditional CFG branch) shortcut of the ID cross-attention; SA_SKIP_ZERO_CTX=0 for A/B
         self.skip_zero_context = os.environ.get("SA_SKIP_ZERO_CTX", "1") != "0"
+        # LayerNorm + GEGLU feed-forward + residual (+ blend) as ONE kernel where the channel count allows it (C <= 320: the
+        # 64x64 / 128x72 level, where the unfused chain is bound by the GEGLU epilogue and the [M, 4C] hidden tensor's HBM
+        # round trip); SA_FF_FUSED=0: LayerNorm -> GEGLU GEMM -> out-projection GEMM, for A/B
+        self.fuse_ff = os.environ.get("SA_FF_FUSED", "1") != "0"
         # stride-2 Downsample2D through TMA element strides (SA_STRIDED_DOWN=0: im2col_s2 + GEMM, for A/B)
         self.strided_downsample = os.environ.get("SA_STRIDED_DOWN", "1") != "0"
         # Upsample2D as four phase convolutions (4/9 of the MACs; SA_UP_PHASES=0: upsample2x + 3x3 conv, for A/B)
@@ -297,8 +301,9 @@ class UNetB200:
         mz, bn = zb * F * S, B - zb
         off = self.ctx_off[t.name]
         nt = self.cfg.num_tokens
+        ff_fused = self.fuse_ff and c in ops.FF_FUSED_CHANNELS
         y2 = torch.empty_like(y1)
-        a = torch.empty_like(y1)
+        a = None if ff_fused else torch.empty_like(y1)
         if bn > 0:
             an = ops.layernorm(y1[mz:], w[f"{b}.norm2.g"], w[f"{b}.norm2.b"])
             q = ops.gemm_tap(an, w[f"{b}.attn2.to_q.w"])
@@ -312,30 +317,50 @@ class UNetB200:
                                  w[f"{b}.attn2.to_out.0.b"], bn, F, S, c, rs, rb)
             ops.gemm_tap(ip, w[f"{b}.attn2.to_out.0.w"], row_scale=rs, row_bias=rb, rows_per_group=S,
                          residual=y1[mz:], out=y2[mz:])
-            ops.layernorm(y2[mz:], w[f"{b}.norm3.g"], w[f"{b}.norm3.b"], out=a[mz:])
-        if zb > 0:  # y2 = y1 + to_out.bias, a = norm3(y2) in one pass
-            ops.layernorm(y1[:mz], w[f"{b}.norm3.g"], w[f"{b}.norm3.b"], addv=w[f"{b}.attn2.to_out.0.b"].reshape(1, c),
-                          rows_per_group=mz, x_out=y2[:mz], out=a[:mz])
-        g = ops.gemm_tap(a, w[f"{b}.ff.w1"], bias=w[f"{b}.ff.b1"], geglu=True)
-        y3 = ops.gemm_tap(g, w[f"{b}.ff.w2"], bias=w[f"{b}.ff.b2"], residual=y2)
+            if not ff_fused:
+                ops.layernorm(y2[mz:], w[f"{b}.norm3.g"], w[f"{b}.norm3.b"], out=a[mz:])
+        if ff_fused:
+            # norm3 -> ff -> + residual in one kernel per row range; on the zero-context rows the attn2 output (the
+            # constant to_out bias) enters as the additive vector, so y2 is never materialised there
+            y3 = torch.empty_like(y1)
+            ffw = (w[f"{b}.norm3.g"], w[f"{b}.norm3.b"], w[f"{b}.ff.w1"], w[f"{b}.ff.b1"], w[f"{b}.ff.w2"], w[f"{b}.ff.b2"])
+            if zb > 0:
+                ops.ff_fused(y1[:mz], *ffw, addv=w[f"{b}.attn2.to_out.0.b"].reshape(1, c), rows_per_group=mz, out=y3[:mz])
+            if bn > 0:
+                ops.ff_fused(y2[mz:], *ffw, out=y3[mz:])
+        else:
+            if zb > 0:  # y2 = y1 + to_out.bias, a = norm3(y2) in one pass
+                ops.layernorm(y1[:mz], w[f"{b}.norm3.g"], w[f"{b}.norm3.b"], addv=w[f"{b}.attn2.to_out.0.b"].reshape(1, c),
+                              rows_per_group=mz, x_out=y2[:mz], out=a[:mz])
+            g = ops.gemm_tap(a, w[f"{b}.ff.w1"], bias=w[f"{b}.ff.b1"], geglu=True)
+            y3 = ops.gemm_tap(g, w[f"{b}.ff.w2"], bias=w[f"{b}.ff.b2"], residual=y2)
         # --- TemporalBasicTransformerBlock (unet.py:919-958) on hidden + frame-position embedding (:686)
-        z0 = torch.empty_like(y3)
-        a = ops.layernorm(y3, w[f"{tb}.norm_in.g"], w[f"{tb}.norm_in.b"], addv=self._pos_embed(t, B, F),
-                          rows_per_group=S, x_out=z0)
-        g = ops.gemm_tap(a, w[f"{tb}.ff_in.w1"], bias=w[f"{tb}.ff_in.b1"], geglu=True)
-        z1 = ops.gemm_tap(g, w[f"{tb}.ff_in.w2"], bias=w[f"{tb}.ff_in.b2"], residual=z0)
+        if ff_fused:
+            z1 = ops.ff_fused(y3, w[f"{tb}.norm_in.g"], w[f"{tb}.norm_in.b"], w[f"{tb}.ff_in.w1"], w[f"{tb}.ff_in.b1"],
+                              w[f"{tb}.ff_in.w2"], w[f"{tb}.ff_in.b2"], addv=self._pos_embed(t, B, F), rows_per_group=S)
+        else:
+            z0 = torch.empty_like(y3)
+            a = ops.layernorm(y3, w[f"{tb}.norm_in.g"], w[f"{tb}.norm_in.b"], addv=self._pos_embed(t, B, F),
+                              rows_per_group=S, x_out=z0)
+            g = ops.gemm_tap(a, w[f"{tb}.ff_in.w1"], bias=w[f"{tb}.ff_in.b1"], geglu=True)
+            z1 = ops.gemm_tap(g, w[f"{tb}.ff_in.w2"], bias=w[f"{tb}.ff_in.b2"], residual=z0)
         a = ops.layernorm(z1, w[f"{tb}.norm1.g"], w[f"{tb}.norm1.b"])
         qkv = ops.gemm_tap(a, w[f"{tb}.attn1.qkv"])
         o = ops.attn_temporal(qkv, B, F, S, heads)
         z2 = ops.gemm_tap(o, w[f"{tb}.attn1.to_out.0.w"], bias=w[f"{tb}.attn1.to_out.0.b"], residual=z1)
         # attn2 vs the single first-frame CLIP token == constant vector per batch element (:945-947)
-        z3 = torch.empty_like(z2)
-        a = ops.layernorm(z2, w[f"{tb}.norm3.g"], w[f"{tb}.norm3.b"], addv=ctx.tconst[t.name],
-                          rows_per_group=F * S, x_out=z3)
-        g = ops.gemm_tap(a, w[f"{tb}.ff.w1"], bias=w[f"{tb}.ff.b1"], geglu=True)
-        # ff out + residual, then time_mixer: alpha * spatial(y3) + (1 - alpha) * temporal  (:693-697)
-        z4 = ops.gemm_tap(g, w[f"{tb}.ff.w2"], bias=w[f"{tb}.ff.b2"], residual=z3, blend_x=y3,
-                          alpha=w[f"{t.name}.alpha"])
+        if ff_fused:
+            z4 = ops.ff_fused(z2, w[f"{tb}.norm3.g"], w[f"{tb}.norm3.b"], w[f"{tb}.ff.w1"], w[f"{tb}.ff.b1"], w[f"{tb}.ff.w2"],
+                              w[f"{tb}.ff.b2"], addv=ctx.tconst[t.name], rows_per_group=F * S, blend_x=y3,
+                              alpha=w[f"{t.name}.alpha"])
+        else:
+            z3 = torch.empty_like(z2)
+            a = ops.layernorm(z2, w[f"{tb}.norm3.g"], w[f"{tb}.norm3.b"], addv=ctx.tconst[t.name],
+                              rows_per_group=F * S, x_out=z3)
+            g = ops.gemm_tap(a, w[f"{tb}.ff.w1"], bias=w[f"{tb}.ff.b1"], geglu=True)
+            # ff out + residual, then time_mixer: alpha * spatial(y3) + (1 - alpha) * temporal  (:693-697)
+            z4 = ops.gemm_tap(g, w[f"{tb}.ff.w2"], bias=w[f"{tb}.ff.b2"], residual=z3, blend_x=y3,
+                              alpha=w[f"{t.name}.alpha"])
         return ops.gemm_tap(z4, w[f"{t.name}.proj_out.w"], bias=w[f"{t.name}.proj_out.b"], residual=x)
 
     def _frame_stats(self, n: int) -> Optional[torch.Tensor]:

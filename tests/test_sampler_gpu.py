@@ -97,21 +97,28 @@ def test_bench_gemm_flop_accounting_matches_the_launches():
     cfg, inp, unet, pose, _, _ = setup(4, 16, 16, 4)
     ctx = unet.prepare_context(inp["encoder_hidden_states"].cuda())
     ati = inp["added_time_ids"].cuda()
-    flops, g_ms, n_launch, full_ms = bench.gemm_family_time(unet, ctx, ati, 2, 4, 16, 16, reps=2)
+    flops, g_ms, n_launch, full_ms, fam = bench.gemm_family_time(unet, ctx, ati, 2, 4, 16, 16, reps=2)
     true = []
-    orig = ops.gemm_tap
+    orig, orig_ff = ops.gemm_tap, ops.ff_fused
 
     def counting(a0, w_, **kw):
         out = orig(a0, w_, **kw)
         true.append(2.0 * (out.numel() // out.shape[-1]) * w_.shape[1] * (kw.get("n") or w_.shape[0]))
         return out
 
-    ops.gemm_tap = counting
+    def counting_ff(x, gamma, beta, w1, b1, w2, b2, **kw):   # the fused feed-forward = its two GEMMs
+        out = orig_ff(x, gamma, beta, w1, b1, w2, b2, **kw)
+        rows = out.numel() // out.shape[-1]
+        true.append(2.0 * rows * w1.shape[1] * w1.shape[0] + 2.0 * rows * w2.shape[1] * w2.shape[0])
+        return out
+
+    ops.gemm_tap, ops.ff_fused = counting, counting_ff
     try:
         x_in = torch.zeros((2 * 4, 16, 16, cfg.in_channels), device="cuda", dtype=torch.bfloat16)
         unet.forward_nhwc(x_in, torch.tensor(1.0, device="cuda"), ctx, ati, 2, 4, 16, 16)
     finally:
-        ops.gemm_tap = orig
+        ops.gemm_tap, ops.ff_fused = orig, orig_ff
+    assert set(fam) >= {"full_ms", "gemm_tap", "groupnorm", "layernorm", "attn_spatial"}
     assert n_launch == len(true)
     assert abs(flops - sum(true)) <= 1e-9 * sum(true), (flops, sum(true))
     assert g_ms > 0 and full_ms > g_ms

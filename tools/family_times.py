@@ -21,7 +21,7 @@ from stableanimator_b200.synth import synth_inputs, synth_unet_state_dict  # noq
 from stableanimator_b200.unet import UNetB200  # noqa: E402
 
 
-from stableanimator_b200.profiling import elided, graph_ms  # noqa: E402
+from stableanimator_b200.profiling import MEMBERS, elided, graph_ms  # noqa: E402
 
 
 def main():
@@ -49,18 +49,21 @@ def main():
     print(f"UNet call B={B} F={F} {h}x{w}: {full:.3f} ms (CUDA graph replay)")
     tot = 0.0
     for fam in ("gemm_tap", "groupnorm", "layernorm", "attn_spatial", "attn_temporal", "attn_id"):
-        orig = getattr(ops, fam)
-        setattr(ops, fam, elided(fam))
+        members = MEMBERS.get(fam, (fam,))
+        origs_m = {m: getattr(ops, m) for m in members}
+        for m in members:
+            setattr(ops, m, elided(m))
         try:
             rest = graph_ms(run, a.reps)
         finally:
-            setattr(ops, fam, orig)
+            for m in members:
+                setattr(ops, m, origs_m[m])
         res[fam] = full - rest
         tot += full - rest
         print(f"  {fam:16s} {full - rest:8.3f} ms  {100 * (full - rest) / full:5.1f}%")
     print(f"  {'(other)':16s} {full - tot:8.3f} ms  {100 * (full - tot) / full:5.1f}%")
     # every family elided at once: what is left is the small kernels outside the families plus launch gaps
-    fams = ("gemm_tap", "groupnorm", "layernorm", "attn_spatial", "attn_temporal", "attn_id")
+    fams = ("gemm_tap", "ff_fused", "groupnorm", "layernorm", "attn_spatial", "attn_temporal", "attn_id")
     origs = {f: getattr(ops, f) for f in fams}
     for f in fams:
         setattr(ops, f, elided(f))
