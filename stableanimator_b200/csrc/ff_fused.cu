@@ -40,7 +40,7 @@ constexpr int FF_ST = 5;                   // weight ring stages
 constexpr int FF_STAGE_BYTES = 20 * 1024;  // W1 stage: [128 rows x 64 k] = 16 KB; W2 stage: [C/2 rows x 64 k] <= 20 KB
 constexpr int FF_A_CHUNK = 128 * 128;      // [128 rows][64 ch] bf16
 constexpr int FF_P_BYTES = 128 * 128;      // [128 rows][64 hidden] bf16
-constexpr int FF_EW = 8;                   // epilogue warps
+constexpr int FF_EW = 16;                  // epilogue warps: 4 per TMEM lane quadrant = 2 chunk sets x 2 column halves
 
 struct FfParams {
   int M, C;
@@ -239,21 +239,22 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     // ------------------------------------------------------------------ epilogue warps
     const int ew = warp - 2;
     const int quad = warp & 3;
-    const int half = ew >> 2;
+    const int half = (ew >> 2) & 1;   // chunk set: hidden chunks half, half + 2, ...
+    const int ch = ew >> 3;           // column half of a chunk: hidden columns 32 ch .. 32 ch + 31
     const int r = quad * 32 + lane;   // tile row == TMEM lane
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-    uint8_t* stage_slot = sP + FF_P_BYTES + ew * 2048;   // P[1] region doubles as the TMA-store staging
+    uint8_t* stage_slot = sP + ew * 2048;   // both P tiles double as the TMA-store staging of the final epilogue
     const int sw64 = (lane >> 1) & 3;
     uint32_t ci = 0;
     int ti = 0;
     for (int tp = pair; tp < pair_tiles; tp += n_pairs, ++ti) {
       const int m0 = (2 * tp + rank) * 128;
-      // ---- LayerNorm of the activation tile, in place.  Two threads per row inside one warp: warp ew owns rows
-      // 16 ew .. 16 ew + 15; thread (row, hh) owns the 16-byte units 4 hh .. 4 hh + 3 of every 64-channel chunk
-      // (conflict-free under the 128-byte swizzle); the halves meet with one shuffle.
+      // ---- LayerNorm of the activation tile, in place.  Four threads per row inside one warp: warp ew owns rows
+      // 8 ew .. 8 ew + 7; thread (row, hh) owns the 16-byte units 2 hh, 2 hh + 1 of every 64-channel chunk
+      // (conflict-free under the 128-byte swizzle); the quarters meet with two shuffles.
       mbar_wait(a_full, ti & 1);
       {
-        const int lr = ew * 16 + (lane >> 1), hh = lane & 1;
+        const int lr = ew * 8 + (lane >> 2), hh = lane & 3;
         const long long grow = static_cast<long long>(m0) + lr;
         const bool in = grow < p.M;
         const float* av = (p.addv && in) ? p.addv + (grow / p.rows_per_group) * C : nullptr;
@@ -262,8 +263,8 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 #pragma unroll
         for (int kc = 0; kc < KC; ++kc)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int u = 4 * hh + j;
+          for (int j = 0; j < 2; ++j) {
+            const int u = 2 * hh + j;
             uint8_t* q = rowp + kc * FF_A_CHUNK + ((u ^ (lr & 7)) << 4);
             uint4 w = *reinterpret_cast<const uint4*>(q);
             uint32_t ww[4] = {w.x, w.y, w.z, w.w};
@@ -285,13 +286,14 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             }
           }
         sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
         const float mean = sum / static_cast<float>(C);
         float var = 0.f;
 #pragma unroll
         for (int kc = 0; kc < KC; ++kc)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int u = 4 * hh + j;
+          for (int j = 0; j < 2; ++j) {
+            const int u = 2 * hh + j;
             const uint4 w = *reinterpret_cast<const uint4*>(rowp + kc * FF_A_CHUNK + ((u ^ (lr & 7)) << 4));
             const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
@@ -302,20 +304,21 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             }
           }
         var += __shfl_xor_sync(0xffffffffu, var, 1);
+        var += __shfl_xor_sync(0xffffffffu, var, 2);
         const float rstd = rsqrtf(var / static_cast<float>(C) + p.eps);
 #pragma unroll
         for (int kc = 0; kc < KC; ++kc)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int u = 4 * hh + j;
+          for (int j = 0; j < 2; ++j) {
+            const int u = 2 * hh + j;
             uint8_t* q = rowp + kc * FF_A_CHUNK + ((u ^ (lr & 7)) << 4);
             const uint4 w = *reinterpret_cast<const uint4*>(q);
             const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-            const int ch = kc * 64 + u * 8;
-            const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + ch));
-            const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + ch + 4));
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta + ch));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.beta + ch + 4));
+            const int chn = kc * 64 + u * 8;
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + chn));
+            const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + chn + 4));
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta + chn));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.beta + chn + 4));
             const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
             const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
             uint32_t o[4];
@@ -338,19 +341,19 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         const uint32_t c = ci + i;       // c & 1 == half (NH is even)
         mbar_wait(&s_full[half], (c >> 1) & 1);
         tc_fence_after();
-        uint32_t u[64], g[64];
-        tmem_ld_32x64(lane_addr, u);          // 64 value columns
-        tmem_ld_32x64(lane_addr + 64, g);     // 64 gate columns
+        uint32_t u[32], g[32];
+        tmem_ld_32x32(lane_addr + 32 * ch, u);          // this warp's 32 value columns
+        tmem_ld_32x32(lane_addr + 64 + 32 * ch, g);     // and 32 gate columns
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(&s_free[half]);   // the tensor core may start S(i+1)
         // P buffer free?  (O(i-2) has read it; the first chunk of a tile reuses the buffer of the previous tile)
         if (c >= 2) mbar_wait(&p_free[half], ((c >> 1) & 1) ^ 1);
         uint8_t* prow = sP + half * FF_P_BYTES + r * 128;
-        const float4* bv = reinterpret_cast<const float4*>(sB1 + i * 128);
-        const float4* bg = reinterpret_cast<const float4*>(sB1 + i * 128 + 64);
+        const float4* bv = reinterpret_cast<const float4*>(sB1 + i * 128 + 32 * ch);
+        const float4* bg = reinterpret_cast<const float4*>(sB1 + i * 128 + 64 + 32 * ch);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {   // 8 hidden columns = one 16-byte unit of the P row
+        for (int j = 0; j < 4; ++j) {   // 8 hidden columns = one 16-byte unit of the P row
           const float4 a0 = bv[2 * j], a1 = bv[2 * j + 1], b0 = bg[2 * j], b1 = bg[2 * j + 1];
           const uint64_t g0 = add2(pack2u(g[8 * j], g[8 * j + 1]), pack2(b0.x, b0.y));
           const uint64_t g1 = add2(pack2u(g[8 * j + 2], g[8 * j + 3]), pack2(b0.z, b0.w));
@@ -360,7 +363,7 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           const uint64_t v1 = mul2(add2(pack2u(u[8 * j + 2], u[8 * j + 3]), pack2(a0.z, a0.w)), gelu2(g1));
           const uint64_t v2 = mul2(add2(pack2u(u[8 * j + 4], u[8 * j + 5]), pack2(a1.x, a1.y)), gelu2(g2));
           const uint64_t v3 = mul2(add2(pack2u(u[8 * j + 6], u[8 * j + 7]), pack2(a1.z, a1.w)), gelu2(g3));
-          *reinterpret_cast<uint4*>(prow + ((j ^ (r & 7)) << 4)) =
+          *reinterpret_cast<uint4*>(prow + (((4 * ch + j) ^ (r & 7)) << 4)) =
               make_uint4(pack_bf16x2_f2(v0), pack_bf16x2_f2(v1), pack_bf16x2_f2(v2), pack_bf16x2_f2(v3));
         }
         fence_proxy_async();
@@ -371,17 +374,22 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       // ---- final epilogue: O + b2 + residual (+ blend) -> bf16 -> TMA store
       mbar_wait(o_full, ti & 1);
       tc_fence_after();
-      // staging lives in P[1]: its last reader, O(NH-1) (NH even -> buffer 1), completed with o_full
+      // staging lives in the two P tiles: their last readers, O(NH-2) and O(NH-1), completed with o_full; the next tile
+      // writes them only after S(0) of that tile, which waits for every epilogue thread's a_ready arrival
       const long long grow = static_cast<long long>(m0) + r;
       const bool in = grow < p.M;
       const long long grow_c = in ? grow : 0;
       const float* av = p.addv ? p.addv + (grow_c / p.rows_per_group) * C : nullptr;
       const uint64_t al2 = pack2(p.alpha, p.alpha), be2 = pack2(1.0f - p.alpha, 1.0f - p.alpha);
-      for (int oc = half; oc < OCH; oc += 2) {
+      if ((ew >> 2) >= OCH) {   // narrow tiles: this warp has no output chunk, the accumulator is not its business
+        tc_fence_before();
+        mbar_arrive(o_free);
+      }
+      for (int oc = ew >> 2; oc < OCH; oc += 4) {
         uint32_t o[32];
         tmem_ld_32x32(lane_addr + O_COL + oc * 32, o);
         tmem_ld_wait();
-        if (oc + 2 >= OCH) {   // last O chunk of this warp: release the accumulator
+        if (oc + 4 >= OCH) {   // last O chunk of this warp: release the accumulator
           tc_fence_before();
           mbar_arrive(o_free);
         }
@@ -439,7 +447,7 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           tma_store_commit();
         }
       }
-      if (lane == 0) tma_store_wait_read<0>();   // P[1] is written again by chunk 1 of the next tile
+      if (lane == 0) tma_store_wait_read<0>();   // the P tiles are written again by the first chunks of the next tile
       __syncwarp();
     }
     if (lane == 0) tma_store_wait_all();
