@@ -311,10 +311,10 @@ template <bool SLIM> struct EpiSlots { static constexpr int RO = SLIM ? 2 : 3, X
 // tile i, and cannot release tile i+1 before it is done with tile i), so three sets never alias.
 constexpr int GN_SETS = 3;
 
-template <int BN, int STAGES, int EW, bool SLIM = false>
+template <int BN, int STAGES, int EW, bool SLIM = false, bool PAIR = false>
 struct Gemm2Smem {
   static constexpr int EPI_WARP_BYTES = (EpiSlots<SLIM>::RO + EpiSlots<SLIM>::X) * EPI_TILE_BYTES;
-  static constexpr int STAGE_BYTES = 128 * 128 + BN * 128;
+  static constexpr int STAGE_BYTES = 128 * 128 + (PAIR ? BN / 2 : BN) * 128;   // PAIR: each CTA holds half of the weight tile
   static constexpr int EPI_OFF = STAGES * STAGE_BYTES;
   static constexpr int BAR_OFF = EPI_OFF + EW * EPI_WARP_BYTES;
   static constexpr int NBARS = 2 * STAGES + 4 + EW * (EpiSlots<SLIM>::RO + EpiSlots<SLIM>::X);
@@ -330,14 +330,22 @@ struct Gemm2Smem {
 // PLAIN: the epilogue is bias (+ GEGLU) only -- no row scale / row bias / output scale / residual / blend /
 // fp16 block.  The short-K GEMMs are bound by the sub-partition issue port, so the instantiation without the
 // per-chunk feature tests and the staging-slot machinery is worth having for the launches that need nothing else.
-template <int BN, int STAGES, bool GEGLU, int EW, bool PLAIN>
+// PAIR: CTA pairs (cluster of two, tcgen05 cta_group::2).  The two CTAs take neighbouring row tiles of the same column
+// tile and run as ONE 256-row MMA issued by the pair's leader; the weight operand of such an MMA is split between the two
+// CTAs' shared memories (BN / 2 rows each), so a CTA streams half of the weight bytes from L2 (the long-K convolutions
+// re-read the weights once per row tile: 1024x at the 64x64 level, L2 throughput 69 % of peak) and a stage shrinks from
+// 16 + BN / 8 KB to 16 + BN / 16 KB -- two more pipeline stages in the same shared memory.  Protocol: each CTA's producer
+// loads its A box and its half of the W box into its own ring slot with the bytes completing on the LEADER's full
+// barrier; the leader's commits (stage free, accumulator full) are multicast to both CTAs; the epilogue warps of both
+// CTAs release the accumulator on the leader's barrier.  Everything behind the accumulator is per CTA and unchanged.
+template <int BN, int STAGES, bool GEGLU, int EW, bool PLAIN, bool PAIR = false>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                         const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
                         const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmBld,
                         const GemmKParams p) {
   constexpr bool SLIM = GEGLU || PLAIN;   // neither ever carries a residual / blend operand
-  using L = Gemm2Smem<BN, STAGES, EW, SLIM>;
+  using L = Gemm2Smem<BN, STAGES, EW, SLIM, PAIR>;
   constexpr int EPI_RO_SLOTS = EpiSlots<SLIM>::RO, EPI_X_SLOTS = EpiSlots<SLIM>::X;
   constexpr int EPI_WARP_BYTES = L::EPI_WARP_BYTES;
   constexpr int CSTRIDE = EW / 4;  // chunk stride of one epilogue warp
@@ -361,6 +369,11 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
   const int KB = p.ntaps * p.kcpt;
   const int out_cols_tile = GEGLU ? BN / 2 : BN;
   const int CPT = out_cols_tile / EPI_CHUNK;  // chunks per tile
+  // tile walk: a "work item" is one output tile (PAIR: one pair of row-neighbouring tiles); items first, first + stride, ...
+  const int rank = PAIR ? static_cast<int>(cluster_ctarank()) : 0;
+  const int item_first = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int item_stride = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int item_count = p.total_tiles;   // PAIR: number of tile pairs
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmA0);
@@ -373,12 +386,15 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], EW * 32);
+      mbar_init(&acc_empty[i], EW * 32 * (PAIR ? 2 : 1));   // PAIR: the epilogue threads of both CTAs, on the leader
     }
     for (int i = 0; i < EW * (EPI_RO_SLOTS + EPI_X_SLOTS); ++i) mbar_init(&epi_bar[i], 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<TCOLS>(tmem_slot);
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_alloc_2cta<TCOLS>(tmem_slot);
+    else tmem_alloc<TCOLS>(tmem_slot);
+  }
   if constexpr (!SLIM) {
     if (p.gn_stats) {
       for (int i = threadIdx.x; i < GN_SETS * 64; i += blockDim.x) gn_acc[i] = 0.0;
@@ -387,12 +403,14 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync();   // the partner's barriers exist before anything is signalled on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   auto tile_origin = [&](int tile, int& n0, int& q1, int& q2, int& q3) {
     uint32_t mt, nt, a, b, c;
     p.fd_ntn.divmod(static_cast<uint32_t>(tile), mt, nt);
+    if constexpr (PAIR) mt = 2 * mt + rank;   // a row tile past the last one is a phantom: all-OOB loads and stores
     p.fd_t1.divmod(mt, a, b);   // b = mt % t1
     p.fd_t2.divmod(a, c, a);    // a = (mt / t1) % t2, c = mt / (t1*t2)
     n0 = static_cast<int>(nt) * BN;
@@ -405,21 +423,33 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
       int it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      constexpr int B_ROWS = PAIR ? BN / 2 : BN;
+      for (int tile = item_first; tile < item_count; tile += item_stride) {
         int n0, q1, q2, q3;
         tile_origin(tile, n0, q1, q2, q3);
         int tap = 0, ch = 0;
         for (int kb = 0; kb < KB; ++kb, ++it) {
           const int s = it % STAGES;
           mbar_wait_relaxed(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
-          mbar_expect_tx(&full_bar[s], STAGE_BYTES);
           uint8_t* sa_ = smem + s * STAGE_BYTES;
           const int o1 = p.tap_off[tap * 3 + 0], o2 = p.tap_off[tap * 3 + 1], o3 = p.tap_off[tap * 3 + 2];
-          if (ch < p.kc0)
-            tma_load_4d(sa_, &tmA0, &full_bar[s], ch * 64, q1 * p.cs + o1, q2 * p.cs + o2, q3 + o3);
-          else
-            tma_load_4d(sa_, &tmA1, &full_bar[s], (ch - p.kc0) * 64, q1 * p.cs + o1, q2 * p.cs + o2, q3 + o3);
-          tma_load_2d(sa_ + A_BYTES, &tmB, &full_bar[s], kb * 64, n0);
+          if constexpr (PAIR) {
+            // both CTAs' boxes complete on the leader's barrier (it expects the bytes of the whole pair)
+            if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
+            const uint32_t fb = mapa_u32(&full_bar[s], 0);
+            if (ch < p.kc0)
+              tma_load_4d_2cta(sa_, &tmA0, fb, ch * 64, q1 * p.cs + o1, q2 * p.cs + o2, q3 + o3);
+            else
+              tma_load_4d_2cta(sa_, &tmA1, fb, (ch - p.kc0) * 64, q1 * p.cs + o1, q2 * p.cs + o2, q3 + o3);
+            tma_load_2d_2cta(sa_ + A_BYTES, &tmB, fb, kb * 64, n0 + rank * B_ROWS);
+          } else {
+            mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+            if (ch < p.kc0)
+              tma_load_4d(sa_, &tmA0, &full_bar[s], ch * 64, q1 * p.cs + o1, q2 * p.cs + o2, q3 + o3);
+            else
+              tma_load_4d(sa_, &tmA1, &full_bar[s], (ch - p.kc0) * 64, q1 * p.cs + o1, q2 * p.cs + o2, q3 + o3);
+            tma_load_2d(sa_ + A_BYTES, &tmB, &full_bar[s], kb * 64, n0);
+          }
           if (++ch == p.kcpt) {
             ch = 0;
             ++tap;
@@ -429,27 +459,37 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+    // ------------------------------------------------------------------ MMA issuer (PAIR: the leader CTA only)
+    if (rank == 0 && elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 256 : 128, BN, 0, 0);
       int it = 0, ti = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
+      for (int tile = item_first; tile < item_count; tile += item_stride, ++ti) {
         const int ab = ti & 1;
-        mbar_wait(&acc_empty[ab], ((ti >> 1) & 1) ^ 1);  // epilogue drained this accumulator
+        // epilogue drained this accumulator (PAIR: in both CTAs)
+        if constexpr (PAIR) mbar_wait_cluster(&acc_empty[ab], ((ti >> 1) & 1) ^ 1);
+        else mbar_wait(&acc_empty[ab], ((ti >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t acc = tmem_base + ab * ACC_STRIDE;
         for (int kb = 0; kb < KB; ++kb, ++it) {
           const int s = it % STAGES;
-          mbar_wait(&full_bar[s], (it / STAGES) & 1);
+          if constexpr (PAIR) mbar_wait_cluster(&full_bar[s], (it / STAGES) & 1);
+          else mbar_wait(&full_bar[s], (it / STAGES) & 1);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
           const uint64_t da = umma_desc_sw128(a_addr);
           const uint64_t db = umma_desc_sw128(a_addr + A_BYTES);
+          if constexpr (PAIR) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16(acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit(&empty_bar[s]);
+            for (int k = 0; k < 4; ++k) umma_f16_2cta(acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_2cta(&empty_bar[s], 3);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16(acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit(&empty_bar[s]);
+          }
         }
-        umma_commit(&acc_full[ab]);
+        if constexpr (PAIR) umma_commit_2cta(&acc_full[ab], 3);
+        else umma_commit(&acc_full[ab]);
       }
     }
     __syncwarp();
@@ -466,8 +506,12 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
     const int w1 = r0 % p.b1, w2 = (r0 / p.b1) % p.b2, w3 = r0 / (p.b1 * p.b2);
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     const float alpha = p.alpha, beta = 1.0f - p.alpha, gs = p.out_scale;
-    const int my_tiles = (p.total_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
-                         static_cast<int>(gridDim.x);
+    const int my_tiles = (item_count - item_first + item_stride - 1) / item_stride;
+    const uint32_t acc_empty_l0 = PAIR ? mapa_u32(&acc_empty[0], 0) : 0u, acc_empty_l1 = PAIR ? mapa_u32(&acc_empty[1], 0) : 0u;
+    auto release_acc = [&](int ab) {   // this thread has read its part of accumulator ab
+      if constexpr (PAIR) mbar_arrive_cluster(ab ? acc_empty_l1 : acc_empty_l0);
+      else mbar_arrive(&acc_empty[ab]);
+    };
     const int cpw = (CPT - half + CSTRIDE - 1) / CSTRIDE;  // chunks of a tile handled by this warp
     const int total_chunks = my_tiles * cpw;
     uint8_t* wbase = smem + L::EPI_OFF + ew * EPI_WARP_BYTES;
@@ -481,7 +525,7 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
 
     // lane 0 prepares the staging slots of this warp's chunks strictly in order (chunk 0, 1, 2, ...),
     // two chunks ahead of their use: TMA-load the residual / blend sub-boxes, or just mark the slot free
-    int nx_g = 0, nx_tile = blockIdx.x, nx_c = half;
+    int nx_g = 0, nx_tile = item_first, nx_c = half;
     int nx_n0 = 0, nx_q1 = 0, nx_q2 = 0, nx_q3 = 0;  // tile coordinates of nx_tile (div/mod chain once per tile)
     bool nx_fresh = true;
     auto issue_next = [&]() {
@@ -509,7 +553,7 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
       nx_c += CSTRIDE;
       if (nx_c >= CPT) {
         nx_c = half;
-        nx_tile += gridDim.x;
+        nx_tile += item_stride;
         nx_fresh = true;
       }
     };
@@ -525,7 +569,7 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
     const bool need_grp = !PLAIN && ((p.row_scale != nullptr) || (p.row_bias != nullptr));
 
     int gc = 0, ti = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
+    for (int tile = item_first; tile < item_count; tile += item_stride, ++ti) {
       int n0, q1, q2, q3;
       tile_origin(tile, n0, q1, q2, q3);
       int grp = 0;
@@ -568,7 +612,7 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
       auto mma_col = [&](int c) { return GEGLU ? ((c >> 1) * 128 + (c & 1) * 32) : c * EPI_CHUNK; };
 #ifdef SA_X_NOEPI
       tc_fence_before();
-      mbar_arrive(&acc_empty[ab]);
+      release_acc(ab);
       continue;
 #endif
 #ifdef SA_X_LDONLY
@@ -580,7 +624,7 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
           if (uu[3] == 0x7fc12345u && uu[7] == 0x1234567u) p.row_scale[0];
         }
         tc_fence_before();
-        mbar_arrive(&acc_empty[ab]);
+        release_acc(ab);
         continue;
       }
 #endif
@@ -639,7 +683,7 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
           if constexpr (GEGLU) tmem_ld_32x32(acc + mma_col(c + CSTRIDE) + 64, reinterpret_cast<uint32_t(&)[32]>(g));
         } else {            // accumulator fully read by this thread: hand it back to the MMA warp
           tc_fence_before();
-          mbar_arrive(&acc_empty[ab]);
+          release_acc(ab);
         }
         if constexpr (GEGLU) {
 #pragma unroll
@@ -859,7 +903,12 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<TCOLS>(tmem_base);
+  if constexpr (PAIR) {
+    cluster_sync();   // neither CTA leaves while the partner may still signal its barriers
+    if (warp == 1) tmem_dealloc_2cta<TCOLS>(tmem_base);
+  } else {
+    if (warp == 1) tmem_dealloc<TCOLS>(tmem_base);
+  }
 }
 
 // ------------------------------------------------------------------------------------ host side
@@ -913,6 +962,52 @@ static int launch_persist(const CUtensorMap* a0, const CUtensorMap* a1, const CU
   else
     gemm_tap_persist_kernel<BN, STAGES, GEGLU, EW, false><<<grid, 64 + 32 * EW, L::TOTAL, stream>>>(*a0, *a1, *b, *o, *r, *x, p);
   SA_CUDA_CHECK(cudaGetLastError());
+  return SA_OK;
+}
+
+// CTA-pair launch (cta_group::2): non-GEGLU, EW epilogue warps; `b` is the weight map with a (64, BN / 2) box
+template <int BN, int STAGES, int EW>
+static int launch_pair(const CUtensorMap* a0, const CUtensorMap* a1, const CUtensorMap* b, const CUtensorMap* o,
+                       const CUtensorMap* r, const CUtensorMap* x, GemmKParams p, int m_tiles, cudaStream_t stream) {
+  using L = Gemm2Smem<BN, STAGES, EW, false, true>;
+  using LP = Gemm2Smem<BN, STAGES + 1, EW, true, true>;
+  static_assert(L::TOTAL <= 232448 && LP::TOTAL <= 232448, "shared memory budget");
+  static DeviceOnce once;
+  if (int rc = once.run([&]() -> int {
+        SA_CUDA_CHECK(cudaFuncSetAttribute(gemm_tap_persist_kernel<BN, STAGES, false, EW, false, true>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        SA_CUDA_CHECK(cudaFuncSetAttribute(gemm_tap_persist_kernel<BN, STAGES + 1, false, EW, true, true>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, LP::TOTAL));
+        return SA_OK;
+      }))
+    return rc;
+  p.n_tiles_n = p.N / BN;
+  p.total_tiles = ((m_tiles + 1) / 2) * p.n_tiles_n;   // work items = pairs of row-neighbouring tiles
+  p.fd_ntn.init(p.n_tiles_n);
+  p.fd_t1.init(p.t1);
+  p.fd_t2.init(p.t2);
+  p.fd_rpg.init(p.rows_per_group);
+  int pairs = num_sms() / 2;
+  if (pairs > p.total_tiles) pairs = p.total_tiles;
+  const bool plain = !p.row_scale && !p.row_bias && p.out_scale == 1.0f && !p.residual && !p.blend_x && p.f16_from == 0 &&
+                     !p.gn_stats;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * pairs, 1, 1);
+  cfg.blockDim = dim3(64 + 32 * EW, 1, 1);
+  cfg.dynamicSmemBytes = plain ? LP::TOTAL : L::TOTAL;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (plain)
+    SA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tap_persist_kernel<BN, STAGES + 1, false, EW, true, true>, *a0, *a1, *b, *o, *r, *x, p));
+  else
+    SA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tap_persist_kernel<BN, STAGES, false, EW, false, true>, *a0, *a1, *b, *o, *r, *x, p));
   return SA_OK;
 }
 
@@ -1109,6 +1204,15 @@ extern "C" int sa_gemm_tap(const sa_gemm_args* a, void* stream_) {
     // long main loop: 4 epilogue warps, one more pipeline stage (SA_GEMM_LONGK=<k> moves the threshold, for A/B runs)
     static const long long long_k_min = getenv("SA_GEMM_LONGK") ? atoll(getenv("SA_GEMM_LONGK")) : 1280;
     const bool long_k = ktot >= long_k_min;
+    // CTA pairs (cta_group::2) for the long-K family (SA_GEMM_PAIR=0: single-CTA kernels, for A/B runs)
+    static const bool use_pair = !(getenv("SA_GEMM_PAIR") && atoi(getenv("SA_GEMM_PAIR")) == 0);
+    if (use_pair && long_k && !p.geglu && (bn == 160 || bn == 128) && m_tiles >= 2) {
+      uint32_t hbox[2] = {64, static_cast<uint32_t>(bn / 2)};
+      const CUtensorMap* tmbh = get_tmap_bf16(a->w, 2, wdims, wstr, hbox);
+      if (!tmbh) return SA_ERR_TMA;
+      if (bn == 160) return launch_pair<160, 7, 4>(tma[0], tma[1], tmbh, tmo, tmr, tmx, p, mt, stream);
+      return launch_pair<128, 7, 4>(tma[0], tma[1], tmbh, tmo, tmr, tmx, p, mt, stream);
+    }
 #define SA_LP(BN_, ST_, G_, EW_) return launch_persist<BN_, ST_, G_, EW_>(tma[0], tma[1], tmb, tmo, tmr, tmx, p, mt, stream)
     if (p.geglu) {
       switch (bn) {
