@@ -7,7 +7,10 @@
  *     (passed as void*), launches asynchronously on that stream, never allocates, never syncs;
  *   - returns 0 on success, a negative SA_ERR_* code otherwise; sa_last_error() gives the text;
  *   - activations are bf16, channel-innermost ("NHWC": [frames, h, w, C] == tokens [frames*h*w, C]);
- *     weights are bf16 K-major ([out, in]); biases / embeddings / statistics are fp32.
+ *     weights are bf16 K-major ([out, in]); biases / embeddings / statistics are fp32;
+ *   - `act_f16` (argument or struct field) = 1 switches the 16-bit tensors of a call -- activations AND the weights
+ *     that multiply them on the tensor core -- to IEEE fp16, the reference's default inference dtype
+ *     (inference_basic.py:486-503); the skinny fp32-activation kernels keep bf16 weights in both modes.
  *
  * Each declaration cites the reference call site(s) it replaces (paths relative to the reference
  * checkout, e.g. animation/modules/unet.py:1633).  The reference is pure PyTorch, so the
@@ -96,6 +99,9 @@ typedef struct sa_gemm_args {
   /* 2*d1 x 2*d2 x d3; tap offsets are in INPUT positions): the stride-2 3x3 conv of Downsample2D (unet.py:1459-1483) */
   /* straight from the full-resolution tensor through TMA element strides, no im2col.  0 / 1 = dense.                */
   int32_t in_stride;
+  /* 16-bit format of a0 / a1 / w / residual / blend_x / out: 0 = bf16, 1 = IEEE fp16 (the reference's default inference  */
+  /* dtype, inference_basic.py:486); fp16 stores saturate at +-65504.  f16_from_col is implied for every column.        */
+  int32_t act_f16;
 } sa_gemm_args;
 
 int sa_gemm_tap(const sa_gemm_args* args, void* stream);
@@ -135,6 +141,7 @@ typedef struct sa_ff_args {
   float alpha;
   void* out;              /* bf16 [m, ldc] */
   int32_t ldc;
+  int32_t act_f16;        /* 16-bit format of x / w1 / w2 / blend_x / out: 0 = bf16, 1 = IEEE fp16 */
 } sa_ff_args;
 
 int sa_ff_fused(const sa_ff_args* args, void* stream);
@@ -149,14 +156,14 @@ int sa_ff_fused(const sa_ff_args* args, void* stream);
  * out: bf16 [frames*S, ldo].
  * ------------------------------------------------------------------------------------------ */
 int sa_attn_spatial(const void* qkv, int32_t ld, int32_t frames, int32_t S, int32_t C,
-                    int32_t heads, void* out, int32_t ldo, void* stream);
+                    int32_t heads, void* out, int32_t ldo, int32_t act_f16, void* stream);
 
 /* Temporal self-attention over the F <= 16 frames of a tile, per (pixel, head).
  * Replaces XFormersAttnProcessor.__call__ self-attention case (unet.py:1830-1848) together with the
  * [B*F,S,C] <-> [B*S,F,C] permutes of TemporalBasicTransformerBlock.forward (:931-933,:954-956).
  * qkv: bf16 [B*F*S, ld] (row = (b*F + f)*S + s), out: bf16 [B*F*S, ldo]. */
 int sa_attn_temporal(const void* qkv, int32_t ld, int32_t B, int32_t F, int32_t S, int32_t C,
-                     int32_t heads, void* out, int32_t ldo, void* stream);
+                     int32_t heads, void* out, int32_t ldo, int32_t act_f16, void* stream);
 
 /* ID cross-attention against the num_tokens (=4) face tokens + per-frame Sum/Sum^2 of the result.
  * Replaces AnimationIDAttnNormalizedProcessor.__call__ lines unet.py:1999-2019 (id_to_k / id_to_v
@@ -165,7 +172,7 @@ int sa_attn_temporal(const void* qkv, int32_t ld, int32_t B, int32_t F, int32_t 
  * [B*F*S, ldo]; stats: fp64 [B*F, 2] workspace (zeroed by the call). */
 int sa_attn_id(const void* q, int32_t ldq, const float* ik, const float* iv, int64_t kv_tok_stride,
                int64_t kv_batch_stride, int32_t B, int32_t F, int32_t S, int32_t C, int32_t heads,
-               int32_t num_tokens, void* out, int32_t ldo, void* stats, void* stream);
+               int32_t num_tokens, void* out, int32_t ldo, void* stats, int32_t act_f16, void* stream);
 
 /* Distribution alignment folded through to_out (unet.py:2018-2024): per frame
  *   row_scale[f]   = std_lat / (std_ip + 1e-5)          (torch.std: unbiased, N = S*C)
@@ -186,17 +193,17 @@ int sa_attn_id_finalize(const void* stats, const float* vclip, int64_t vclip_bat
  * epilogue of the sa_gemm_tap launch that produced x0 (sa_gemm_args.gn_stats); same arguments. */
 int sa_groupnorm(const void* x0, const void* x1, int32_t c0, int32_t c1, int32_t ld0, int32_t ld1,
                  int64_t rows_per_stat, int32_t ns, const float* gamma, const float* beta, float eps,
-                 int32_t do_silu, void* stats_ws, void* out, int32_t ldo, void* stream);
+                 int32_t do_silu, void* stats_ws, void* out, int32_t ldo, int32_t act_f16, void* stream);
 int sa_groupnorm_apply(const void* x0, const void* x1, int32_t c0, int32_t c1, int32_t ld0, int32_t ld1,
                        int64_t rows_per_stat, int32_t ns, const float* gamma, const float* beta, float eps,
-                       int32_t do_silu, const void* stats_ws, void* out, int32_t ldo, void* stream);
+                       int32_t do_silu, const void* stats_ws, void* out, int32_t ldo, int32_t act_f16, void* stream);
 
 /* LayerNorm over C (unet.py:499,510,521,892,898,907,916), eps 1e-5:
  *   y = LN(x + addv[row / rows_per_group]); if x_out: x_out = x + addv (the new residual stream).
  * addv fp32 [groups, C] or NULL (frame position embedding :686, temporal attn2 constant :946-947). */
 int sa_layernorm(const void* x, int32_t ldx, int64_t rows, int32_t c, const float* addv,
                  int32_t rows_per_group, void* x_out, int32_t ldxo, const float* gamma,
-                 const float* beta, float eps, void* y, int32_t ldy, void* stream);
+                 const float* beta, float eps, void* y, int32_t ldy, int32_t act_f16, void* stream);
 
 /* Skinny linear (m <= a few dozen rows), fp32 activations, bf16 weights [n, k], fp32 out:
  *   out (+)= act_out(act_in(x) @ W^T + b); silu_out: 0 none, 1 SiLU, 2 exact GELU.  TimestepEmbedding (unet.py:429-436), time_emb_proj(silu(.))
@@ -236,7 +243,7 @@ int sa_sinusoid(const float* t, int32_t n, int32_t dim, float* out, void* stream
 int sa_conv_direct(const void* x, int32_t n, int32_t h, int32_t w, int32_t cin, const void* wt,
                    const float* bias, int32_t cout, int32_t cout_pad, int32_t ksz, int32_t stride,
                    int32_t pad, int32_t silu_out, float scale, const void* add, int32_t add_from,
-                   void* out, void* stream);
+                   void* out, int32_t act_f16, void* stream);
 
 /* F.interpolate(scale_factor=2, mode="nearest") on NHWC bf16 (unet.py:1799). */
 int sa_upsample2x(const void* in, int32_t n, int32_t h, int32_t w, int32_t c, void* out, void* stream);
@@ -252,7 +259,7 @@ int sa_im2col3x3_c8(const void* in, int32_t n, int32_t h, int32_t w, void* out, 
 
 /* Boundary layout conversion: reference tensors are NCHW, the kernels are NHWC. */
 int sa_nchw_to_nhwc(const void* src, int32_t src_is_bf16, int32_t n, int32_t c, int32_t hw, void* dst,
-                    void* stream);
+                    int32_t act_f16, void* stream);
 int sa_nhwc_to_nchw_f32(const float* src, int32_t lds, int32_t n, int32_t c, int32_t hw, float* dst,
                         void* stream);
 
@@ -263,7 +270,7 @@ int sa_nhwc_to_nchw_f32(const float* src, int32_t lds, int32_t n, int32_t c, int
  * latents fp32 [F,4,h,w]; image_latents fp32 [2,F,4,h,w]; noise fp32 [2,F,4,h,w]. */
 int sa_sampler_prepare(const float* latents, const float* image_latents, const int32_t* idx,
                        int32_t nb, int32_t b0, int32_t t, int32_t f, int32_t hw, float sigma, void* out,
-                       void* stream);
+                       int32_t act_f16, void* stream);
 int sa_sampler_accumulate(const float* unet_out, int32_t ldo, const int32_t* idx, const float* weight,
                           int32_t nb, int32_t b0, int32_t t, int32_t f, int32_t hw, float* noise,
                           void* stream);

@@ -46,6 +46,7 @@ class GemmArgs(C.Structure):
         ("gn_stats", C.c_void_p), ("gn_cpg", C.c_int32), ("gn_rows_per_stat", C.c_int32),
         ("ldc2", C.c_int64), ("ldc3", C.c_int64),
         ("in_stride", C.c_int32),
+        ("act_f16", C.c_int32),
     ]
 
 
@@ -58,7 +59,7 @@ class FfArgs(C.Structure):
         ("gamma", C.c_void_p), ("beta", C.c_void_p), ("eps", C.c_float),
         ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p),
         ("blend_x", C.c_void_p), ("ldbx", C.c_int32), ("alpha", C.c_float),
-        ("out", C.c_void_p), ("ldc", C.c_int32),
+        ("out", C.c_void_p), ("ldc", C.c_int32), ("act_f16", C.c_int32),
     ]
 
 
@@ -91,27 +92,27 @@ SIGNATURES: dict[str, list] = {
     "sa_gemm_tap": [C.POINTER(GemmArgs), _P],
     "sa_gemm_pick_tile": [_I, _I, _I],
     "sa_ff_fused": [C.POINTER(FfArgs), _P],
-    "sa_attn_spatial": [_P, _I, _I, _I, _I, _I, _P, _I, _P],
-    "sa_attn_temporal": [_P, _I, _I, _I, _I, _I, _I, _P, _I, _P],
-    "sa_attn_id": [_P, _I, _P, _P, _L, _L, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P],
+    "sa_attn_spatial": [_P, _I, _I, _I, _I, _I, _P, _I, _I, _P],
+    "sa_attn_temporal": [_P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _P],
+    "sa_attn_id": [_P, _I, _P, _P, _L, _L, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _P],
     "sa_attn_id_finalize": [_P, _P, _L, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P],
-    "sa_groupnorm": [_P, _P, _I, _I, _I, _I, _L, _I, _P, _P, _F, _I, _P, _P, _I, _P],
-    "sa_groupnorm_apply": [_P, _P, _I, _I, _I, _I, _L, _I, _P, _P, _F, _I, _P, _P, _I, _P],
-    "sa_layernorm": [_P, _I, _L, _I, _P, _I, _P, _I, _P, _P, _F, _P, _I, _P],
+    "sa_groupnorm": [_P, _P, _I, _I, _I, _I, _L, _I, _P, _P, _F, _I, _P, _P, _I, _I, _P],
+    "sa_groupnorm_apply": [_P, _P, _I, _I, _I, _I, _L, _I, _P, _P, _F, _I, _P, _P, _I, _I, _P],
+    "sa_layernorm": [_P, _I, _L, _I, _P, _I, _P, _I, _P, _P, _F, _P, _I, _I, _P],
     "sa_small_linear": [_P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _P, _I, _P],
     "sa_sinusoid": [_P, _I, _I, _P, _P],
     "sa_softmax_rows": [_P, _L, _I, _I, _F, _P, _L, _P],
     "sa_time_conv_out": [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P],
     "sa_layernorm_f32": [_P, _I, _I, _I, _P, _P, _F, _P, _I, _P],
     "sa_perceiver_attn": [_P, _I, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P],
-    "sa_conv_direct": [_P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _I, _P, _P],
+    "sa_conv_direct": [_P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _I, _P, _I, _P],
     "sa_upsample2x": [_P, _I, _I, _I, _I, _P, _P],
     "sa_im2col_s2": [_P, _I, _I, _I, _I, _P, _P],
     "sa_im2col_s2_pad": [_P, _I, _I, _I, _I, _I, _P, _P],
     "sa_im2col3x3_c8": [_P, _I, _I, _I, _P, _P],
-    "sa_nchw_to_nhwc": [_P, _I, _I, _I, _I, _P, _P],
+    "sa_nchw_to_nhwc": [_P, _I, _I, _I, _I, _P, _I, _P],
     "sa_nhwc_to_nchw_f32": [_P, _I, _I, _I, _I, _P, _P],
-    "sa_sampler_prepare": [_P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P],
+    "sa_sampler_prepare": [_P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _I, _P],
     "sa_sampler_accumulate": [_P, _I, _P, _P, _I, _I, _I, _I, _I, _P, _P],
     "sa_sampler_step": [_P, _P, _P, _I, _I, _F, _F, _P, _P],
     "sa_gauss_blur_axis": [_P, _P, _I, _I, _I, _P, _I, _I, _F, _F, _P],

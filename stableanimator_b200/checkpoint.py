@@ -5,8 +5,9 @@ The reference resumes three ``.pth`` state dicts with ``load_state_dict(strict=T
 the SVD checkpoint (``vae/diffusion_pytorch_model.safetensors``, ``AutoencoderKLTemporalDecoder.from_pretrained``).
 These helpers read the same files (``torch.load`` or safetensors) and hand the state dicts to the B200 modules,
 whose constructors do the strict key / shape check and the packing (bf16 K-major matrices, fused q|k|v,
-interleaved GEGLU rows, concatenated time / context projections).  fp16 checkpoints are accepted: matrices
-are re-rounded to bf16 (8-bit significand instead of fp16's 11 -- an fp16-activation parity mode is not built).
+interleaved GEGLU rows, concatenated time / context projections).  ``dtype=torch.float16`` runs the UNet / PoseNet in
+the reference's default inference dtype (inference_basic.py:486-503): fp16 checkpoints then keep their 11-bit
+significands; with the default ``torch.bfloat16`` their matrices are re-rounded to bf16.
 """
 from __future__ import annotations
 
@@ -45,16 +46,16 @@ def read_state_dict(path: PathLike, prefix: str = "") -> Dict[str, torch.Tensor]
     return sd
 
 
-def load_unet(path: PathLike, cfg: Optional[UNetConfig] = None, device="cuda"):
+def load_unet(path: PathLike, cfg: Optional[UNetConfig] = None, device="cuda", dtype=torch.bfloat16):
     """``unet.pth`` (inference_basic.py:465-468) -> UNetB200."""
     from .unet import UNetB200
-    return UNetB200(cfg or UNetConfig.full(), read_state_dict(path), device)
+    return UNetB200(cfg or UNetConfig.full(), read_state_dict(path), device, dtype)
 
 
-def load_pose_net(path: PathLike, noise_latent_channels: int = 320, device="cuda"):
+def load_pose_net(path: PathLike, noise_latent_channels: int = 320, device="cuda", dtype=torch.bfloat16):
     """``pose_net.pth`` (inference_basic.py:451-454) -> PoseNetB200."""
     from .pose_net import PoseNetB200
-    return PoseNetB200(read_state_dict(path), noise_latent_channels, device)
+    return PoseNetB200(read_state_dict(path), noise_latent_channels, device, dtype)
 
 
 def load_face_encoder(path: PathLike, device="cuda"):

@@ -97,7 +97,7 @@ __device__ __forceinline__ void exp2_poly2(uint64_t x, float& e0, float& e1) {
 template <int POLY>
 __global__ void __launch_bounds__(FA3_LB, 1)
 attn_flash_kernel(const __grid_constant__ CUtensorMap tm, int S, int C, __nv_bfloat16* __restrict__ out,
-                  int ldo) {
+                  int ldo, int f16) {   // f16: q, k and out are IEEE fp16 like v (the fp16 activation mode)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;                          // 2 tiles
@@ -158,7 +158,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm, int S, int C, __nv_bfl
   } else if (warp == FA3_SW + 1) {
     // ------------------------------------------------------------ MMA issuer
     if (elect_one()) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, FA_BN, 0, 0);  // S = Q K^T (bf16, both K-major)
+      const uint32_t idesc_s = f16 ? umma_idesc_f16(128, FA_BN, 0, 0) : umma_idesc_bf16(128, FA_BN, 0, 0);  // S = Q K^T
       constexpr uint32_t idesc_o = umma_idesc_f16(128, FA_D, 0, 1);    // O += P V, fp16 x fp16 (V MN-major)
       auto issue_s = [&](int t, int j) {
         const uint64_t dq = umma_desc_sw128(smem_u32(sQ + t * FA_TILE));
@@ -326,11 +326,12 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm, int S, int C, __nv_bfl
       if (qrow < S) {
         uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<long long>(frame) * S + qrow) * ldo + head * FA_D + hc * 32);
 #pragma unroll
+        const bool h16 = f16 != 0;
         for (int g = 0; g < 4; ++g)
-          dst[g] = make_uint4(pack_bf16x2(__uint_as_float(o[8 * g]) * inv, __uint_as_float(o[8 * g + 1]) * inv),
-                              pack_bf16x2(__uint_as_float(o[8 * g + 2]) * inv, __uint_as_float(o[8 * g + 3]) * inv),
-                              pack_bf16x2(__uint_as_float(o[8 * g + 4]) * inv, __uint_as_float(o[8 * g + 5]) * inv),
-                              pack_bf16x2(__uint_as_float(o[8 * g + 6]) * inv, __uint_as_float(o[8 * g + 7]) * inv));
+          dst[g] = make_uint4(pack16x2(__uint_as_float(o[8 * g]) * inv, __uint_as_float(o[8 * g + 1]) * inv, h16),
+                              pack16x2(__uint_as_float(o[8 * g + 2]) * inv, __uint_as_float(o[8 * g + 3]) * inv, h16),
+                              pack16x2(__uint_as_float(o[8 * g + 4]) * inv, __uint_as_float(o[8 * g + 5]) * inv, h16),
+                              pack16x2(__uint_as_float(o[8 * g + 6]) * inv, __uint_as_float(o[8 * g + 7]) * inv, h16));
       }
     }
   }
@@ -345,7 +346,7 @@ using namespace sa;
 
 // qkv: bf16 [frames*S, ld] with q | k | v column blocks of width C = heads*64; out: bf16 [frames*S, ldo]
 extern "C" int sa_attn_spatial(const void* qkv, int32_t ld, int32_t frames, int32_t S, int32_t C,
-                               int32_t heads, void* out, int32_t ldo, void* stream_) {
+                               int32_t heads, void* out, int32_t ldo, int32_t act_f16, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!qkv || !out) return fail(SA_ERR_INVALID, "sa_attn_spatial: null pointer");
   if (C != heads * 64 || ld < 3 * C || ld % 8 || ldo % 8)
@@ -371,11 +372,11 @@ extern "C" int sa_attn_spatial(const void* qkv, int32_t ld, int32_t frames, int3
   dim3 grid((S + 2 * FA_BM - 1) / (2 * FA_BM), heads, frames);
   __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
   switch (poly) {
-    case 0: attn_flash_kernel<0><<<grid, FA3_THREADS, FA3_SMEM, stream>>>(*tm, S, C, o, ldo); break;
-    case 2: attn_flash_kernel<2><<<grid, FA3_THREADS, FA3_SMEM, stream>>>(*tm, S, C, o, ldo); break;
-    case 3: attn_flash_kernel<3><<<grid, FA3_THREADS, FA3_SMEM, stream>>>(*tm, S, C, o, ldo); break;
-    case 8: attn_flash_kernel<8><<<grid, FA3_THREADS, FA3_SMEM, stream>>>(*tm, S, C, o, ldo); break;
-    default: attn_flash_kernel<4><<<grid, FA3_THREADS, FA3_SMEM, stream>>>(*tm, S, C, o, ldo); break;
+    case 0: attn_flash_kernel<0><<<grid, FA3_THREADS, FA3_SMEM, stream>>>(*tm, S, C, o, ldo, act_f16); break;
+    case 2: attn_flash_kernel<2><<<grid, FA3_THREADS, FA3_SMEM, stream>>>(*tm, S, C, o, ldo, act_f16); break;
+    case 3: attn_flash_kernel<3><<<grid, FA3_THREADS, FA3_SMEM, stream>>>(*tm, S, C, o, ldo, act_f16); break;
+    case 8: attn_flash_kernel<8><<<grid, FA3_THREADS, FA3_SMEM, stream>>>(*tm, S, C, o, ldo, act_f16); break;
+    default: attn_flash_kernel<4><<<grid, FA3_THREADS, FA3_SMEM, stream>>>(*tm, S, C, o, ldo, act_f16); break;
   }
   SA_CUDA_CHECK(cudaGetLastError());
   return SA_OK;

@@ -49,6 +49,18 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint3
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ void mma_f16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                              uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+template <bool F16>
+__device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                          uint32_t b1) {
+  if constexpr (F16) mma_f16_16816(c, a0, a1, a2, a3, b0, b1);
+  else mma_bf16_16816(c, a0, a1, a2, a3, b0, b1);
+}
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
@@ -56,6 +68,7 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
 constexpr int AT_WARPS = 8;
 constexpr int AT_TILE = 16 * 128;  // one [16 frames x 64 dims] bf16 tile
 
+template <bool F16>   // F16: q | k | v and out hold IEEE fp16 instead of bf16
 __global__ void __launch_bounds__(AT_WARPS * 32)
 attn_temporal_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, int B, int F, int S, int C,
                      int heads, __nv_bfloat16* __restrict__ out, int ldo) {
@@ -109,8 +122,8 @@ attn_temporal_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, int B, int F
       uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
       ldsm_x4(smem_u32(sq + ar * 128 + (((2 * ks + (lane >> 4)) ^ (ar & 7)) << 4)), a0, a1, a2, a3);
       ldsm_x4(smem_u32(sk + br * 128 + (((2 * ks + ((lane >> 3) & 1)) ^ (br & 7)) << 4)), b0, b1, b2, b3);
-      mma_bf16_16816(sc[0], a0, a1, a2, a3, b0, b1);
-      mma_bf16_16816(sc[1], a0, a1, a2, a3, b2, b3);
+      mma_16816<F16>(sc[0], a0, a1, a2, a3, b0, b1);
+      mma_16816<F16>(sc[1], a0, a1, a2, a3, b2, b3);
     }
   }
   // ---- softmax over keys (columns); fragment: e0,e1 -> row lane/4, cols 8n + 2(lane%4) + {0,1};
@@ -152,9 +165,9 @@ attn_temporal_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, int B, int F
   uint32_t ph[4], pl[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    ph[i] = pack_bf16x2(pn[2 * i], pn[2 * i + 1]);
-    const float2 hf = unpack_bf16x2(ph[i]);
-    pl[i] = pack_bf16x2(pn[2 * i] - hf.x, pn[2 * i + 1] - hf.y);
+    ph[i] = pack16x2(pn[2 * i], pn[2 * i + 1], F16);
+    const float2 hf = unpack16x2(ph[i], F16);
+    pl[i] = pack16x2(pn[2 * i] - hf.x, pn[2 * i + 1] - hf.y, F16);
   }
 
   // ---- O = P V : 8 n-tiles of 8 dims, one k-step (16 keys); V^T fragments via ldmatrix.trans
@@ -169,10 +182,10 @@ attn_temporal_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, int B, int F
     for (int np = 0; np < 4; ++np) {
       uint32_t b0, b1, b2, b3;
       ldsm_x4_t(smem_u32(sv + vr * 128 + (((2 * np + (lane >> 4)) ^ (vr & 7)) << 4)), b0, b1, b2, b3);
-      mma_bf16_16816(o[2 * np], ph[0], ph[1], ph[2], ph[3], b0, b1);
-      mma_bf16_16816(o[2 * np], pl[0], pl[1], pl[2], pl[3], b0, b1);
-      mma_bf16_16816(o[2 * np + 1], ph[0], ph[1], ph[2], ph[3], b2, b3);
-      mma_bf16_16816(o[2 * np + 1], pl[0], pl[1], pl[2], pl[3], b2, b3);
+      mma_16816<F16>(o[2 * np], ph[0], ph[1], ph[2], ph[3], b0, b1);
+      mma_16816<F16>(o[2 * np], pl[0], pl[1], pl[2], pl[3], b0, b1);
+      mma_16816<F16>(o[2 * np + 1], ph[0], ph[1], ph[2], ph[3], b2, b3);
+      mma_16816<F16>(o[2 * np + 1], pl[0], pl[1], pl[2], pl[3], b2, b3);
     }
   }
   // ---- stage O (bf16) in the Q tile, then coalesced 16-byte stores
@@ -180,9 +193,9 @@ attn_temporal_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, int B, int F
 #pragma unroll
   for (int n = 0; n < 8; ++n) {
     const int r = lane >> 2;
-    *reinterpret_cast<uint32_t*>(sq + r * 128 + ((n ^ (r & 7)) << 4) + (lane & 3) * 4) = pack_bf16x2(o[n][0], o[n][1]);
+    *reinterpret_cast<uint32_t*>(sq + r * 128 + ((n ^ (r & 7)) << 4) + (lane & 3) * 4) = pack16x2(o[n][0], o[n][1], F16);
     *reinterpret_cast<uint32_t*>(sq + (r + 8) * 128 + ((n ^ ((r + 8) & 7)) << 4) + (lane & 3) * 4) =
-        pack_bf16x2(o[n][2], o[n][3]);
+        pack16x2(o[n][2], o[n][3], F16);
   }
   __syncwarp();
 #pragma unroll
@@ -203,7 +216,8 @@ __global__ void __launch_bounds__(256)
 attn_id_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const float* __restrict__ ik,
                const float* __restrict__ iv, long long tok_stride, long long batch_stride, int F, int S,
                int C, int heads,
-               __nv_bfloat16* __restrict__ out, int ldo, double* __restrict__ stats) {
+               __nv_bfloat16* __restrict__ out, int ldo, double* __restrict__ stats, int f16_) {
+  const bool f16 = f16_ != 0;   // q / out hold IEEE fp16 instead of bf16
   extern __shared__ float sm_kv[];  // [2][NTOK][C]
   __shared__ double red[2][8];
   const int frame = blockIdx.y;
@@ -232,7 +246,7 @@ attn_id_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const float* __rest
         const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const float2 f = unpack_bf16x2(w[k]);
+          const float2 f = unpack16x2(w[k], f16);
           qv[8 * i + 2 * k] = f.x;
           qv[8 * i + 2 * k + 1] = f.y;
         }
@@ -286,9 +300,8 @@ attn_id_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const float* __rest
     uint4* dst = reinterpret_cast<uint4*>(out + row * ldo + h * 64);
 #pragma unroll
     for (int i = 0; i < 8; ++i)
-      dst[i] = make_uint4(pack_bf16x2(o[8 * i], o[8 * i + 1]), pack_bf16x2(o[8 * i + 2], o[8 * i + 3]),
-                          pack_bf16x2(o[8 * i + 4], o[8 * i + 5]),
-                          pack_bf16x2(o[8 * i + 6], o[8 * i + 7]));
+      dst[i] = make_uint4(pack16x2(o[8 * i], o[8 * i + 1], f16), pack16x2(o[8 * i + 2], o[8 * i + 3], f16),
+                          pack16x2(o[8 * i + 4], o[8 * i + 5], f16), pack16x2(o[8 * i + 6], o[8 * i + 7], f16));
   }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) {
@@ -372,15 +385,19 @@ attn_id_finalize_kernel(const double* __restrict__ stats, const float* __restric
 using namespace sa;
 
 extern "C" int sa_attn_temporal(const void* qkv, int32_t ld, int32_t B, int32_t F, int32_t S,
-                                int32_t C, int32_t heads, void* out, int32_t ldo, void* stream_) {
+                                int32_t C, int32_t heads, void* out, int32_t ldo, int32_t act_f16, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!qkv || !out) return fail(SA_ERR_INVALID, "sa_attn_temporal: null pointer");
   if (F < 1 || F > 16) return fail(SA_ERR_INVALID, "sa_attn_temporal: F=%d must be in [1,16]", F);
   if (C != heads * 64 || ld % 8 || ldo % 8) return fail(SA_ERR_INVALID, "sa_attn_temporal: head_dim must be 64");
   const long long ntasks = static_cast<long long>(B) * S * heads;
   const unsigned grid = static_cast<unsigned>((ntasks + AT_WARPS - 1) / AT_WARPS);
-  attn_temporal_kernel<<<grid, AT_WARPS * 32, 0, stream>>>(static_cast<const __nv_bfloat16*>(qkv), ld, B, F, S, C,
-                                                 heads, static_cast<__nv_bfloat16*>(out), ldo);
+  if (act_f16)
+    attn_temporal_kernel<true><<<grid, AT_WARPS * 32, 0, stream>>>(static_cast<const __nv_bfloat16*>(qkv), ld, B, F, S, C,
+                                                                   heads, static_cast<__nv_bfloat16*>(out), ldo);
+  else
+    attn_temporal_kernel<false><<<grid, AT_WARPS * 32, 0, stream>>>(static_cast<const __nv_bfloat16*>(qkv), ld, B, F, S, C,
+                                                                    heads, static_cast<__nv_bfloat16*>(out), ldo);
   SA_CUDA_CHECK(cudaGetLastError());
   return SA_OK;
 }
@@ -389,7 +406,7 @@ extern "C" int sa_attn_temporal(const void* qkv, int32_t ld, int32_t B, int32_t 
 extern "C" int sa_attn_id(const void* q, int32_t ldq, const float* ik, const float* iv,
                           int64_t kv_tok_stride, int64_t kv_batch_stride, int32_t B, int32_t F,
                           int32_t S, int32_t C, int32_t heads, int32_t num_tokens, void* out,
-                          int32_t ldo, void* stats, void* stream_) {
+                          int32_t ldo, void* stats, int32_t act_f16, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!q || !ik || !iv || !out || !stats) return fail(SA_ERR_INVALID, "sa_attn_id: null pointer");
   if (num_tokens != 4) return fail(SA_ERR_INVALID, "sa_attn_id: num_tokens must be 4");
@@ -406,7 +423,7 @@ extern "C" int sa_attn_id(const void* q, int32_t ldq, const float* ik, const flo
   attn_id_kernel<4><<<grid, 256, smem, stream>>>(static_cast<const __nv_bfloat16*>(q), ldq, ik, iv,
                                                  kv_tok_stride, kv_batch_stride, F, S, C,
                                                  heads, static_cast<__nv_bfloat16*>(out), ldo,
-                                                 static_cast<double*>(stats));
+                                                 static_cast<double*>(stats), act_f16);
   SA_CUDA_CHECK(cudaGetLastError());
   return SA_OK;
 }

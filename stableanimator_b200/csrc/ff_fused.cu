@@ -57,6 +57,7 @@ struct FfParams {
   int ldbx;
   float alpha;
   int m_tiles;
+  int act_f16;   // x / w1 / w2 / blend_x / out are IEEE fp16 instead of bf16
 };
 
 template <int KC>
@@ -181,8 +182,8 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (elect_one()) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
-      constexpr uint32_t idesc_o = umma_idesc_bf16(128, NHALF, 0, 0);
+      const uint32_t idesc_s = p.act_f16 ? umma_idesc_f16(128, 128, 0, 0) : umma_idesc_bf16(128, 128, 0, 0);
+      const uint32_t idesc_o = p.act_f16 ? umma_idesc_f16(128, NHALF, 0, 0) : umma_idesc_bf16(128, NHALF, 0, 0);
       int it = 0, ti = 0;
       uint32_t ci = 0;   // global chunk counter (phases of s_full / s_free / p_full / p_free)
       for (int tp = pair; tp < pair_tiles; tp += n_pairs, ++ti) {
@@ -245,6 +246,7 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     uint8_t* stage_slot = sP + ew * 2048;   // both P tiles double as the TMA-store staging of the final epilogue
     const int sw64 = (lane >> 1) & 3;
+    const bool f16 = p.act_f16 != 0;
     uint32_t ci = 0;
     int ti = 0;
     for (int tp = pair; tp < pair_tiles; tp += n_pairs, ++ti) {
@@ -274,14 +276,14 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
               const float aa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const float2 f = unpack_bf16x2(ww[e]);
-                ww[e] = pack_bf16x2(f.x + aa[2 * e], f.y + aa[2 * e + 1]);
+                const float2 f = unpack16x2(ww[e], f16);
+                ww[e] = pack16x2(f.x + aa[2 * e], f.y + aa[2 * e + 1], f16);
               }
               *reinterpret_cast<uint4*>(q) = make_uint4(ww[0], ww[1], ww[2], ww[3]);
             }
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const float2 f = unpack_bf16x2(ww[e]);
+              const float2 f = unpack16x2(ww[e], f16);
               sum += f.x + f.y;
             }
           }
@@ -298,7 +300,7 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const float2 f = unpack_bf16x2(ww[e]);
+              const float2 f = unpack16x2(ww[e], f16);
               const float d0 = f.x - mean, d1 = f.y - mean;
               var += d0 * d0 + d1 * d1;
             }
@@ -324,9 +326,9 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             uint32_t o[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const float2 f = unpack_bf16x2(ww[e]);
-              o[e] = pack_bf16x2(fmaf((f.x - mean) * rstd, g[2 * e], bb[2 * e]),
-                                 fmaf((f.y - mean) * rstd, g[2 * e + 1], bb[2 * e + 1]));
+              const float2 f = unpack16x2(ww[e], f16);
+              o[e] = pack16x2(fmaf((f.x - mean) * rstd, g[2 * e], bb[2 * e]),
+                              fmaf((f.y - mean) * rstd, g[2 * e + 1], bb[2 * e + 1]), f16);
             }
             *reinterpret_cast<uint4*>(q) = make_uint4(o[0], o[1], o[2], o[3]);
           }
@@ -364,7 +366,7 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           const uint64_t v2 = mul2(add2(pack2u(u[8 * j + 4], u[8 * j + 5]), pack2(a1.x, a1.y)), gelu2(g2));
           const uint64_t v3 = mul2(add2(pack2u(u[8 * j + 6], u[8 * j + 7]), pack2(a1.z, a1.w)), gelu2(g3));
           *reinterpret_cast<uint4*>(prow + (((4 * ch + j) ^ (r & 7)) << 4)) =
-              make_uint4(pack_bf16x2_f2(v0), pack_bf16x2_f2(v1), pack_bf16x2_f2(v2), pack_bf16x2_f2(v3));
+              make_uint4(pack16x2_f2(v0, f16), pack16x2_f2(v1, f16), pack16x2_f2(v2, f16), pack16x2_f2(v3, f16));
         }
         fence_proxy_async();
         mbar_arrive(&p_full[half]);
@@ -413,12 +415,12 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
               const float aa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const float2 f = unpack_bf16x2(ww[e]);
-                ww[e] = pack_bf16x2(f.x + aa[2 * e], f.y + aa[2 * e + 1]);
+                const float2 f = unpack16x2(ww[e], f16);
+                ww[e] = pack16x2(f.x + aa[2 * e], f.y + aa[2 * e + 1], f16);
               }
             }
 #pragma unroll
-            for (int e = 0; e < 4; ++e) v2[4 * j + e] = add2(v2[4 * j + e], bf16x2_to_f32x2(ww[e]));
+            for (int e = 0; e < 4; ++e) v2[4 * j + e] = add2(v2[4 * j + e], h16x2_to_f32x2(ww[e], f16));
           }
         }
         if (p.blend_x) {
@@ -426,10 +428,10 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint4 q = __ldg(x4 + j);
-            v2[4 * j + 0] = fma2(al2, bf16x2_to_f32x2(q.x), mul2(be2, v2[4 * j + 0]));
-            v2[4 * j + 1] = fma2(al2, bf16x2_to_f32x2(q.y), mul2(be2, v2[4 * j + 1]));
-            v2[4 * j + 2] = fma2(al2, bf16x2_to_f32x2(q.z), mul2(be2, v2[4 * j + 2]));
-            v2[4 * j + 3] = fma2(al2, bf16x2_to_f32x2(q.w), mul2(be2, v2[4 * j + 3]));
+            v2[4 * j + 0] = fma2(al2, h16x2_to_f32x2(q.x, f16), mul2(be2, v2[4 * j + 0]));
+            v2[4 * j + 1] = fma2(al2, h16x2_to_f32x2(q.y, f16), mul2(be2, v2[4 * j + 1]));
+            v2[4 * j + 2] = fma2(al2, h16x2_to_f32x2(q.z, f16), mul2(be2, v2[4 * j + 2]));
+            v2[4 * j + 3] = fma2(al2, h16x2_to_f32x2(q.w, f16), mul2(be2, v2[4 * j + 3]));
           }
         }
         if (lane == 0) tma_store_wait_read<0>();   // the staging slot's previous store has read it
@@ -438,8 +440,8 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           *reinterpret_cast<uint4*>(ro + ((j ^ sw64) << 4)) =
-              make_uint4(pack_bf16x2_f2(v2[4 * j]), pack_bf16x2_f2(v2[4 * j + 1]), pack_bf16x2_f2(v2[4 * j + 2]),
-                         pack_bf16x2_f2(v2[4 * j + 3]));
+              make_uint4(pack16x2_f2(v2[4 * j], f16), pack16x2_f2(v2[4 * j + 1], f16), pack16x2_f2(v2[4 * j + 2], f16),
+                         pack16x2_f2(v2[4 * j + 3], f16));
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
@@ -522,6 +524,7 @@ extern "C" int sa_ff_fused(const sa_ff_args* a, void* stream_) {
   p.ldbx = a->ldbx;
   p.alpha = a->alpha;
   p.m_tiles = static_cast<int>((a->m + 127) / 128);
+  p.act_f16 = a->act_f16 ? 1 : 0;
 
   // x [M, C] (box 64 ch x 128 rows), W1 [8C, C] (64 x 64 = half a stage), W2 [C, 4C] (64 x C/4), out [M, C] (32 x 32, SWIZZLE_64B)
   uint64_t xd[2] = {static_cast<uint64_t>(C), static_cast<uint64_t>(a->m)};

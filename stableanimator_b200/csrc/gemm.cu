@@ -54,6 +54,7 @@ struct GemmKParams {
   float out_scale;  // v = (acc*rs + bias + row_bias [geglu]) * out_scale + residual ...
   int f16_from;     // > 0: output columns >= f16_from are stored as fp16 instead of bf16
   int cs;           // coordinate scale of the source grid along dims 1, 2 (2 = stride-2 convolution)
+  int act_f16;      // 16-bit operands / outputs are IEEE fp16 instead of bf16
   double* gn_stats; // fused GroupNorm statistics of the output: fp64 [M / rows_per_stat, n_out / cpg, 2] or null
   int gn_groups;    // n_out / cpg
   FastDiv fd_ntn, fd_t1, fd_t2, fd_rpg, fd_gcpg, fd_grps;
@@ -132,7 +133,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     __syncwarp();
   } else if (warp == 1) {
     if (elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+      const uint32_t idesc = p.act_f16 ? umma_idesc_f16(128, BN, 0, 0) : umma_idesc_bf16(128, BN, 0, 0);
       for (int kb = 0; kb < KB; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
@@ -164,6 +165,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   const float rs = (p.row_scale && valid) ? p.row_scale[grp] : 1.0f;
   const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
   const float alpha = p.alpha, beta = 1.0f - p.alpha;
+  const bool f16 = p.act_f16 != 0;
 
   // output-column geometry: plain -> BN columns at n0; GEGLU -> BN/2 columns at n0/2, MMA columns
   // come in 128-wide groups [64 value | 64 gate]
@@ -239,7 +241,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
-            const float2 f = unpack_bf16x2(w[t]);
+            const float2 f = unpack16x2(w[t], f16);
             v[8 * j + 2 * t] += f.x;
             v[8 * j + 2 * t + 1] += f.y;
           }
@@ -255,7 +257,7 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
-            const float2 f = unpack_bf16x2(w[t]);
+            const float2 f = unpack16x2(w[t], f16);
             v[8 * j + 2 * t] = alpha * f.x + beta * v[8 * j + 2 * t];
             v[8 * j + 2 * t + 1] = alpha * f.y + beta * v[8 * j + 2 * t + 1];
           }
@@ -274,9 +276,8 @@ gemm_tap_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         if (ncol + 8 * j < n_out_total)
-          o4[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                             pack_bf16x2(v[8 * j + 4], v[8 * j + 5]),
-                             pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+          o4[j] = make_uint4(pack16x2(v[8 * j], v[8 * j + 1], f16), pack16x2(v[8 * j + 2], v[8 * j + 3], f16),
+                             pack16x2(v[8 * j + 4], v[8 * j + 5], f16), pack16x2(v[8 * j + 6], v[8 * j + 7], f16));
     }
   }
 
@@ -461,7 +462,7 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (PAIR: the leader CTA only)
     if (rank == 0 && elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 256 : 128, BN, 0, 0);
+      const uint32_t idesc = p.act_f16 ? umma_idesc_f16(PAIR ? 256 : 128, BN, 0, 0) : umma_idesc_bf16(PAIR ? 256 : 128, BN, 0, 0);
       int it = 0, ti = 0;
       for (int tile = item_first; tile < item_count; tile += item_stride, ++ti) {
         const int ab = ti & 1;
@@ -715,13 +716,24 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
         if (staged) mbar_wait(&ro_ready[slot], (gc / EPI_RO_SLOTS) & 1);
         uint8_t* ro = my_ro + slot * EPI_TILE_BYTES;
         if (!SLIM && p.residual) {
+          if (p.act_f16) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 q = *reinterpret_cast<const uint4*>(ro + ((j ^ sw) << 4));
-            v2[4 * j + 0] = add2(v2[4 * j + 0], bf16x2_to_f32x2(q.x));
-            v2[4 * j + 1] = add2(v2[4 * j + 1], bf16x2_to_f32x2(q.y));
-            v2[4 * j + 2] = add2(v2[4 * j + 2], bf16x2_to_f32x2(q.z));
-            v2[4 * j + 3] = add2(v2[4 * j + 3], bf16x2_to_f32x2(q.w));
+            for (int j = 0; j < 4; ++j) {
+              const uint4 q = *reinterpret_cast<const uint4*>(ro + ((j ^ sw) << 4));
+              v2[4 * j + 0] = add2(v2[4 * j + 0], h16x2_to_f32x2(q.x, true));
+              v2[4 * j + 1] = add2(v2[4 * j + 1], h16x2_to_f32x2(q.y, true));
+              v2[4 * j + 2] = add2(v2[4 * j + 2], h16x2_to_f32x2(q.z, true));
+              v2[4 * j + 3] = add2(v2[4 * j + 3], h16x2_to_f32x2(q.w, true));
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 q = *reinterpret_cast<const uint4*>(ro + ((j ^ sw) << 4));
+              v2[4 * j + 0] = add2(v2[4 * j + 0], bf16x2_to_f32x2(q.x));
+              v2[4 * j + 1] = add2(v2[4 * j + 1], bf16x2_to_f32x2(q.y));
+              v2[4 * j + 2] = add2(v2[4 * j + 2], bf16x2_to_f32x2(q.z));
+              v2[4 * j + 3] = add2(v2[4 * j + 3], bf16x2_to_f32x2(q.w));
+            }
           }
         }
         if constexpr (!PLAIN && EPI_X_SLOTS > 0) if (p.blend_x) {
@@ -730,15 +742,17 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
           const uint8_t* xr = my_x + xs * EPI_TILE_BYTES;
           const uint64_t al2 = pack2(alpha, alpha), be2 = pack2(beta, beta);
 #pragma unroll
+          const bool xf16 = p.act_f16 != 0;
+#pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint4 q = *reinterpret_cast<const uint4*>(xr + ((j ^ sw) << 4));
-            v2[4 * j + 0] = fma2(al2, bf16x2_to_f32x2(q.x), mul2(be2, v2[4 * j + 0]));
-            v2[4 * j + 1] = fma2(al2, bf16x2_to_f32x2(q.y), mul2(be2, v2[4 * j + 1]));
-            v2[4 * j + 2] = fma2(al2, bf16x2_to_f32x2(q.z), mul2(be2, v2[4 * j + 2]));
-            v2[4 * j + 3] = fma2(al2, bf16x2_to_f32x2(q.w), mul2(be2, v2[4 * j + 3]));
+            v2[4 * j + 0] = fma2(al2, h16x2_to_f32x2(q.x, xf16), mul2(be2, v2[4 * j + 0]));
+            v2[4 * j + 1] = fma2(al2, h16x2_to_f32x2(q.y, xf16), mul2(be2, v2[4 * j + 1]));
+            v2[4 * j + 2] = fma2(al2, h16x2_to_f32x2(q.z, xf16), mul2(be2, v2[4 * j + 2]));
+            v2[4 * j + 3] = fma2(al2, h16x2_to_f32x2(q.w, xf16), mul2(be2, v2[4 * j + 3]));
           }
         }
-        if (!PLAIN && p.f16_from > 0 && ncol >= p.f16_from) {  // chunk-uniform: half-precision block (attention V)
+        if (p.act_f16 || (!PLAIN && p.f16_from > 0 && ncol >= p.f16_from)) {  // chunk-uniform: fp16 mode / attention V block
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             *reinterpret_cast<uint4*>(ro + ((j ^ sw) << 4)) =
@@ -770,6 +784,7 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
             // the first lane of each group adds to the fp64 accumulators.
             const uint8_t* tile = sRO + slot * EPI_TILE_BYTES;
             const int gid = static_cast<int>(p.fd_gcpg.div(static_cast<uint32_t>(ncol + lane)));
+            const bool gn_f16 = p.act_f16 != 0;
             if (gn_tile) {
               // lane = (row parity hf, 32-bit word w = column pair (2w, 2w+1)): 16 conflict-free word loads cover the
               // 32 x 32 tile; channels-per-group and chunk origins are even, so a column pair never straddles a group
@@ -779,7 +794,7 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
               uint64_t sv = pack2(0.f, 0.f), qv = pack2(0.f, 0.f);
 #pragma unroll
               for (int rr = 0; rr < 16; ++rr) {
-                const uint64_t v = bf16x2_to_f32x2(*reinterpret_cast<const uint32_t*>(colp + rr * 128 + ((u ^ (rr & 3)) << 4)));
+                const uint64_t v = h16x2_to_f32x2(*reinterpret_cast<const uint32_t*>(colp + rr * 128 + ((u ^ (rr & 3)) << 4)), gn_f16);
                 sv = add2(sv, v);
                 qv = fma2(v, v, qv);
               }
@@ -818,8 +833,7 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
               const int cj = lane >> 3, ej = (lane & 7) * 2;
 #pragma unroll 8
               for (int rr = 0; rr < 32; ++rr) {
-                const float v = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(
-                    tile + rr * 64 + ((cj ^ ((rr >> 1) & 3)) << 4) + ej));
+                const float v = load16(tile + rr * 64 + ((cj ^ ((rr >> 1) & 3)) << 4) + ej, gn_f16);
                 s1 += static_cast<double>(v);
                 s2 += static_cast<double>(v * v);
               }
@@ -847,8 +861,7 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
               int gcur = static_cast<int>(p.fd_gcpg.div(static_cast<uint32_t>(ncol)));
               int left = (gcur + 1) * static_cast<int>(p.fd_gcpg.d) - ncol;  // columns until the group ends
               for (int j = 0; j < 32; ++j) {
-                const float v = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(
-                    rowp + (((j >> 3) ^ sw) << 4) + (j & 7) * 2));
+                const float v = load16(rowp + (((j >> 3) ^ sw) << 4) + (j & 7) * 2, gn_f16);
                 s1 += static_cast<double>(v);
                 s2 += static_cast<double>(v * v);
                 if (--left == 0 || j == 31) {
@@ -1117,6 +1130,7 @@ extern "C" int sa_gemm_tap(const sa_gemm_args* a, void* stream_) {
   p.out = a->out;
   p.ldc = a->ldc;
   p.out_f32 = a->out_f32;
+  p.act_f16 = a->act_f16 ? 1 : 0;
 
   const long long ktot_pick = static_cast<long long>(a->ntaps) * (a->c0 + a->c1);
   int bn = a->tile_n ? a->tile_n : pick_tile(p.M, p.N, p.geglu, ktot_pick);

@@ -199,7 +199,8 @@ conv_direct_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int
                    const __nv_bfloat16* __restrict__ w, const float* __restrict__ bias, int Cout,
                    int CoutPad, int ksz, int stride, int pad, int Ho, int Wo, int silu_out,
                    float scale, const __nv_bfloat16* __restrict__ add, int add_from,
-                   __nv_bfloat16* __restrict__ out) {
+                   __nv_bfloat16* __restrict__ out, int f16_) {
+  const bool f16 = f16_ != 0;   // x / w / add / out hold IEEE fp16 instead of bf16
   const int octs = CoutPad >> 3;
   const long long total = static_cast<long long>(N) * Ho * Wo * octs;
   for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
@@ -222,12 +223,12 @@ conv_direct_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int
         const __nv_bfloat16* xp = x + ((static_cast<long long>(n) * H + yi) * W + xi) * Cin;
         const __nv_bfloat16* wp = w + static_cast<long long>((ky * ksz + kx) * Cin) * CoutPad + oc;
         for (int ci = 0; ci < Cin; ++ci) {
-          const float xv = __bfloat162float(xp[ci]);
+          const float xv = load16(xp + ci, f16);
           const uint4 u = __ldg(reinterpret_cast<const uint4*>(wp + static_cast<long long>(ci) * CoutPad));
           const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
-            const float2 f = unpack_bf16x2(ww[t]);
+            const float2 f = unpack16x2(ww[t], f16);
             acc[2 * t] += xv * f.x;
             acc[2 * t + 1] += xv * f.y;
           }
@@ -242,8 +243,9 @@ conv_direct_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int
         if (silu_out) v = silu(v);
         v *= scale;
         if (add && n >= add_from)
-          v += __bfloat162float(add[((static_cast<long long>(n - add_from) * Ho + yo) * Wo + xo) * Cout + oc + t]);
-        out[orow * Cout + oc + t] = __float2bfloat16_rn(v);
+          v += load16(add + ((static_cast<long long>(n - add_from) * Ho + yo) * Wo + xo) * Cout + oc + t, f16);
+        if (f16) reinterpret_cast<__half*>(out)[orow * Cout + oc + t] = __float2half_rn(fminf(fmaxf(v, -65504.0f), 65504.0f));
+        else out[orow * Cout + oc + t] = __float2bfloat16_rn(v);
       }
     }
   }
@@ -315,22 +317,30 @@ __global__ void im2col3x3_c8_kernel(const uint4* __restrict__ in, int N, int H, 
 }
 
 // ------------------------------------------------------------------ layout conversion (boundary)
-// src [N, C, HW] (fp32 or bf16) -> dst bf16 [N, HW, C]
+// src [N, C, HW] (fp32, or 16-bit in the activation format) -> dst 16-bit [N, HW, C]
 template <typename T>
 __global__ void nchw_to_nhwc_kernel(const T* __restrict__ src, int C, int HW,
-                                    __nv_bfloat16* __restrict__ dst) {
+                                    __nv_bfloat16* __restrict__ dst, int f16) {
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
     const int c = c0 + j, p = p0 + threadIdx.x;
-    if (c < C && p < HW) tile[j][threadIdx.x] = static_cast<float>(src[(static_cast<long long>(n) * C + c) * HW + p]);
+    if (c < C && p < HW) {
+      const T* sp = src + (static_cast<long long>(n) * C + c) * HW + p;
+      if constexpr (sizeof(T) == 2) tile[j][threadIdx.x] = load16(sp, f16 != 0);
+      else tile[j][threadIdx.x] = static_cast<float>(*sp);
+    }
   }
   __syncthreads();
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
     const int p = p0 + j, c = c0 + threadIdx.x;
-    if (c < C && p < HW)
-      dst[(static_cast<long long>(n) * HW + p) * C + c] = __float2bfloat16_rn(tile[threadIdx.x][j]);
+    if (c < C && p < HW) {
+      const float v = tile[threadIdx.x][j];
+      const long long o = (static_cast<long long>(n) * HW + p) * C + c;
+      if (f16) reinterpret_cast<__half*>(dst)[o] = __float2half_rn(fminf(fmaxf(v, -65504.0f), 65504.0f));
+      else dst[o] = __float2bfloat16_rn(v);
+    }
   }
 }
 // src fp32 [N, HW, lds] (first C columns) -> dst [N, C, HW] fp32, dst = dst*keep + scale*src
@@ -351,7 +361,8 @@ __global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, int lds, int 
 __global__ void sampler_prepare_kernel(const float* __restrict__ latents,
                                        const float* __restrict__ image_latents,
                                        const int* __restrict__ idx, int nb, int b0, int T, int F, int HW,
-                                       float inv_scale, __nv_bfloat16* __restrict__ out) {
+                                       float inv_scale, __nv_bfloat16* __restrict__ out, int f16_) {
+  const bool f16 = f16_ != 0;
   const long long total = static_cast<long long>(nb) * T * HW;
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -365,8 +376,8 @@ __global__ void sampler_prepare_kernel(const float* __restrict__ latents,
     v[c] = latents[(static_cast<long long>(f) * 4 + c) * HW + p] * inv_scale;
     v[4 + c] = image_latents[((static_cast<long long>(b0 + b) * F + f) * 4 + c) * HW + p];
   }
-  *reinterpret_cast<uint4*>(out + i * 8) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
-                                                      pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  *reinterpret_cast<uint4*>(out + i * 8) = make_uint4(pack16x2(v[0], v[1], f16), pack16x2(v[2], v[3], f16),
+                                                      pack16x2(v[4], v[5], f16), pack16x2(v[6], v[7], f16));
 }
 
 // :673,685: noise[b0 + b, idx[t]] += unet_out[b, t] * weight[t]   (unet_out: fp32 NHWC, ld = ldo)
@@ -492,7 +503,7 @@ extern "C" int sa_sinusoid(const float* t, int32_t n, int32_t dim, float* out, v
 extern "C" int sa_conv_direct(const void* x, int32_t n, int32_t h, int32_t w, int32_t cin,
                               const void* wt, const float* bias, int32_t cout, int32_t cout_pad,
                               int32_t ksz, int32_t stride, int32_t pad, int32_t silu_out, float scale,
-                              const void* add, int32_t add_from, void* out, void* stream_) {
+                              const void* add, int32_t add_from, void* out, int32_t act_f16, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!x || !wt || !out) return fail(SA_ERR_INVALID, "sa_conv_direct: null pointer");
   if (cout_pad % 8 || cout_pad < cout) return fail(SA_ERR_INVALID, "sa_conv_direct: cout_pad must be a multiple of 8");
@@ -501,7 +512,7 @@ extern "C" int sa_conv_direct(const void* x, int32_t n, int32_t h, int32_t w, in
   conv_direct_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(x), n, h, w, cin, static_cast<const __nv_bfloat16*>(wt), bias, cout,
       cout_pad, ksz, stride, pad, ho, wo, silu_out, scale, static_cast<const __nv_bfloat16*>(add), add_from,
-      static_cast<__nv_bfloat16*>(out));
+      static_cast<__nv_bfloat16*>(out), act_f16);
   SA_CUDA_CHECK(cudaGetLastError());
   return SA_OK;
 }
@@ -551,16 +562,16 @@ extern "C" int sa_im2col3x3_c8(const void* in, int32_t n, int32_t h, int32_t w, 
 }
 
 extern "C" int sa_nchw_to_nhwc(const void* src, int32_t src_is_bf16, int32_t n, int32_t c, int32_t hw,
-                               void* dst, void* stream_) {
+                               void* dst, int32_t act_f16, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!src || !dst) return fail(SA_ERR_INVALID, "sa_nchw_to_nhwc: null pointer");
   dim3 grid((hw + 31) / 32, (c + 31) / 32, n), block(32, 8);
   if (src_is_bf16)
     nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(src), c, hw,
-                                                                   static_cast<__nv_bfloat16*>(dst));
+                                                                   static_cast<__nv_bfloat16*>(dst), act_f16);
   else
     nchw_to_nhwc_kernel<float><<<grid, block, 0, stream>>>(static_cast<const float*>(src), c, hw,
-                                                           static_cast<__nv_bfloat16*>(dst));
+                                                           static_cast<__nv_bfloat16*>(dst), act_f16);
   SA_CUDA_CHECK(cudaGetLastError());
   return SA_OK;
 }
@@ -577,13 +588,13 @@ extern "C" int sa_nhwc_to_nchw_f32(const float* src, int32_t lds, int32_t n, int
 
 extern "C" int sa_sampler_prepare(const float* latents, const float* image_latents, const int32_t* idx,
                                   int32_t nb, int32_t b0, int32_t t, int32_t f, int32_t hw, float sigma,
-                                  void* out, void* stream_) {
+                                  void* out, int32_t act_f16, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!latents || !image_latents || !idx || !out) return fail(SA_ERR_INVALID, "sa_sampler_prepare: null pointer");
   const long long total = static_cast<long long>(nb) * t * hw;
   const float inv = 1.0f / sqrtf(sigma * sigma + 1.0f);
   sampler_prepare_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
-      latents, image_latents, idx, nb, b0, t, f, hw, inv, static_cast<__nv_bfloat16*>(out));
+      latents, image_latents, idx, nb, b0, t, f, hw, inv, static_cast<__nv_bfloat16*>(out), act_f16);
   SA_CUDA_CHECK(cudaGetLastError());
   return SA_OK;
 }

@@ -12,19 +12,20 @@
 
 namespace sa {
 
-__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
+// `f16`: the 16-bit tensors hold IEEE fp16 instead of bf16 (warp-uniform run-time flag; pointers stay typed bf16)
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8], bool f16) {
   const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
   const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
-    const float2 f = unpack_bf16x2(w[t]);
+    const float2 f = unpack16x2(w[t], f16);
     v[2 * t] = f.x;
     v[2 * t + 1] = f.y;
   }
 }
-__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
-  *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
-                                            pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8], bool f16) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(pack16x2(v[0], v[1], f16), pack16x2(v[2], v[3], f16),
+                                            pack16x2(v[4], v[5], f16), pack16x2(v[6], v[7], f16));
 }
 
 // ------------------------------------------------------------------ GroupNorm statistics
@@ -32,7 +33,7 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
 __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x0,
                                 const __nv_bfloat16* __restrict__ x1, int C0, int C1, int ld0,
                                 int ld1, long long P, int cpg, int rows_per_cta,
-                                double* __restrict__ stats) {
+                                double* __restrict__ stats, int f16) {
   __shared__ double sm[32][2];
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
   if (tid < 64) sm[tid >> 1][tid & 1] = 0.0;
@@ -61,7 +62,7 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x0,
     for (; r + 3 * step < r1; r += 4 * step) {
       float v[4][8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) load8(src + (ns * P + r + u * step) * ld, v[u]);
+      for (int u = 0; u < 4; ++u) load8(src + (ns * P + r + u * step) * ld, v[u], f16);
 #pragma unroll
       for (int u = 0; u < 4; ++u)
 #pragma unroll
@@ -72,7 +73,7 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x0,
     }
     for (; r < r1; r += step) {
       float v[8];
-      load8(src + (ns * P + r) * ld, v);
+      load8(src + (ns * P + r) * ld, v, f16);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         s[k] += v[k];
@@ -107,7 +108,7 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0,
                                 int ld1, long long P, int cpg, int rows_per_cta,
                                 const double* __restrict__ stats, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, float eps, int do_silu,
-                                __nv_bfloat16* __restrict__ out, int ldo) {
+                                __nv_bfloat16* __restrict__ out, int ldo, int f16) {
   const int c = threadIdx.x * 8;
   const long long ns = blockIdx.y;
   const double n = static_cast<double>(P) * cpg;
@@ -140,7 +141,7 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0,
   for (; r + 3 * step < r1; r += 4 * step) {
     float v[4][8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) load8(src + (ns * P + r + u * step) * ld, v[u]);
+    for (int u = 0; u < 4; ++u) load8(src + (ns * P + r + u * step) * ld, v[u], f16);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
 #pragma unroll
@@ -150,12 +151,12 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0,
         v[u][k] = o.x;
         v[u][k + 1] = o.y;
       }
-      store8(out + (ns * P + r + u * step) * ldo + c, v[u]);
+      store8(out + (ns * P + r + u * step) * ldo + c, v[u], f16);
     }
   }
   for (; r < r1; r += step) {
     float v[8];
-    load8(src + (ns * P + r) * ld, v);
+    load8(src + (ns * P + r) * ld, v, f16);
 #pragma unroll
     for (int k = 0; k < 8; k += 2) {
       const uint64_t y2 = fma2(pack2(v[k], v[k + 1]), pack2(a[k], a[k + 1]), pack2(b[k], b[k + 1]));
@@ -163,7 +164,7 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0,
       v[k] = o.x;
       v[k + 1] = o.y;
     }
-    store8(out + (ns * P + r) * ldo + c, v);
+    store8(out + (ns * P + r) * ldo + c, v, f16);
   }
 }
 
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const __nv_bfloat16* __restrict__ x, int ldx, long long M, int C,
                  const float* __restrict__ addv, int rows_per_group,
                  __nv_bfloat16* __restrict__ x_out, int ldxo, const float* __restrict__ gamma,
-                 const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y, int ldy) {
+                 const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y, int ldy, int f16) {
   constexpr int RPW = 32 / LPR;  // rows per warp
   const int lane = threadIdx.x & 31;
   const int sub = lane / LPR, l = lane % LPR;
@@ -191,17 +192,17 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, int ldx, long long M, int 
 #pragma unroll
   for (int o = 0; o < OPL; ++o) {
     const int oc = l + LPR * o;
-    load8(x + rr * ldx + oc * 8, v[o]);
+    load8(x + rr * ldx + oc * 8, v[o], f16);
     if (av) {
       const float4 a0 = __ldg(reinterpret_cast<const float4*>(av + oc * 8));
       const float4 a1 = __ldg(reinterpret_cast<const float4*>(av + oc * 8 + 4));
       v[o][0] += a0.x; v[o][1] += a0.y; v[o][2] += a0.z; v[o][3] += a0.w;
       v[o][4] += a1.x; v[o][5] += a1.y; v[o][6] += a1.z; v[o][7] += a1.w;
       if (x_out) {
-        if (active) store8(x_out + rr * ldxo + oc * 8, v[o]);
-        // keep the bf16-rounded value: it is what every later consumer of the stream reads
+        if (active) store8(x_out + rr * ldxo + oc * 8, v[o], f16);
+        // keep the rounded value: it is what every later consumer of the stream reads
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[o][k] = __bfloat162float(__float2bfloat16_rn(v[o][k]));
+        for (int k = 0; k < 8; ++k) v[o][k] = round16(v[o][k], f16);
       }
     }
 #pragma unroll
@@ -235,7 +236,7 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, int ldx, long long M, int 
     float o8[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) o8[k] = fmaf((v[o][k] - mean) * rstd, g[k], bb[k]);
-    store8(y + rr * ldy + oc * 8, o8);
+    store8(y + rr * ldy + oc * 8, o8, f16);
   }
 }
 
@@ -260,26 +261,26 @@ struct LnStream {
   static constexpr int SMEM = LN_ST * STAGE_BYTES + 2 * LN_ST * 8 + 128;
 };
 
-__device__ __forceinline__ void load8s(const uint8_t* p, float (&v)[8]) {
+__device__ __forceinline__ void load8s(const uint8_t* p, float (&v)[8], bool f16) {
   const uint4 q = *reinterpret_cast<const uint4*>(p);
   const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
-    const float2 f = unpack_bf16x2(w[t]);
+    const float2 f = unpack16x2(w[t], f16);
     v[2 * t] = f.x;
     v[2 * t + 1] = f.y;
   }
 }
-__device__ __forceinline__ void store8s(uint8_t* p, const float (&v)[8]) {
-  *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
-                                            pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+__device__ __forceinline__ void store8s(uint8_t* p, const float (&v)[8], bool f16) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(pack16x2(v[0], v[1], f16), pack16x2(v[2], v[3], f16),
+                                            pack16x2(v[4], v[5], f16), pack16x2(v[6], v[7], f16));
 }
 
 template <int LPR, int OPL, bool XOUT>
 __global__ void __launch_bounds__(32 * (LN_CW + 1))
 layernorm_stream_kernel(const __nv_bfloat16* __restrict__ x, long long M, const float* __restrict__ addv,
                         int rows_per_group, __nv_bfloat16* __restrict__ x_out, const float* __restrict__ gamma,
-                        const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y) {
+                        const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y, int f16) {
   using L = LnStream<LPR, OPL, XOUT>;
   constexpr int C = L::C;
   extern __shared__ uint8_t ln_smem_raw[];
@@ -348,7 +349,7 @@ layernorm_stream_kernel(const __nv_bfloat16* __restrict__ x, long long M, const 
       for (int o = 0; o < OPL; ++o) {
         const int oc = l + LPR * o;
         if (active) {
-          load8s(base + oc * 16, v[o]);
+          load8s(base + oc * 16, v[o], f16);
         } else {
 #pragma unroll
           for (int k = 0; k < 8; ++k) v[o][k] = 0.f;
@@ -359,10 +360,10 @@ layernorm_stream_kernel(const __nv_bfloat16* __restrict__ x, long long M, const 
           v[o][0] += a0.x; v[o][1] += a0.y; v[o][2] += a0.z; v[o][3] += a0.w;
           v[o][4] += a1.x; v[o][5] += a1.y; v[o][6] += a1.z; v[o][7] += a1.w;
           if (XOUT) {
-            store8s(base + L::TILE_BYTES + oc * 16, v[o]);
-            // keep the bf16-rounded value: it is what every later consumer of the stream reads
+            store8s(base + L::TILE_BYTES + oc * 16, v[o], f16);
+            // keep the rounded value: it is what every later consumer of the stream reads
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[o][k] = __bfloat162float(__float2bfloat16_rn(v[o][k]));
+            for (int k = 0; k < 8; ++k) v[o][k] = round16(v[o][k], f16);
           }
         }
 #pragma unroll
@@ -396,7 +397,7 @@ layernorm_stream_kernel(const __nv_bfloat16* __restrict__ x, long long M, const 
           float o8[8];
 #pragma unroll
           for (int k = 0; k < 8; ++k) o8[k] = fmaf((v[o][k] - mean) * rstd, g[k], bb[k]);
-          store8s(base + oc * 16, o8);
+          store8s(base + oc * 16, o8, f16);
         }
       }
       fence_proxy_async();  // our generic-proxy writes must be visible to the bulk store
@@ -430,6 +431,7 @@ struct GnStreamP {
   float eps;
   int do_silu;
   __nv_bfloat16* out;       // apply only, dense [rows, C0 + C1]
+  int f16;                  // 16-bit tensors are IEEE fp16 instead of bf16
 };
 
 template <bool APPLY>
@@ -583,7 +585,7 @@ gn_stream_kernel(const GnStreamP p) {
           uint8_t* dst = two_src ? slot + in_bytes + oc * 16 : slot + oc * 16;
           for (int r = rl; r < p.R; r += rl_n) {
             float v[8];
-            load8s(src + r * src_ld, v);
+            load8s(src + r * src_ld, v, p.f16 != 0);
             if (APPLY) {
               // packed fp32x2 lanes; silu2: one MUFU (tanh) per element
               uint32_t w[4];
@@ -591,11 +593,7 @@ gn_stream_kernel(const GnStreamP p) {
               for (int k = 0; k < 8; k += 2) {
                 const uint64_t y2 = fma2(pack2(v[k], v[k + 1]), pack2(a[cs][k], a[cs][k + 1]),
                                          pack2(b[cs][k], b[cs][k + 1]));
-                if (p.do_silu) {
-                  w[k >> 1] = pack_bf16x2_f2(silu2(y2));
-                } else {
-                  w[k >> 1] = pack_bf16x2_f2(y2);
-                }
+                w[k >> 1] = pack16x2_f2(p.do_silu ? silu2(y2) : y2, p.f16 != 0);
               }
               *reinterpret_cast<uint4*>(dst + r * (C * 2)) = make_uint4(w[0], w[1], w[2], w[3]);
             } else {
@@ -644,7 +642,7 @@ static int gn_geometry(int C, long long P, int ns, dim3* block, dim3* grid, int*
 static int groupnorm_impl(const void* x0, const void* x1, int32_t c0, int32_t c1, int32_t ld0,
                           int32_t ld1, int64_t rows_per_stat, int32_t ns, const float* gamma,
                           const float* beta, float eps, int32_t do_silu, void* stats_ws,
-                          void* out, int32_t ldo, void* stream_, bool have_stats) {
+                          void* out, int32_t ldo, void* stream_, bool have_stats, int32_t f16) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int C = c0 + c1;
   if (!x0 || !out || !stats_ws || !gamma || !beta) return fail(SA_ERR_INVALID, "sa_groupnorm: null pointer");
@@ -679,6 +677,7 @@ static int groupnorm_impl(const void* x0, const void* x1, int32_t c0, int32_t c1
       sp.eps = eps;
       sp.do_silu = do_silu;
       sp.out = static_cast<__nv_bfloat16*>(out);
+      sp.f16 = f16;
       const int tile = R * C * 2;
       const int smem_stats = GN_ST * tile + 2 * GN_ST * 8 + 64 * 8 + 128;
       const int smem_apply = GN_ST * tile * (c1 > 0 ? 2 : 1) + 2 * GN_ST * 8 + 64 * 8 + 128;
@@ -706,13 +705,13 @@ static int groupnorm_impl(const void* x0, const void* x1, int32_t c0, int32_t c1
   if (!have_stats) {
     gn_stats_kernel<<<grid, block, 0, stream>>>(
         static_cast<const __nv_bfloat16*>(x0), static_cast<const __nv_bfloat16*>(x1), c0, c1, ld0, ld1,
-        rows_per_stat, cpg, rpc, static_cast<double*>(stats_ws));
+        rows_per_stat, cpg, rpc, static_cast<double*>(stats_ws), f16);
     SA_CUDA_CHECK(cudaGetLastError());
   }
   gn_apply_kernel<<<grid, block, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(x0), static_cast<const __nv_bfloat16*>(x1), c0, c1, ld0, ld1,
       rows_per_stat, cpg, rpc, static_cast<const double*>(stats_ws), gamma, beta, eps, do_silu,
-      static_cast<__nv_bfloat16*>(out), ldo);
+      static_cast<__nv_bfloat16*>(out), ldo, f16);
   SA_CUDA_CHECK(cudaGetLastError());
   return SA_OK;
 }
@@ -720,22 +719,22 @@ static int groupnorm_impl(const void* x0, const void* x1, int32_t c0, int32_t c1
 extern "C" int sa_groupnorm(const void* x0, const void* x1, int32_t c0, int32_t c1, int32_t ld0,
                             int32_t ld1, int64_t rows_per_stat, int32_t ns, const float* gamma,
                             const float* beta, float eps, int32_t do_silu, void* stats_ws,
-                            void* out, int32_t ldo, void* stream_) {
+                            void* out, int32_t ldo, int32_t act_f16, void* stream_) {
   return groupnorm_impl(x0, x1, c0, c1, ld0, ld1, rows_per_stat, ns, gamma, beta, eps, do_silu, stats_ws, out, ldo,
-                        stream_, false);
+                        stream_, false, act_f16);
 }
 
 extern "C" int sa_groupnorm_apply(const void* x0, const void* x1, int32_t c0, int32_t c1, int32_t ld0,
                                   int32_t ld1, int64_t rows_per_stat, int32_t ns, const float* gamma,
                                   const float* beta, float eps, int32_t do_silu, const void* stats_ws,
-                                  void* out, int32_t ldo, void* stream_) {
+                                  void* out, int32_t ldo, int32_t act_f16, void* stream_) {
   return groupnorm_impl(x0, x1, c0, c1, ld0, ld1, rows_per_stat, ns, gamma, beta, eps, do_silu,
-                        const_cast<void*>(stats_ws), out, ldo, stream_, true);
+                        const_cast<void*>(stats_ws), out, ldo, stream_, true, act_f16);
 }
 
 extern "C" int sa_layernorm(const void* x, int32_t ldx, int64_t rows, int32_t c, const float* addv,
                             int32_t rows_per_group, void* x_out, int32_t ldxo, const float* gamma,
-                            const float* beta, float eps, void* y, int32_t ldy, void* stream_) {
+                            const float* beta, float eps, void* y, int32_t ldy, int32_t act_f16, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!x || !y || !gamma || !beta) return fail(SA_ERR_INVALID, "sa_layernorm: null pointer");
   if (c % 64 || c > 2048 || c <= 0) return fail(SA_ERR_INVALID, "sa_layernorm: C=%d unsupported (multiple of 64, <= 2048)", c);
@@ -773,14 +772,14 @@ extern "C" int sa_layernorm(const void* x, int32_t ldx, int64_t rows, int32_t c,
     long long g = static_cast<long long>(n_sm) * (L::SMEM <= 110 * 1024 ? 2 : 1);                         \
     if (g > nt) g = nt;                                                                                   \
     layernorm_stream_kernel<LPR, OPL, XO><<<static_cast<unsigned>(g), 32 * (LN_CW + 1), L::SMEM, stream>>>( \
-        xp, rows, addv, rpg, xo, gamma, beta, eps, yp);                                                   \
+        xp, rows, addv, rpg, xo, gamma, beta, eps, yp, act_f16);                                          \
   } while (0)
 #define SA_LN(LPR, OPL)                                                                               \
   if (dense && LnStream<LPR, OPL, true>::SMEM <= 227 * 1024) {                                        \
     if (xo) SA_LN_STREAM(LPR, OPL, true); else SA_LN_STREAM(LPR, OPL, false);                         \
   } else                                                                                              \
     layernorm_kernel<LPR, OPL><<<grid, warps * 32, 0, stream>>>(xp, ldx, rows, c, addv, rpg, xo, ldxo, \
-                                                                gamma, beta, eps, yp, ldy)
+                                                                gamma, beta, eps, yp, ldy, act_f16)
 #define SA_LN_ROW(LPR)                                                         \
   switch (opl) {                                                               \
     case 1: SA_LN(LPR, 1); break;                                              \

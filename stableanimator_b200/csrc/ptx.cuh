@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -528,6 +529,40 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(t);
+}
+
+// ---------------------------------------------------------------- 16-bit activation format (bf16 or IEEE fp16)
+// The reference's default inference dtype is fp16 (inference_basic.py:486); every kernel that touches 16-bit activations
+// takes the format as a warp-uniform run-time flag.  fp16 stores saturate at +-65504 instead of producing inf.
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t u) {
+  __half2 t = *reinterpret_cast<__half2*>(&u);
+  return __half22float2(t);
+}
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float2 unpack16x2(uint32_t u, bool f16) { return f16 ? unpack_f16x2(u) : unpack_bf16x2(u); }
+__device__ __forceinline__ uint32_t pack16x2(float a, float b, bool f16) {
+  return f16 ? pack_f16x2_sat(a, b) : pack_bf16x2(a, b);
+}
+__device__ __forceinline__ uint64_t h16x2_to_f32x2(uint32_t w, bool f16) {
+  if (f16) {
+    const float2 f = unpack_f16x2(w);
+    return pack2(f.x, f.y);
+  }
+  return bf16x2_to_f32x2(w);
+}
+__device__ __forceinline__ uint32_t pack16x2_f2(uint64_t v, bool f16) {
+  return f16 ? pack_f16x2_sat_f2(v) : pack_bf16x2_f2(v);
+}
+__device__ __forceinline__ float load16(const void* p, bool f16) {
+  return f16 ? __half2float(*reinterpret_cast<const __half*>(p)) : __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(p));
+}
+// round a float to the activation format and back (the value later consumers of a stored tensor read)
+__device__ __forceinline__ float round16(float v, bool f16) {
+  return f16 ? __half2float(__float2half_rn(fminf(fmaxf(v, -65504.0f), 65504.0f))) : __bfloat162float(__float2bfloat16_rn(v));
 }
 
 }  // namespace sa

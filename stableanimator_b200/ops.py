@@ -65,11 +65,22 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
-def _chk_bf16(t: torch.Tensor, name: str) -> None:
-    if t.dtype != torch.bfloat16 or not t.is_cuda:
-        raise ValueError(f"{name} must be a CUDA bf16 tensor, got {t.dtype} on {t.device}")
+ACT_DTYPES = (torch.bfloat16, torch.float16)
+
+
+def _chk_bf16(t: torch.Tensor, name: str, like: Optional[torch.Tensor] = None) -> None:
+    """A 16-bit activation / weight tensor: CUDA, bf16 (default mode) or fp16 (the reference's default inference dtype,
+    inference_basic.py:486), channel-innermost; ``like``: must share that tensor's format."""
+    if t.dtype not in ACT_DTYPES or not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA bf16 / fp16 tensor, got {t.dtype} on {t.device}")
+    if like is not None and t.dtype != like.dtype:
+        raise ValueError(f"{name} is {t.dtype} but the call runs in {like.dtype}: all 16-bit operands share one format")
     if t.stride(-1) != 1:
         raise ValueError(f"{name} must be channel-innermost (stride(-1) == 1)")
+
+
+def _f16(t: torch.Tensor) -> int:
+    return int(t.dtype == torch.float16)
 
 
 def _chk_f32(t: Optional[torch.Tensor], name: str) -> None:
@@ -116,7 +127,7 @@ def gemm_tap(
     ``w``: bf16 ``[N, ntaps*(C0+C1)]``.
     """
     _chk_bf16(a0, "a0")
-    _chk_bf16(w, "w")
+    _chk_bf16(w, "w", a0)
     c0 = a0.shape[-1]
     lda0 = a0.stride(-2) if a0.dim() >= 2 else c0
     src_rows = a0.numel() // c0
@@ -125,7 +136,7 @@ def gemm_tap(
     rows = src_rows // (in_stride * in_stride)   # output positions
     c1, lda1 = 0, 0
     if a1 is not None:
-        _chk_bf16(a1, "a1")
+        _chk_bf16(a1, "a1", a0)
         c1 = a1.shape[-1]
         lda1 = a1.stride(-2)
         if a1.numel() // c1 != src_rows:
@@ -146,7 +157,9 @@ def gemm_tap(
     n_out = n_mma // 2 if geglu else n_mma
     if out is None:
         out = torch.empty((rows, n_out), device=a0.device,
-                          dtype=torch.float32 if out_f32 else torch.bfloat16)
+                          dtype=torch.float32 if out_f32 else a0.dtype)
+    elif out.dtype != torch.float32 and out.dtype != a0.dtype:
+        raise ValueError(f"out is {out.dtype} but the call runs in {a0.dtype}")
     _chk_f32(bias, "bias")
     _chk_f32(row_scale, "row_scale")
     args = GemmArgs()
@@ -164,12 +177,13 @@ def gemm_tap(
         args.row_bias, args.ldrb = row_bias.data_ptr(), row_bias.stride(0)
     args.rows_per_group = rows_per_group
     if residual is not None:
-        _chk_bf16(residual, "residual")
+        _chk_bf16(residual, "residual", a0)
         args.residual, args.ldr = residual.data_ptr(), residual.stride(-2)
     if blend_x is not None:
-        _chk_bf16(blend_x, "blend_x")
+        _chk_bf16(blend_x, "blend_x", a0)
         args.blend_x, args.ldx = blend_x.data_ptr(), blend_x.stride(-2)
     args.alpha = float(alpha)
+    args.act_f16 = _f16(a0)
     args.geglu = int(geglu)
     args.out, args.ldc = out.data_ptr(), out.stride(-2)
     if out.dim() == 4 and not out.is_contiguous():
@@ -203,8 +217,8 @@ def ff_fused(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, w1: torch
     """``out = W2 . GEGLU(W1 . LN(x + addv) + b1) + b2 + (x + addv)`` (optionally alpha-blended with ``blend_x``) in ONE
     kernel -- see ``sa_ff_fused`` in include/sa_b200.h.  ``w1`` / ``b1`` are GEGLU-interleaved (:func:`interleave_geglu`)."""
     _chk_bf16(x, "x")
-    _chk_bf16(w1, "w1")
-    _chk_bf16(w2, "w2")
+    _chk_bf16(w1, "w1", x)
+    _chk_bf16(w2, "w2", x)
     c = x.shape[-1]
     rows = x.numel() // c
     if c not in FF_FUSED_CHANNELS:
@@ -214,16 +228,17 @@ def ff_fused(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, w1: torch
     for t, nm in ((gamma, "gamma"), (beta, "beta"), (b1, "b1"), (b2, "b2"), (addv, "addv")):
         _chk_f32(t, nm)
     if out is None:
-        out = torch.empty((rows, c), device=x.device, dtype=torch.bfloat16)
+        out = torch.empty((rows, c), device=x.device, dtype=x.dtype)
     a = FfArgs()
     a.x, a.ldx, a.m, a.c = x.data_ptr(), x.stride(-2), rows, c
     a.addv, a.rows_per_group = _ptr(addv), int(rows_per_group)
     a.gamma, a.beta, a.eps = gamma.data_ptr(), beta.data_ptr(), float(eps)
     a.w1, a.b1, a.w2, a.b2 = w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr()
     if blend_x is not None:
-        _chk_bf16(blend_x, "blend_x")
+        _chk_bf16(blend_x, "blend_x", x)
         a.blend_x, a.ldbx = blend_x.data_ptr(), blend_x.stride(-2)
     a.alpha = float(alpha)
+    a.act_f16 = _f16(x)
     a.out, a.ldc = out.data_ptr(), out.stride(-2)
     check(lib().sa_ff_fused(C.byref(a), _stream()), "sa_ff_fused")
     return out
@@ -276,14 +291,16 @@ def attn_spatial(qkv: torch.Tensor, frames: int, s: int, heads: int,
     _chk_bf16(qkv, "qkv")
     c = heads * 64
     if out is None:
-        out = torch.empty((frames * s, c), device=qkv.device, dtype=torch.bfloat16)
+        out = torch.empty((frames * s, c), device=qkv.device, dtype=qkv.dtype)
     check(lib().sa_attn_spatial(qkv.data_ptr(), qkv.stride(-2), frames, s, c, heads, out.data_ptr(),
-                                out.stride(-2), _stream()), "sa_attn_spatial")
+                                out.stride(-2), _f16(qkv), _stream()), "sa_attn_spatial")
     return out
 
 
 def v_block_to_f16_(qkv: torch.Tensor, c: int) -> torch.Tensor:
     """In place: re-encode the v block (columns >= 2C) of an all-bf16 q|k|v tensor as fp16 bit patterns."""
+    if qkv.dtype == torch.float16:
+        return qkv
     v = qkv[:, 2 * c:3 * c]
     v.copy_(v.float().clamp(-65504.0, 65504.0).half().view(torch.bfloat16))
     return qkv
@@ -295,9 +312,9 @@ def attn_temporal(qkv: torch.Tensor, b: int, f: int, s: int, heads: int,
     _chk_bf16(qkv, "qkv")
     c = heads * 64
     if out is None:
-        out = torch.empty((b * f * s, c), device=qkv.device, dtype=torch.bfloat16)
+        out = torch.empty((b * f * s, c), device=qkv.device, dtype=qkv.dtype)
     check(lib().sa_attn_temporal(qkv.data_ptr(), qkv.stride(-2), b, f, s, c, heads, out.data_ptr(),
-                                 out.stride(-2), _stream()), "sa_attn_temporal")
+                                 out.stride(-2), _f16(qkv), _stream()), "sa_attn_temporal")
     return out
 
 
@@ -314,9 +331,9 @@ def attn_id(q: torch.Tensor, ik: torch.Tensor, iv: torch.Tensor, b: int, f: int,
     if ik.stride() != iv.stride():
         raise ValueError("ik and iv must share strides")
     if out is None:
-        out = torch.empty((b * f * s, c), device=q.device, dtype=torch.bfloat16)
+        out = torch.empty((b * f * s, c), device=q.device, dtype=q.dtype)
     check(lib().sa_attn_id(q.data_ptr(), q.stride(-2), ik.data_ptr(), iv.data_ptr(), ik.stride(1), ik.stride(0),
-                           b, f, s, c, heads, 4, out.data_ptr(), out.stride(-2), stats.data_ptr(), _stream()),
+                           b, f, s, c, heads, 4, out.data_ptr(), out.stride(-2), stats.data_ptr(), _f16(q), _stream()),
           "sa_attn_id")
     return out
 
@@ -346,7 +363,7 @@ def groupnorm(x0: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: fl
     rows = x0.numel() // c0
     c1, ld1 = 0, 0
     if x1 is not None:
-        _chk_bf16(x1, "x1")
+        _chk_bf16(x1, "x1", x0)
         c1, ld1 = x1.shape[-1], x1.stride(-2)
     ns = rows // rows_per_stat
     if ns * rows_per_stat != rows:
@@ -356,13 +373,13 @@ def groupnorm(x0: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: fl
     if stats_ws is None:
         stats_ws = torch.empty((ns, 32, 2), device=x0.device, dtype=torch.float64)
     if out is None:
-        out = torch.empty((rows, c0 + c1), device=x0.device, dtype=torch.bfloat16)
+        out = torch.empty((rows, c0 + c1), device=x0.device, dtype=x0.dtype)
     _chk_f32(gamma, "gamma")
     _chk_f32(beta, "beta")
     fn, what = (lib().sa_groupnorm_apply, "sa_groupnorm_apply") if stats_ready else (lib().sa_groupnorm, "sa_groupnorm")
     check(fn(x0.data_ptr(), _ptr(x1), c0, c1, x0.stride(-2), ld1, rows_per_stat, ns,
              gamma.data_ptr(), beta.data_ptr(), float(eps), int(silu), stats_ws.data_ptr(),
-             out.data_ptr(), out.stride(-2), _stream()), what)
+             out.data_ptr(), out.stride(-2), _f16(x0), _stream()), what)
     return out
 
 
@@ -374,11 +391,11 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, addv:
     c = x.shape[-1]
     rows = x.numel() // c
     if out is None:
-        out = torch.empty((rows, c), device=x.device, dtype=torch.bfloat16)
+        out = torch.empty((rows, c), device=x.device, dtype=x.dtype)
     _chk_f32(addv, "addv")
     check(lib().sa_layernorm(x.data_ptr(), x.stride(-2), rows, c, _ptr(addv), rows_per_group, _ptr(x_out),
                              0 if x_out is None else x_out.stride(-2), gamma.data_ptr(), beta.data_ptr(),
-                             float(eps), out.data_ptr(), out.stride(-2), _stream()), "sa_layernorm")
+                             float(eps), out.data_ptr(), out.stride(-2), _f16(x), _stream()), "sa_layernorm")
     return out
 
 
@@ -391,6 +408,8 @@ def small_linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] 
     if x.dtype != torch.float32 or x.stride(-1) != 1:
         raise ValueError("x must be fp32 with unit inner stride")
     _chk_bf16(w, "w")
+    if w.dtype != torch.bfloat16:
+        raise ValueError("small_linear weights are bf16 in both activation modes")
     m, k = x.shape
     n = w.shape[0]
     if out is None:
@@ -418,14 +437,14 @@ def conv_direct(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor],
                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """x bf16 [n, h, w, cin] (NHWC); wt bf16 [k*k*cin, cout_pad] -> bf16 [n, ho, wo, cout]."""
     _chk_bf16(x, "x")
-    _chk_bf16(wt, "wt")
+    _chk_bf16(wt, "wt", x)
     n, h, w, cin = x.shape
     ho, wo = (h + 2 * pad - ksz) // stride + 1, (w + 2 * pad - ksz) // stride + 1
     if out is None:
-        out = torch.empty((n, ho, wo, cout), device=x.device, dtype=torch.bfloat16)
+        out = torch.empty((n, ho, wo, cout), device=x.device, dtype=x.dtype)
     check(lib().sa_conv_direct(x.data_ptr(), n, h, w, cin, wt.data_ptr(), _ptr(bias), cout, wt.shape[1], ksz,
                                stride, pad, int(silu), float(scale), _ptr(add), add_from, out.data_ptr(),
-                               _stream()), "sa_conv_direct")
+                               _f16(x), _stream()), "sa_conv_direct")
     return out
 
 
@@ -434,7 +453,7 @@ def upsample2x(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Ten
     _chk_bf16(x, "x")
     n, h, w, c = x.shape
     if out is None:
-        out = torch.empty((n, 2 * h, 2 * w, c), device=x.device, dtype=torch.bfloat16)
+        out = torch.empty((n, 2 * h, 2 * w, c), device=x.device, dtype=x.dtype)
     check(lib().sa_upsample2x(x.data_ptr(), n, h, w, c, out.data_ptr(), _stream()), "sa_upsample2x")
     return out
 
@@ -445,7 +464,7 @@ def im2col_s2(x: torch.Tensor, out: Optional[torch.Tensor] = None, pad: int = 1)
     _chk_bf16(x, "x")
     n, h, w, c = x.shape
     if out is None:
-        out = torch.empty((n * (h // 2) * (w // 2), 9 * c), device=x.device, dtype=torch.bfloat16)
+        out = torch.empty((n * (h // 2) * (w // 2), 9 * c), device=x.device, dtype=x.dtype)
     if pad == 1:
         check(lib().sa_im2col_s2(x.data_ptr(), n, h, w, c, out.data_ptr(), _stream()), "sa_im2col_s2")
     else:
@@ -461,21 +480,21 @@ def im2col3x3_c8(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.T
     if c != 8 or not x.is_contiguous():
         raise ValueError("x must be contiguous [n, h, w, 8]")
     if out is None:
-        out = torch.empty((n * h * w, 128), device=x.device, dtype=torch.bfloat16)
+        out = torch.empty((n * h * w, 128), device=x.device, dtype=x.dtype)
     check(lib().sa_im2col3x3_c8(x.data_ptr(), n, h, w, out.data_ptr(), _stream()), "sa_im2col3x3_c8")
     return out
 
 
 @_launcher("layout")
-def nchw_to_nhwc(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """[n, c, h, w] fp32/bf16 contiguous -> bf16 [n, h, w, c]."""
-    if not x.is_contiguous() or x.dtype not in (torch.float32, torch.bfloat16):
-        raise ValueError("x must be contiguous fp32/bf16 NCHW")
+def nchw_to_nhwc(x: torch.Tensor, out: Optional[torch.Tensor] = None, dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    """[n, c, h, w] contiguous, fp32 or already in the activation format ``dtype`` -> ``dtype`` [n, h, w, c]."""
+    if dtype not in ACT_DTYPES or not x.is_contiguous() or x.dtype not in (torch.float32, dtype):
+        raise ValueError(f"x must be contiguous NCHW in fp32 or {dtype}")
     n, c, h, w = x.shape
     if out is None:
-        out = torch.empty((n, h, w, c), device=x.device, dtype=torch.bfloat16)
-    check(lib().sa_nchw_to_nhwc(x.data_ptr(), int(x.dtype == torch.bfloat16), n, c, h * w, out.data_ptr(),
-                                _stream()), "sa_nchw_to_nhwc")
+        out = torch.empty((n, h, w, c), device=x.device, dtype=dtype)
+    check(lib().sa_nchw_to_nhwc(x.data_ptr(), int(x.dtype != torch.float32), n, c, h * w, out.data_ptr(),
+                                int(dtype == torch.float16), _stream()), "sa_nchw_to_nhwc")
     return out
 
 
@@ -494,7 +513,7 @@ def nhwc_to_nchw_f32(x: torch.Tensor, n: int, c: int, hw: int, out: Optional[tor
 @_launcher("sampler")
 def sampler_prepare(latents, image_latents, idx, nb, b0, f, hw, sigma, out) -> None:
     check(lib().sa_sampler_prepare(latents.data_ptr(), image_latents.data_ptr(), idx.data_ptr(), nb, b0,
-                                   idx.numel(), f, hw, float(sigma), out.data_ptr(), _stream()),
+                                   idx.numel(), f, hw, float(sigma), out.data_ptr(), _f16(out), _stream()),
           "sa_sampler_prepare")
 
 

@@ -14,7 +14,11 @@ from .arch import POSENET_CONVS, posenet_param_shapes
 
 
 class PoseNetB200:
-    def __init__(self, state_dict: Dict[str, torch.Tensor], noise_latent_channels: int = 320, device="cuda"):
+    def __init__(self, state_dict: Dict[str, torch.Tensor], noise_latent_channels: int = 320, device="cuda",
+                 dtype=torch.bfloat16):
+        if dtype not in ops.ACT_DTYPES:
+            raise ValueError(f"dtype must be torch.bfloat16 or torch.float16, got {dtype}")
+        self.dtype = dtype   # 16-bit format of activations and weights (fp16 = the reference's default, inference_basic.py:486)
         self.dev = torch.device(device)
         self.cout = noise_latent_channels
         shapes = posenet_param_shapes(noise_latent_channels)
@@ -38,15 +42,15 @@ class PoseNetB200:
         cpad = (co + 7) // 8 * 8
         p = torch.zeros(k * k * ci, cpad, dtype=torch.float32)
         p[:, :co] = w.detach().float().cpu().permute(2, 3, 1, 0).reshape(k * k * ci, co)
-        return p.to(self.dev, torch.bfloat16).contiguous()
+        return p.to(self.dev, self.dtype).contiguous()
 
     @torch.no_grad()
     def forward_nhwc(self, x: torch.Tensor) -> torch.Tensor:
         """x [F,3,H,W] (fp32/bf16, NCHW) -> bf16 [F, H/8, W/8, 320] (NHWC)."""
         x = x.to(self.dev)
-        if x.dtype not in (torch.float32, torch.bfloat16):
+        if x.dtype not in (torch.float32, self.dtype):
             x = x.float()
-        y = ops.nchw_to_nhwc(x.contiguous())
+        y = ops.nchw_to_nhwc(x.contiguous(), dtype=self.dtype)
         for wt, b, co, k, stride, pad in self.layers:
             y = ops.conv_direct(y, wt, b, co, k, stride, pad, silu=True)
         return ops.conv_direct(y, self.proj_w, self.proj_b, self.cout, 1, 1, 0, scale=self.scale)

@@ -32,9 +32,9 @@ class _GraphedUNet:
         self.unet, self.ctx, self.ati = unet, ctx, ati
         self.B, self.T, self.h, self.w = B, T, h, w
         self.pose_batch_from = pose_batch_from
-        self.x_in = torch.zeros((B * T, h, w, unet.cfg.in_channels), device=dev, dtype=torch.bfloat16)
+        self.x_in = torch.zeros((B * T, h, w, unet.cfg.in_channels), device=dev, dtype=unet.dtype)
         self.t = torch.zeros((), device=dev, dtype=torch.float32)
-        self.pose = (torch.zeros(((B - pose_batch_from) * T, h, w, c0), device=dev, dtype=torch.bfloat16)
+        self.pose = (torch.zeros(((B - pose_batch_from) * T, h, w, c0), device=dev, dtype=unet.dtype)
                      if with_pose else None)
         self.out = None
         self.graph = None

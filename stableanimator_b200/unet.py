@@ -26,8 +26,8 @@ from . import ops
 from .arch import ResSpec, TstSpec, UNetConfig, build_stages, unet_param_shapes
 
 
-def _bf16(t: torch.Tensor, dev) -> torch.Tensor:
-    return t.detach().to(device=dev, dtype=torch.bfloat16).contiguous()
+def _bf16(t: torch.Tensor, dev, dtype=torch.bfloat16) -> torch.Tensor:
+    return t.detach().to(device=dev, dtype=dtype).contiguous()
 
 
 def _f32(t: torch.Tensor, dev) -> torch.Tensor:
@@ -42,8 +42,14 @@ class _Ctx:
 class UNetB200:
     """Weights packed for the kernels + the forward orchestration."""
 
-    def __init__(self, cfg: UNetConfig, state_dict: Dict[str, torch.Tensor], device="cuda"):
+    def __init__(self, cfg: UNetConfig, state_dict: Dict[str, torch.Tensor], device="cuda", dtype=torch.bfloat16):
+        """``dtype``: the 16-bit format of activations and tensor-core weights -- ``torch.bfloat16`` (BASELINE's GPU
+        configs) or ``torch.float16``, the reference's default inference dtype (inference_basic.py:486-503).  The
+        skinny fp32-activation kernels (time / context embeddings) keep bf16 weights in both modes."""
+        if dtype not in ops.ACT_DTYPES:
+            raise ValueError(f"dtype must be torch.bfloat16 or torch.float16, got {dtype}")
         self.cfg = cfg
+        self.dtype = dtype
         self.dev = torch.device(device)
         self.stages = build_stages(cfg)
         shapes = unet_param_shapes(cfg)
@@ -76,9 +82,10 @@ class UNetB200:
     # ------------------------------------------------------------------ weight packing
     def _pack(self, sd: Dict[str, torch.Tensor]) -> None:
         dev, w, cfg = self.dev, self.w, self.cfg
+        act = self.dtype   # format of the tensor-core weights; the skinny fp32-activation kernels always take bf16
 
-        def lin(name, bias=True):
-            w[f"{name}.w"] = _bf16(sd[f"{name}.weight"], dev)
+        def lin(name, bias=True, small=False):
+            w[f"{name}.w"] = _bf16(sd[f"{name}.weight"], dev, torch.bfloat16 if small else act)
             if bias:
                 w[f"{name}.b"] = _f32(sd[f"{name}.bias"], dev)
 
@@ -88,36 +95,36 @@ class UNetB200:
 
         def conv3(name):  # OIHW -> [O, (ky, kx, ci)]
             t = sd[f"{name}.weight"]
-            w[f"{name}.w"] = _bf16(t.permute(0, 2, 3, 1).reshape(t.shape[0], -1), dev)
+            w[f"{name}.w"] = _bf16(t.permute(0, 2, 3, 1).reshape(t.shape[0], -1), dev, act)
             w[f"{name}.b"] = _f32(sd[f"{name}.bias"], dev)
 
         def convt(name):  # OIDHW (3,1,1) -> [O, (kt, ci)]
             t = sd[f"{name}.weight"][:, :, :, 0, 0]
-            w[f"{name}.w"] = _bf16(t.permute(0, 2, 1).reshape(t.shape[0], -1), dev)
+            w[f"{name}.w"] = _bf16(t.permute(0, 2, 1).reshape(t.shape[0], -1), dev, act)
             w[f"{name}.b"] = _f32(sd[f"{name}.bias"], dev)
 
         def geglu(name):
             wi, bi = ops.interleave_geglu(sd[f"{name}.net.0.proj.weight"], sd[f"{name}.net.0.proj.bias"])
-            w[f"{name}.w1"], w[f"{name}.b1"] = _bf16(wi, dev), _f32(bi, dev)
-            w[f"{name}.w2"] = _bf16(sd[f"{name}.net.2.weight"], dev)
+            w[f"{name}.w1"], w[f"{name}.b1"] = _bf16(wi, dev, act), _f32(bi, dev)
+            w[f"{name}.w2"] = _bf16(sd[f"{name}.net.2.weight"], dev, act)
             w[f"{name}.b2"] = _f32(sd[f"{name}.net.2.bias"], dev)
 
         def qkv(name):
             cat = torch.cat([sd[f"{name}.to_q.weight"], sd[f"{name}.to_k.weight"], sd[f"{name}.to_v.weight"]], 0)
-            w[f"{name}.qkv"] = _bf16(cat, dev)
+            w[f"{name}.qkv"] = _bf16(cat, dev, act)
             lin(f"{name}.to_out.0")
 
         # conv_in: direct conv weights [k*k*cin, cout]
         t = sd["conv_in.weight"]
-        w["conv_in.w"] = _bf16(t.permute(2, 3, 1, 0).reshape(-1, t.shape[0]), dev)
+        w["conv_in.w"] = _bf16(t.permute(2, 3, 1, 0).reshape(-1, t.shape[0]), dev, act)
         w["conv_in.b"] = _f32(sd["conv_in.bias"], dev)
         if t.shape[1] == 8 and t.shape[2:] == (3, 3):  # tensor-core path: [O, 72 (ky, kx, ci) | 56 zeros]
             wg = torch.zeros(t.shape[0], 128, dtype=torch.float32)
             wg[:, :72] = t.permute(0, 2, 3, 1).reshape(t.shape[0], 72).float().cpu()
-            w["conv_in.wg"] = _bf16(wg, dev)
+            w["conv_in.wg"] = _bf16(wg, dev, act)
         for n in ("time_embedding.linear_1", "time_embedding.linear_2", "add_embedding.linear_1",
                   "add_embedding.linear_2"):
-            lin(n)
+            lin(n, small=True)
 
         temb_w, temb_b, self.temb_off = [], [], {}
         ctx_w, self.ctx_off = [], {}
@@ -128,7 +135,7 @@ class UNetB200:
                 norm(f"{s_}.norm1"); conv3(f"{s_}.conv1"); norm(f"{s_}.norm2"); conv3(f"{s_}.conv2")
                 if r.shortcut:
                     t = sd[f"{s_}.conv_shortcut.weight"]
-                    w[f"{s_}.conv_shortcut.w"] = _bf16(t.reshape(t.shape[0], t.shape[1]), dev)
+                    w[f"{s_}.conv_shortcut.w"] = _bf16(t.reshape(t.shape[0], t.shape[1]), dev, act)
                     w[f"{s_}.conv_shortcut.b"] = _f32(sd[f"{s_}.conv_shortcut.bias"], dev)
                 norm(f"{t_}.norm1"); convt(f"{t_}.conv1"); norm(f"{t_}.norm2"); convt(f"{t_}.conv2")
                 for blk in (s_, t_):  # all 44 time_emb_proj share the input silu(emb): one skinny GEMM
@@ -145,13 +152,16 @@ class UNetB200:
                 b = f"{t.name}.transformer_blocks.0"
                 norm(f"{b}.norm1"); qkv(f"{b}.attn1"); norm(f"{b}.norm2")
                 lin(f"{b}.attn2.to_q", bias=False); lin(f"{b}.attn2.to_out.0")
+                # the same matrix for sa_small_linear (W_out . v_clip): bf16 in both modes
+                w[f"{b}.attn2.to_out.0.w_sl"] = (w[f"{b}.attn2.to_out.0.w"] if act == torch.bfloat16 else
+                                                 _bf16(sd[f"{b}.attn2.to_out.0.weight"], dev))
                 # rowsum(W_out) for the folded distribution alignment (weight-only constant)
                 w[f"{b}.attn2.rowsum"] = w[f"{b}.attn2.to_out.0.w"].float().sum(dim=1).contiguous()
                 norm(f"{b}.norm3"); geglu(f"{b}.ff")
                 tb = f"{t.name}.temporal_transformer_blocks.0"
                 norm(f"{tb}.norm_in"); geglu(f"{tb}.ff_in"); norm(f"{tb}.norm1"); qkv(f"{tb}.attn1")
-                lin(f"{tb}.attn2.to_out.0"); norm(f"{tb}.norm3"); geglu(f"{tb}.ff")
-                lin(f"{t.name}.time_pos_embed.linear_1"); lin(f"{t.name}.time_pos_embed.linear_2")
+                lin(f"{tb}.attn2.to_out.0", small=True); norm(f"{tb}.norm3"); geglu(f"{tb}.ff")
+                lin(f"{t.name}.time_pos_embed.linear_1", small=True); lin(f"{t.name}.time_pos_embed.linear_2", small=True)
                 w[f"{t.name}.alpha"] = float(torch.sigmoid(sd[f"{t.name}.time_mixer.mix_factor"].float()).item())
                 # context projections of the 5 tokens, batched over the whole net:
                 #   [spatial to_v | id_to_k | id_to_v | temporal to_v]  (to_k of a single key is inert)
@@ -164,7 +174,7 @@ class UNetB200:
                     conv3(key)
             if st.upsample:  # Upsample2D as four 2x2-tap phase convolutions on the low-resolution input
                 for i, (_, _, _, wp) in enumerate(ops.upsample_conv_phases(sd[f"{st.upsample}.weight"])):
-                    w[f"{st.upsample}.ph{i}.w"] = _bf16(wp, dev)
+                    w[f"{st.upsample}.ph{i}.w"] = _bf16(wp, dev, act)
         w["temb_all.w"] = _bf16(torch.cat(temb_w, 0), dev)
         w["temb_all.b"] = _f32(torch.cat(temb_b, 0), dev)
         w["ctx_all.w"] = _bf16(torch.cat(ctx_w, 0), dev)
@@ -175,7 +185,7 @@ class UNetB200:
         wo[: t.shape[0]] = t.permute(0, 2, 3, 1).reshape(t.shape[0], -1).float().cpu()
         bo = torch.zeros(8)
         bo[: t.shape[0]] = sd["conv_out.bias"].float().cpu()
-        w["conv_out.w"], w["conv_out.b"] = _bf16(wo, dev), _f32(bo, dev)
+        w["conv_out.w"], w["conv_out.b"] = _bf16(wo, dev, act), _f32(bo, dev)
 
     # ------------------------------------------------------------------ embeddings / context
     def _time_embedding(self, timestep: torch.Tensor, added_time_ids: torch.Tensor, B: int) -> torch.Tensor:
@@ -221,7 +231,7 @@ class UNetB200:
                 tb = f"{t.name}.temporal_transformer_blocks.0"
                 vclip = ctx.all[:, 0, o:o + c]
                 tv = ctx.all[:, 0, o + 3 * c:o + 4 * c]
-                ctx.wv[t.name] = ops.small_linear(vclip, w[f"{b}.attn2.to_out.0.w"])
+                ctx.wv[t.name] = ops.small_linear(vclip, w[f"{b}.attn2.to_out.0.w_sl"])
                 ctx.tconst[t.name] = ops.small_linear(tv, w[f"{tb}.attn2.to_out.0.w"], w[f"{tb}.attn2.to_out.0.b"])
         return ctx
 
@@ -376,7 +386,7 @@ class UNetB200:
             return ops.conv_direct(x_in, w["conv_in.w"], w["conv_in.b"], c0, 3, 1, 1, add=pose,
                                    add_from=pose_from).reshape(-1, c0)
         cols = ops.im2col3x3_c8(x_in.contiguous())
-        x = torch.empty((n * h * wd, c0), device=self.dev, dtype=torch.bfloat16)
+        x = torch.empty((n * h * wd, c0), device=self.dev, dtype=self.dtype)
         r0 = pose_from * h * wd if pose is not None else n * h * wd
         if r0 > 0:
             ops.gemm_tap(cols[:r0], w["conv_in.wg"], bias=w["conv_in.b"], out=x[:r0])
@@ -448,7 +458,7 @@ class UNetB200:
                     # nearest x2 + conv3x3 (unet.py:1789-1807): each output phase (py, px) is a 2x2-tap convolution of
                     # the low-resolution tensor written to every other pixel -- 4/9 of the MACs, no upsampled tensor
                     xin = x.reshape(B * F, ch, cw, st.cout)
-                    up = torch.empty((B * F, 2 * ch, 2 * cw, st.cout), device=self.dev, dtype=torch.bfloat16)
+                    up = torch.empty((B * F, 2 * ch, 2 * cw, st.cout), device=self.dev, dtype=self.dtype)
                     for i, (py, px, ptaps) in enumerate(ops.UPSAMPLE_PHASE_TAPS):
                         ops.gemm_tap(xin, w[f"{st.upsample}.ph{i}.w"], grid=(cw, ch, B * F), taps=ptaps,
                                      bias=w[f"{st.upsample}.b"], out=up[:, py::2, px::2, :])
@@ -475,15 +485,15 @@ class UNetB200:
             raise ValueError(f"sample must be [B, F, {self.cfg.in_channels}, h, w]")
         B, F, _, h, wd = sample.shape
         s = sample.to(self.dev)
-        if s.dtype not in (torch.float32, torch.bfloat16):
+        if s.dtype not in (torch.float32, self.dtype):
             s = s.float()
-        x_in = ops.nchw_to_nhwc(s.reshape(B * F, self.cfg.in_channels, h, wd).contiguous())
+        x_in = ops.nchw_to_nhwc(s.reshape(B * F, self.cfg.in_channels, h, wd).contiguous(), dtype=self.dtype)
         pose = None
         if pose_latents is not None:
             p = pose_latents.to(self.dev)
-            if p.dtype not in (torch.float32, torch.bfloat16):
+            if p.dtype not in (torch.float32, self.dtype):
                 p = p.float()
-            pose = ops.nchw_to_nhwc(p.contiguous())
+            pose = ops.nchw_to_nhwc(p.contiguous(), dtype=self.dtype)
         if not torch.is_tensor(timestep):
             timestep = torch.tensor(float(timestep))
         ctx = self.prepare_context(encoder_hidden_states)

@@ -45,15 +45,37 @@ def test_gemm_args_struct_matches_header():
     assert C.sizeof(GemmArgs) % 8 == 0
 
 
+def test_ff_args_struct_matches_header():
+    from stableanimator_b200._lib import FfArgs
+    hdr = (ROOT / "include" / "sa_b200.h").read_text()
+    body = hdr[hdr.index("typedef struct sa_ff_args {"):hdr.index("} sa_ff_args;")]
+    fields = []
+    for ln in body.splitlines()[1:]:
+        ln = ln.split("/*")[0].strip().rstrip(";")
+        if not ln:
+            continue
+        decl = ln.split()
+        names = " ".join(decl[1:]) if decl[0] != "const" else " ".join(decl[2:])
+        for nm in names.split(","):
+            fields.append(nm.strip().lstrip("*").split("[")[0])
+    assert fields == [f[0] for f in FfArgs._fields_]
+
+
 def test_argument_errors_are_reported_not_thrown(lib):
     from stableanimator_b200._lib import GemmArgs
     a = GemmArgs()
     assert lib.sa_gemm_tap(C.byref(a), None) == -1
     assert b"null pointer" in lib.sa_last_error()
-    assert lib.sa_attn_temporal(C.c_void_p(8), 192, 1, 17, 4, 64, 1, C.c_void_p(8), 64, None) == -1
+    assert lib.sa_attn_temporal(C.c_void_p(8), 192, 1, 17, 4, 64, 1, C.c_void_p(8), 64, 0, None) == -1
     assert b"F=17" in lib.sa_last_error()
     assert lib.sa_layernorm(C.c_void_p(8), 60, 4, 60, None, 1, None, 0, C.c_void_p(8), C.c_void_p(8), 1e-5,
-                            C.c_void_p(8), 60, None) == -1
+                            C.c_void_p(8), 60, 0, None) == -1
+    from stableanimator_b200._lib import FfArgs
+    f = FfArgs()
+    assert lib.sa_ff_fused(C.byref(f), None) == -1 and b"null pointer" in lib.sa_last_error()
+    f.x = f.gamma = f.beta = f.w1 = f.b1 = f.w2 = f.b2 = f.out = 8
+    f.c, f.m, f.ldx, f.ldc = 192, 4, 192, 192
+    assert lib.sa_ff_fused(C.byref(f), None) == -1 and b"C=192" in lib.sa_last_error()
     assert lib.sa_gemm_pick_tile(65536, 320, 0) == 160
     assert lib.sa_gemm_pick_tile(65536, 2560, 1) in (128, 256)
 
