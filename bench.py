@@ -51,10 +51,10 @@ CONFIGS = {
     3: (64, 64, 64, "512x512, 64-frame long video, tile 16 / overlap 4, (tile, CFG branch) units over the ranks"),
     4: (128, 72, 128, "576x1024 (w x h), 128-frame long video, tile 16 / overlap 4, (tile, CFG branch) units over the ranks"),
 }
-# average DRAM bytes (read + write) per sa_gemm_tap launch in one B=2 UNet call at 64x64x16, from the ncu pass
-# `--metrics dram__bytes_read.sum,dram__bytes_write.sum` over all 334 launches of the family
-# (profiles/r1_v8_launches_unet_b2_64x64x16.csv, summary next to it)
-GEMM_DRAM_BYTES_PER_LAUNCH = 132.2e6
+# average DRAM bytes (read + write) per GEMM-family launch (sa_gemm_tap + sa_ff_fused) in one B=2 UNet call at 64x64x16,
+# re-measured at round-2 HEAD with the ncu pass `--metrics dram__bytes_read.sum,dram__bytes_write.sum` over all 333
+# launches of the family (profiles/r2_v3_launches_unet_b2_64x64x16.csv, summary next to it; round 1: 132.2 MB over 343)
+GEMM_DRAM_BYTES_PER_LAUNCH = 102.7e6
 
 
 def peaks():
@@ -278,6 +278,22 @@ def long_video_record(unet, pose_net, dev, world, rank, euler_steps, size):
         tt = torch.tensor([ms], device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = tt.item()
+    # the one collective of the path, timed on its own: NCCL all-reduce (sum) of the fp32 [2, F, 4, h, w] noise accumulator
+    ar_ms = None
+    if world > 1:
+        buf = torch.zeros((2, frames, 4, lh, lw), device=dev, dtype=torch.float32)
+        for _ in range(3):
+            dist.all_reduce(buf)
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(10):
+            dist.all_reduce(buf)
+        a1.record()
+        torch.cuda.synchronize()
+        tt = torch.tensor([a0.elapsed_time(a1) / 10], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ar_ms = tt.item()
     n_tiles = len(sch.tile_indices(frames, 16, 4))
     units = 2 * n_tiles
     rounds = -(-units // world)
@@ -285,6 +301,12 @@ def long_video_record(unet, pose_net, dev, world, rank, euler_steps, size):
            "scaling": "strong", "n_gpus": world, "ms_per_denoise": ms, "video_frames_per_s": frames / (ms / 1e3),
            "units_per_step": units, "partition_ceiling": units / (rounds * world),
            "timed": "1 full denoise after a 1-step warm-up, CUDA events, max over ranks"}
+    if ar_ms is not None:
+        nbytes = 2 * frames * 4 * lh * lw * 4
+        rec["exchange"] = {"collective": "ncclAllReduce(sum) of the fp32 noise accumulator, once per Euler step",
+                           "bytes_per_step": nbytes, "ms_per_step_standalone": ar_ms,
+                           "share_of_denoise": euler_steps * ar_ms / ms,
+                           "algbw_GBps": nbytes / (ar_ms * 1e-3) / 1e9}
     if size == "full":
         rec["whole_step_tflops_reference_graph_per_gpu"] = (euler_steps * units * FLOPS_PER_CALL_128x72x16 / (ms * 1e-3)
                                                             / 1e12 / world)

@@ -36,7 +36,7 @@ def _f32(t: torch.Tensor, dev) -> torch.Tensor:
 
 class _Ctx:
     """Per-call context-derived tensors (they depend on encoder_hidden_states only)."""
-    __slots__ = ("all", "wv", "tconst", "b", "zero_prefix")
+    __slots__ = ("all", "wv", "tconst", "b", "zero_prefix", "ffaddv")
 
 
 class UNetB200:
@@ -221,7 +221,7 @@ class UNetB200:
         nz = (ehs.abs().amax(dim=(1, 2)) > 0).tolist()
         ctx.zero_prefix = next((i for i, v in enumerate(nz) if v), B) if self.skip_zero_context else 0
         ctx.all = ops.small_linear(ehs.reshape(B * L, D), w["ctx_all.w"]).reshape(B, L, self.n_ctx)
-        ctx.wv, ctx.tconst = {}, {}
+        ctx.wv, ctx.tconst, ctx.ffaddv = {}, {}, {}
         for st in self.stages:
             for t in st.tst:
                 if t is None:
@@ -233,6 +233,10 @@ class UNetB200:
                 tv = ctx.all[:, 0, o + 3 * c:o + 4 * c]
                 ctx.wv[t.name] = ops.small_linear(vclip, w[f"{b}.attn2.to_out.0.w_sl"])
                 ctx.tconst[t.name] = ops.small_linear(tv, w[f"{tb}.attn2.to_out.0.w"], w[f"{tb}.attn2.to_out.0.b"])
+                if ctx.zero_prefix > 0:   # attn2 output of the zero-context batch elements: the to_out bias (others: 0)
+                    av = torch.zeros((B, c), device=self.dev, dtype=torch.float32)
+                    av[:ctx.zero_prefix] = w[f"{b}.attn2.to_out.0.b"]
+                    ctx.ffaddv[t.name] = av
         return ctx
 
     def _pos_embed(self, t: TstSpec, B: int, F: int) -> torch.Tensor:
@@ -312,7 +316,9 @@ class UNetB200:
         off = self.ctx_off[t.name]
         nt = self.cfg.num_tokens
         ff_fused = self.fuse_ff and c in ops.FF_FUSED_CHANNELS
-        y2 = torch.empty_like(y1)
+        # fused path: the attn2 output is added to y1 IN PLACE on the rows that have a context (each epilogue thread reads
+        # the residual element it overwrites), so one feed-forward launch covers all rows
+        y2 = y1 if ff_fused else torch.empty_like(y1)
         a = None if ff_fused else torch.empty_like(y1)
         if bn > 0:
             an = ops.layernorm(y1[mz:], w[f"{b}.norm2.g"], w[f"{b}.norm2.b"])
@@ -330,14 +336,10 @@ class UNetB200:
             if not ff_fused:
                 ops.layernorm(y2[mz:], w[f"{b}.norm3.g"], w[f"{b}.norm3.b"], out=a[mz:])
         if ff_fused:
-            # norm3 -> ff -> + residual in one kernel per row range; on the zero-context rows the attn2 output (the
-            # constant to_out bias) enters as the additive vector, so y2 is never materialised there
-            y3 = torch.empty_like(y1)
-            ffw = (w[f"{b}.norm3.g"], w[f"{b}.norm3.b"], w[f"{b}.ff.w1"], w[f"{b}.ff.b1"], w[f"{b}.ff.w2"], w[f"{b}.ff.b2"])
-            if zb > 0:
-                ops.ff_fused(y1[:mz], *ffw, addv=w[f"{b}.attn2.to_out.0.b"].reshape(1, c), rows_per_group=mz, out=y3[:mz])
-            if bn > 0:
-                ops.ff_fused(y2[mz:], *ffw, out=y3[mz:])
+            # norm3 -> ff -> + residual in one kernel; on the zero-context batch elements the attn2 output (the constant
+            # to_out bias) enters as the per-batch-element additive vector, zero on the others
+            y3 = ops.ff_fused(y2, w[f"{b}.norm3.g"], w[f"{b}.norm3.b"], w[f"{b}.ff.w1"], w[f"{b}.ff.b1"], w[f"{b}.ff.w2"],
+                              w[f"{b}.ff.b2"], addv=ctx.ffaddv.get(t.name), rows_per_group=F * S)
         else:
             if zb > 0:  # y2 = y1 + to_out.bias, a = norm3(y2) in one pass
                 ops.layernorm(y1[:mz], w[f"{b}.norm3.g"], w[f"{b}.norm3.b"], addv=w[f"{b}.attn2.to_out.0.b"].reshape(1, c),
