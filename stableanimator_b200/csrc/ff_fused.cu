@@ -42,6 +42,16 @@ constexpr int FF_A_CHUNK = 128 * 128;      // [128 rows][64 ch] bf16
 constexpr int FF_P_BYTES = 128 * 128;      // [128 rows][64 hidden] bf16
 constexpr int FF_EW = 16;                  // epilogue warps: 4 per TMEM lane quadrant = 2 chunk sets x 2 column halves
 
+// -DSA_FF_TRACE (tools/ff_trace.py builds a private copy of this file with it): CTA 0 records clock64() at the hand-off
+// points of its first tile -- [0][c] S(c) issued, [1][c] O(c) issued (MMA thread); [2][c] S(c) seen complete, [3][c] P(c)
+// written (lane 0 of epilogue warp 0 of each set) -- into the buffer registered with sa_ff_set_trace().
+#ifdef SA_FF_TRACE
+__device__ long long* g_ff_trace = nullptr;
+#define FF_TRACE(ev, idx) do { if (blockIdx.x == 0 && ti == 0 && g_ff_trace) g_ff_trace[(ev) * 64 + (idx)] = clock64(); } while (0)
+#else
+#define FF_TRACE(ev, idx) do { } while (0)
+#endif
+
 struct FfParams {
   int M, C;
   const __nv_bfloat16* x;   // [M, ldx_in]: residual source (re-read by the final epilogue)
@@ -81,6 +91,7 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   constexpr int NHALF = C / 2;      // O is accumulated as two column halves (MMA N <= 256)
   constexpr int W1_BYTES = 128 * 128, W2_BYTES = NHALF * 128;
   constexpr int O_COL = 128;
+  constexpr int ODLY = 2;           // O(c) is issued after S(c + ODLY)
   constexpr int OCH = C / 32;       // 32-column chunks of the output tile
 
   extern __shared__ uint8_t smem_raw[];
@@ -150,7 +161,7 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         // weight stream in the order the MMA warp consumes it: W1(0) | W1(1) W2(0) | ... | W1(NH-1) W2(NH-2) | W2(NH-1);
         // the activation tile is requested after W1(0), so the weights of the next tile are already on their way while
         // the last MMAs of this one still read A
-        for (int i = 0; i <= NH; ++i) {
+        for (int i = 0; i < NH + ODLY; ++i) {
           if (i < NH) {
             for (int kc = 0; kc < KC; ++kc, ++it) {
               const int s = it % FF_ST;
@@ -166,12 +177,12 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 #pragma unroll
             for (int kc = 0; kc < KC; ++kc) tma_load_2d(sA + kc * FF_A_CHUNK, &tmX, a_full, kc * 64, m0);
           }
-          if (i > 0) {
+          if (i >= ODLY) {
             for (int h = 0; h < 2; ++h, ++it) {
               const int s = it % FF_ST;
               mbar_wait_relaxed(&empty_bar[s], ((it / FF_ST) & 1) ^ 1);
               mbar_expect_tx(&full_bar[s], W2_BYTES);
-              tma_load_2d_mc(sRing + s * FF_STAGE_BYTES + rank * (W2_HALF_ROWS * 128), &tmW2, &full_bar[s], (i - 1) * 64,
+              tma_load_2d_mc(sRing + s * FF_STAGE_BYTES + rank * (W2_HALF_ROWS * 128), &tmW2, &full_bar[s], (i - ODLY) * 64,
                              h * NHALF + rank * W2_HALF_ROWS, 3);
             }
           }
@@ -189,7 +200,7 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       for (int tp = pair; tp < pair_tiles; tp += n_pairs, ++ti) {
         mbar_wait(a_ready, ti & 1);
         tc_fence_after();
-        for (int i = 0; i <= NH; ++i) {
+        for (int i = 0; i < NH + ODLY; ++i) {
           if (i < NH) {
             // S(i): the epilogue set of chunk i-1 must have read S(i-1) out of TMEM
             const uint32_t c = ci + i;
@@ -208,14 +219,17 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
               umma_commit_mc(&empty_bar[s], 3);
             }
             umma_commit(&s_full[c & 1]);
+            FF_TRACE(0, i);
             if (i == NH - 1) umma_commit(a_empty);   // the activation tile may be overwritten
           }
-          if (i > 0) {
-            // O += P(i-1) . W2(i-1)^T
-            const uint32_t c = ci + i - 1;
+          if (i >= ODLY) {
+            // O += P(i-ODLY) . W2(i-ODLY)^T -- issued ODLY chunks late: by then the GELU epilogue of that chunk is long
+            // done, so this wait never holds up the S MMAs queued behind it (the first version issued O(i-1) here and the
+            // tensor pipe idled for the epilogue latency of every chunk: tools/ff_trace.py)
+            const uint32_t c = ci + i - ODLY;
             const int pb = c & 1;
             mbar_wait(&p_full[pb], (c >> 1) & 1);
-            if (i == 1) mbar_wait(o_free, (ti & 1) ^ 1);   // previous tile's O drained by the final epilogue
+            if (i == ODLY) mbar_wait(o_free, (ti & 1) ^ 1);   // previous tile's O drained by the final epilogue
             tc_fence_after();
             const uint64_t dp = umma_desc_sw128(smem_u32(sP + pb * FF_P_BYTES));
             for (int h = 0; h < 2; ++h, ++it) {
@@ -225,10 +239,11 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
               const uint64_t dw = umma_desc_sw128(smem_u32(sRing + s * FF_STAGE_BYTES));
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                umma_f16(tmem_base + O_COL + h * NHALF, dp + 2 * k, dw + 2 * k, idesc_o, (i > 1 || k != 0) ? 1u : 0u);
+                umma_f16(tmem_base + O_COL + h * NHALF, dp + 2 * k, dw + 2 * k, idesc_o, (i > ODLY || k != 0) ? 1u : 0u);
               umma_commit_mc(&empty_bar[s], 3);
             }
             umma_commit(&p_free[pb]);
+            FF_TRACE(1, i - ODLY);
           }
         }
         umma_commit(o_full);
@@ -343,6 +358,7 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         const uint32_t c = ci + i;       // c & 1 == half (NH is even)
         mbar_wait(&s_full[half], (c >> 1) & 1);
         tc_fence_after();
+        if (ch == 0 && quad == 0 && lane == 0) FF_TRACE(2, i);
         uint32_t u[32], g[32];
         tmem_ld_32x32(lane_addr + 32 * ch, u);          // this warp's 32 value columns
         tmem_ld_32x32(lane_addr + 64 + 32 * ch, g);     // and 32 gate columns
@@ -370,6 +386,7 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         }
         fence_proxy_async();
         mbar_arrive(&p_full[half]);
+        if (ch == 0 && quad == 0 && lane == 0) FF_TRACE(3, i);
       }
       ci += NH;
 
@@ -493,6 +510,12 @@ static int launch_ff(const CUtensorMap* tx, const CUtensorMap* tw1, const CUtens
 }
 
 }  // namespace sa
+
+#ifdef SA_FF_TRACE
+extern "C" int sa_ff_set_trace(void* buf) {
+  return cudaMemcpyToSymbol(sa::g_ff_trace, &buf, sizeof(buf)) == cudaSuccess ? 0 : -2;
+}
+#endif
 
 extern "C" int sa_ff_fused(const sa_ff_args* a, void* stream_) {
   using namespace sa;
