@@ -52,13 +52,26 @@ constexpr int FA_TILE = 128 * 128;  // bytes of a [128][64] 16-bit tile
 // TMEM columns (all 512): S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384) P_A [384,448) P_B [448,512).
 // smem: Q 2x16K | K 4x16K | V 4x16K = 160 KB + barriers + 4 KB exchange -> one CTA per SM.
 // -----------------------------------------------------------------------------------------------------
-constexpr int FA3_ST = 4;
-constexpr int FA3_SW = 16;                      // softmax warps
-constexpr int FA3_THREADS = (FA3_SW + 4) * 32;  // + one warpgroup: TMA, MMA, two idle warps (setmaxnreg is per warpgroup)
-// 640 threads start with 96 registers each; the control warpgroup gives most of its share to the softmax warpgroups
-// (setmaxnreg.inc can only take what setmaxnreg.dec released inside the SAME CTA: the pool is 640 x 96 registers)
-constexpr int FA3_REGS_CTRL = 24, FA3_REGS_SOFTMAX = 112;
-static_assert(FA3_SW * 32 * FA3_REGS_SOFTMAX + 4 * 32 * FA3_REGS_CTRL <= FA3_THREADS * 96, "register pool of the CTA");
+// NT = query tiles per CTA.  NT = 2: one CTA per SM, the two tiles ping-pong on the tensor core and share the K / V ring.
+// NT = 1 (SA_FA_NT=1): two co-resident CTAs per SM of one tile each (256 TMEM columns, 80 KB of shared memory, 8 softmax
+// warps): the prologue / epilogue of one CTA (TMEM allocation, Q load, first S; final O read-out) runs under the other
+// CTA's main loop instead of leaving the SM idle, at the price of loading K / V once per tile.
+template <int NT> struct Fa3Cfg {
+  static constexpr int ST = NT == 2 ? 4 : 2;          // K / V ring stages
+  static constexpr int SW = 8 * NT;                   // softmax warps
+  // NT = 2: + one warpgroup (TMA, MMA, two idle warps: setmaxnreg is per warpgroup); NT = 1: + TMA and MMA warps only --
+  // 2 x 320 threads leave each thread 96 registers, which the softmax code fits without rebalancing
+  static constexpr int THREADS = (SW + 4) * 32;
+  static constexpr bool REBALANCE = true;
+  static constexpr int TCOLS = 256 * NT;              // S | O | P
+  static constexpr int O_COL = 128 * NT, P_COL = 192 * NT;
+  static constexpr int REGS0 = NT == 2 ? 96 : 80;     // registers per thread the CTA is launched with
+  static constexpr int REGS_CTRL = 24, REGS_SOFTMAX = NT == 2 ? 112 : 104;
+  static_assert(!REBALANCE || SW * 32 * REGS_SOFTMAX + 4 * 32 * REGS_CTRL <= THREADS * REGS0, "register pool of the CTA");
+};
+constexpr int FA3_ST = 4;                       // (barrier arrays are sized for the larger ring)
+constexpr int FA3_SW = 16;
+constexpr int FA3_THREADS = (FA3_SW + 4) * 32;
 constexpr float FA3_TAU = 8.0f;  // lazy-rescale threshold (log2 units)
 // columns whose 2^x comes from the FMA-pipe polynomial: every POLY-th group of 4 columns (template parameter; 0 = none)
 
@@ -69,7 +82,9 @@ struct Fa3Bars {
   uint32_t tmem_slot;
   float xch[2][8][2][32];  // [block parity][warp pair][column half][lane]: half-row maxima / final row sums
 };
-constexpr int FA3_SMEM = FA_TILE * (2 + 2 * FA3_ST) + 1024 + static_cast<int>(sizeof(Fa3Bars)) + 64;
+template <int NT> constexpr int fa3_smem() {
+  return FA_TILE * (NT + 2 * Fa3Cfg<NT>::ST) + 1024 + static_cast<int>(sizeof(Fa3Bars)) + 64;
+}
 
 // 2^x for two lanes on the FMA pipe: x = n + f, n = round(x), f in [-0.5, 0.5]; 2^f by a degree-3 minimax
 // polynomial (relative error <= 7.5e-5), 2^n by adding n to the exponent field.  x is clamped at -126 (2^-126 ~ 1e-38
@@ -91,31 +106,30 @@ __device__ __forceinline__ void exp2_poly2(uint64_t x, float& e0, float& e1) {
   e1 = exp2_poly(xf.y);
 }
 
-#ifndef FA3_LB
-#define FA3_LB FA3_THREADS
-#endif
-template <int POLY>
-__global__ void __launch_bounds__(FA3_LB, 1)
+template <int POLY, int NT>
+__global__ void __launch_bounds__(Fa3Cfg<NT>::THREADS, NT == 2 ? 1 : 2)
 attn_flash_kernel(const __grid_constant__ CUtensorMap tm, int S, int C, __nv_bfloat16* __restrict__ out,
                   int ldo, int f16) {   // f16: q, k and out are IEEE fp16 like v (the fp16 activation mode)
+  using Cfg = Fa3Cfg<NT>;
+  constexpr int ST = Cfg::ST, SW = Cfg::SW, THREADS = Cfg::THREADS, O_COL = Cfg::O_COL, P_COL = Cfg::P_COL;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sQ = smem;                          // 2 tiles
-  uint8_t* sK = smem + 2 * FA_TILE;            // FA3_ST stages
-  uint8_t* sV = sK + FA3_ST * FA_TILE;         // FA3_ST stages
-  Fa3Bars* bars = reinterpret_cast<Fa3Bars*>(sV + FA3_ST * FA_TILE);
+  uint8_t* sQ = smem;                          // NT tiles
+  uint8_t* sK = smem + NT * FA_TILE;           // ST stages
+  uint8_t* sV = sK + ST * FA_TILE;             // ST stages
+  Fa3Bars* bars = reinterpret_cast<Fa3Bars*>(sV + ST * FA_TILE);
 
   const int warp = threadIdx.x >> 5;
-  const int q0 = blockIdx.x * 2 * FA_BM;
+  const int q0 = blockIdx.x * NT * FA_BM;
   const int head = blockIdx.y;
   const int frame = blockIdx.z;
   const int nblk = (S + FA_BN - 1) / FA_BN;
-  const int ntiles = (q0 + FA_BM < S) ? 2 : 1;
+  const int ntiles = (NT == 2 && q0 + FA_BM < S) ? 2 : 1;
 
-  if (warp == FA3_SW && elect_one()) {
+  if (warp == SW && elect_one()) {
     tma_prefetch_desc(&tm);
     mbar_init(&bars->q_full, 1);
-    for (int i = 0; i < FA3_ST; ++i) {
+    for (int i = 0; i < ST; ++i) {
       mbar_init(&bars->k_full[i], 1);
       mbar_init(&bars->v_full[i], 1);
       mbar_init(&bars->kv_empty[i], 1);
@@ -128,26 +142,24 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm, int S, int C, __nv_bfl
     }
     fence_barrier_init();
   }
-  if (warp == FA3_SW + 1) tmem_alloc<512>(&bars->tmem_slot);
+  if (warp == SW + 1) tmem_alloc<Cfg::TCOLS>(&bars->tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_slot;
   // Register rebalancing: the two branches below never re-join (each ends with its own CTA-wide barrier and return),
   // so ptxas allocates them under different budgets.
-  if (warp >= FA3_SW) {
-#ifndef FA3_NATURAL_REGS   // -DFA3_NATURAL_REGS -DFA3_LB=256: what ptxas would use unconstrained (register audit)
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FA3_REGS_CTRL));
-#endif
-  if (warp == FA3_SW) {
+  if (warp >= SW) {
+    if constexpr (Cfg::REBALANCE) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::REGS_CTRL));
+  if (warp == SW) {
     // ------------------------------------------------------------ TMA producer
     if (elect_one()) {
       mbar_expect_tx(&bars->q_full, ntiles * FA_TILE);
       for (int t = 0; t < ntiles; ++t)
         tma_load_3d(sQ + t * FA_TILE, &tm, &bars->q_full, head * FA_D, q0 + t * FA_BM, frame);
       for (int j = 0; j < nblk; ++j) {
-        const int st = j % FA3_ST;
-        mbar_wait(&bars->kv_empty[st], ((j / FA3_ST) & 1) ^ 1);
+        const int st = j % ST;
+        mbar_wait(&bars->kv_empty[st], ((j / ST) & 1) ^ 1);
         mbar_expect_tx(&bars->k_full[st], FA_TILE);
         tma_load_3d(sK + st * FA_TILE, &tm, &bars->k_full[st], C + head * FA_D, j * FA_BN, frame);
         mbar_expect_tx(&bars->v_full[st], FA_TILE);
@@ -155,14 +167,14 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm, int S, int C, __nv_bfl
       }
     }
     __syncwarp();
-  } else if (warp == FA3_SW + 1) {
+  } else if (warp == SW + 1) {
     // ------------------------------------------------------------ MMA issuer
     if (elect_one()) {
       const uint32_t idesc_s = f16 ? umma_idesc_f16(128, FA_BN, 0, 0) : umma_idesc_bf16(128, FA_BN, 0, 0);  // S = Q K^T
       constexpr uint32_t idesc_o = umma_idesc_f16(128, FA_D, 0, 1);    // O += P V, fp16 x fp16 (V MN-major)
       auto issue_s = [&](int t, int j) {
         const uint64_t dq = umma_desc_sw128(smem_u32(sQ + t * FA_TILE));
-        const uint64_t dk = umma_desc_sw128(smem_u32(sK + (j % FA3_ST) * FA_TILE));
+        const uint64_t dk = umma_desc_sw128(smem_u32(sK + (j % ST) * FA_TILE));
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_f16(tmem_base + t * 128, dq + 2 * k, dk + 2 * k, idesc_s, k != 0 ? 1u : 0u);
@@ -173,25 +185,25 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm, int S, int C, __nv_bfl
       tc_fence_after();
       for (int t = 0; t < ntiles; ++t) issue_s(t, 0);
       for (int j = 0; j < nblk; ++j) {
-        const int st = j % FA3_ST;
+        const int st = j % ST;
         if (j + 1 < nblk) {
           // S(j+1) as soon as the softmax threads hold S(j) in registers
-          mbar_wait(&bars->k_full[(j + 1) % FA3_ST], ((j + 1) / FA3_ST) & 1);
+          mbar_wait(&bars->k_full[(j + 1) % ST], ((j + 1) / ST) & 1);
           for (int t = 0; t < ntiles; ++t) {
             mbar_wait(&bars->s_free[t], j & 1);
             tc_fence_after();
             issue_s(t, j + 1);
           }
         }
-        mbar_wait(&bars->v_full[st], (j / FA3_ST) & 1);
+        mbar_wait(&bars->v_full[st], (j / ST) & 1);
         for (int t = 0; t < ntiles; ++t) {
           mbar_wait(&bars->p_full[t], j & 1);  // P_t(j) in TMEM, O_t corrected if it had to be
           tc_fence_after();
-          const uint32_t p_tmem = tmem_base + 384 + t * 64;
+          const uint32_t p_tmem = tmem_base + P_COL + t * 64;
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk) {
             const uint64_t dv = umma_desc_sw128(smem_u32(sV + st * FA_TILE + kk * 2048));
-            umma_f16_ts(tmem_base + 256 + t * 64, p_tmem + kk * 8, dv, idesc_o, (j | kk) != 0 ? 1u : 0u);
+            umma_f16_ts(tmem_base + O_COL + t * 64, p_tmem + kk * 8, dv, idesc_o, (j | kk) != 0 ? 1u : 0u);
           }
           umma_commit(&bars->o_full[t]);
         }
@@ -201,25 +213,23 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm, int S, int C, __nv_bfl
     __syncwarp();
   }
     tc_fence_before();
-    named_bar_sync(15, FA3_THREADS);   // every softmax thread is done with TMEM
-    if (warp == FA3_SW + 1) tmem_dealloc<512>(tmem_base);
+    named_bar_sync(15, THREADS);   // every softmax thread is done with TMEM
+    if (warp == SW + 1) tmem_dealloc<Cfg::TCOLS>(tmem_base);
     return;
   }
-#ifndef FA3_NATURAL_REGS
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FA3_REGS_SOFTMAX));
-#endif
+  if constexpr (Cfg::REBALANCE) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::REGS_SOFTMAX));
   {
     // ------------------------------------------------------------ softmax warps (two threads per query row)
     const int quad = warp & 3;               // TMEM lane quadrant
-    const int t = (warp >> 2) & 1;           // tile handled by this warp
-    const int hc = warp >> 3;                // column half of the key block
-    const int pair = warp & 7;               // (tile, quadrant): the two warps sharing these 32 rows
+    const int t = (warp >> 2) & (NT - 1);    // tile handled by this warp
+    const int hc = warp >> (NT == 2 ? 3 : 2);   // column half of the key block
+    const int pair = warp & (4 * NT - 1);    // (tile, quadrant): the two warps sharing these 32 rows
     const int lane = threadIdx.x & 31;
     if (t < ntiles) {
       const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
       const uint32_t s_addr = lane_addr + t * 128 + hc * 64;
-      const uint32_t o_addr = lane_addr + 256 + t * 64 + hc * 32;   // this thread's half of the row's O columns
-      const uint32_t p_addr = lane_addr + 384 + t * 64 + hc * 32;
+      const uint32_t o_addr = lane_addr + O_COL + t * 64 + hc * 32;   // this thread's half of the row's O columns
+      const uint32_t p_addr = lane_addr + P_COL + t * 64 + hc * 32;
       const float sl2 = 0.125f * 1.4426950408889634f;  // attn.scale * log2(e)
       const uint64_t sl22 = pack2(sl2, sl2);
       float m_ref = -INFINITY;                 // reference max the exponentials are taken against
@@ -230,7 +240,12 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm, int S, int C, __nv_bfl
         mbar_wait(&bars->s_full[t], j & 1);
         tc_fence_after();
         uint32_t s[64];
-        tmem_ld_32x64(s_addr, s);
+        if constexpr (NT == 2) {
+          tmem_ld_32x64(s_addr, s);
+        } else {   // two 32-column loads: the 64-register destination block of the x64 form does not fit next to the rest
+          tmem_ld_32x32(s_addr, reinterpret_cast<uint32_t(&)[32]>(s[0]));
+          tmem_ld_32x32(s_addr + 32, reinterpret_cast<uint32_t(&)[32]>(s[32]));
+        }
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(&bars->s_free[t]);  // the tensor core may overwrite S_t with S_t(j+1) now
@@ -325,8 +340,8 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm, int S, int C, __nv_bfl
       const int qrow = q0 + t * FA_BM + quad * 32 + lane;
       if (qrow < S) {
         uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<long long>(frame) * S + qrow) * ldo + head * FA_D + hc * 32);
-#pragma unroll
         const bool h16 = f16 != 0;
+#pragma unroll
         for (int g = 0; g < 4; ++g)
           dst[g] = make_uint4(pack16x2(__uint_as_float(o[8 * g]) * inv, __uint_as_float(o[8 * g + 1]) * inv, h16),
                               pack16x2(__uint_as_float(o[8 * g + 2]) * inv, __uint_as_float(o[8 * g + 3]) * inv, h16),
@@ -337,7 +352,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm, int S, int C, __nv_bfl
   }
 
   tc_fence_before();
-  named_bar_sync(15, FA3_THREADS);
+  named_bar_sync(15, THREADS);
 }
 
 }  // namespace sa
@@ -357,26 +372,32 @@ extern "C" int sa_attn_spatial(const void* qkv, int32_t ld, int32_t frames, int3
   uint32_t box[3] = {64, 128, 1};
   const CUtensorMap* tm = get_tmap_bf16(qkv, 3, dims, strides, box);
   if (!tm) return SA_ERR_TMA;
-  // SA_FA_POLY=<n>: every n-th group of four score columns takes its exp2 from the FMA pipe (0 = MUFU only); A/B knob
+  // SA_FA_POLY=<n>: every n-th group of four score columns takes its exp2 from the FMA pipe (0 = MUFU only); A/B knob.
+  // SA_FA_NT=1: one query tile per CTA, two CTAs per SM (see Fa3Cfg); default 2.
   static const int poly = getenv("SA_FA_POLY") ? atoi(getenv("SA_FA_POLY")) : 8;
+  static const int nt = getenv("SA_FA_NT") ? atoi(getenv("SA_FA_NT")) : 2;
   static DeviceOnce once;
   if (int rc = once.run([&]() -> int {
-        SA_CUDA_CHECK(cudaFuncSetAttribute(attn_flash_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA3_SMEM));
-        SA_CUDA_CHECK(cudaFuncSetAttribute(attn_flash_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA3_SMEM));
-        SA_CUDA_CHECK(cudaFuncSetAttribute(attn_flash_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA3_SMEM));
-        SA_CUDA_CHECK(cudaFuncSetAttribute(attn_flash_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA3_SMEM));
-        SA_CUDA_CHECK(cudaFuncSetAttribute(attn_flash_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA3_SMEM));
+        SA_CUDA_CHECK(cudaFuncSetAttribute(attn_flash_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, fa3_smem<2>()));
+        SA_CUDA_CHECK(cudaFuncSetAttribute(attn_flash_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, fa3_smem<2>()));
+        SA_CUDA_CHECK(cudaFuncSetAttribute(attn_flash_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, fa3_smem<2>()));
+        SA_CUDA_CHECK(cudaFuncSetAttribute(attn_flash_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fa3_smem<1>()));
+        SA_CUDA_CHECK(cudaFuncSetAttribute(attn_flash_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fa3_smem<1>()));
         return SA_OK;
       }))
     return rc;
-  dim3 grid((S + 2 * FA_BM - 1) / (2 * FA_BM), heads, frames);
   __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
-  switch (poly) {
-    case 0: attn_flash_kernel<0><<<grid, FA3_THREADS, FA3_SMEM, stream>>>(*tm, S, C, o, ldo, act_f16); break;
-    case 2: attn_flash_kernel<2><<<grid, FA3_THREADS, FA3_SMEM, stream>>>(*tm, S, C, o, ldo, act_f16); break;
-    case 3: attn_flash_kernel<3><<<grid, FA3_THREADS, FA3_SMEM, stream>>>(*tm, S, C, o, ldo, act_f16); break;
-    case 8: attn_flash_kernel<8><<<grid, FA3_THREADS, FA3_SMEM, stream>>>(*tm, S, C, o, ldo, act_f16); break;
-    default: attn_flash_kernel<4><<<grid, FA3_THREADS, FA3_SMEM, stream>>>(*tm, S, C, o, ldo, act_f16); break;
+  if (nt == 1) {
+    dim3 grid((S + FA_BM - 1) / FA_BM, heads, frames);
+    if (poly == 0) attn_flash_kernel<0, 1><<<grid, Fa3Cfg<1>::THREADS, fa3_smem<1>(), stream>>>(*tm, S, C, o, ldo, act_f16);
+    else attn_flash_kernel<8, 1><<<grid, Fa3Cfg<1>::THREADS, fa3_smem<1>(), stream>>>(*tm, S, C, o, ldo, act_f16);
+  } else {
+    dim3 grid((S + 2 * FA_BM - 1) / (2 * FA_BM), heads, frames);
+    switch (poly) {
+      case 0: attn_flash_kernel<0, 2><<<grid, Fa3Cfg<2>::THREADS, fa3_smem<2>(), stream>>>(*tm, S, C, o, ldo, act_f16); break;
+      case 4: attn_flash_kernel<4, 2><<<grid, Fa3Cfg<2>::THREADS, fa3_smem<2>(), stream>>>(*tm, S, C, o, ldo, act_f16); break;
+      default: attn_flash_kernel<8, 2><<<grid, Fa3Cfg<2>::THREADS, fa3_smem<2>(), stream>>>(*tm, S, C, o, ldo, act_f16); break;
+    }
   }
   SA_CUDA_CHECK(cudaGetLastError());
   return SA_OK;
