@@ -90,6 +90,34 @@ def test_conv3x3(f, h, w_, cin, cout):
     assert_close(out.reshape(f, h, w_, cout), ref)
 
 
+@pytest.mark.parametrize("f,h,w_,cin,cout,res,stats", [
+    (5, 8, 8, 256, 320, True, True),      # 3 row tiles (odd): the pair's second CTA runs a phantom tile in the last item
+    (16, 16, 16, 640, 1280, True, False),  # 32 row tiles x 8 column tiles, K = 5760
+    (3, 18, 9, 192, 160, False, True),    # ragged boxes at the 9-wide level of the 576x1024 geometry, K = 1728
+    (7, 16, 8, 256, 128, True, False),    # tile_n = 128 pair kernel
+])
+def test_long_k_conv_on_the_cta_pair_kernels(f, h, w_, cin, cout, res, stats):
+    """K >= 1280 routes to the cta_group::2 kernels (M = 256 per CTA pair, weight tile split across the pair): every
+    epilogue feature they carry, odd row-tile counts and ragged boxes, against F.conv2d."""
+    from stableanimator_b200 import ops
+    x = rnd(f, h, w_, cin, seed=51)
+    wt = rnd(cout, cin, 3, 3, scale=(9 * cin) ** -0.5, seed=52)
+    bias = torch.randn(cout, device="cuda")
+    wp = wt.permute(0, 2, 3, 1).reshape(cout, 9 * cin).contiguous()
+    r = rnd(f * h * w_, cout, seed=53) if res else None
+    st = torch.empty((f, 32, 2), device="cuda", dtype=torch.float64) if stats else None
+    out = ops.gemm_tap(x, wp, grid=(w_, h, f), taps=ops.TAPS_3X3, bias=bias, residual=r, out_scale=0.5,
+                       gn_stats=st, gn_rows_per_stat=h * w_ if stats else 0)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, padding=1).permute(0, 2, 3, 1).reshape(-1, cout) * 0.5
+    if res:
+        ref = ref + r.float()
+    assert_close(out, ref)
+    if stats:
+        v = out.double().reshape(f, h * w_, 32, cout // 32)
+        assert torch.allclose(st[..., 0], v.sum(dim=(1, 3)), rtol=2e-6, atol=1e-4)
+        assert torch.allclose(st[..., 1], (v * v).sum(dim=(1, 3)), rtol=2e-6, atol=1e-4)
+
+
 def test_conv3x3_concat_sources():
     from stableanimator_b200 import ops
     f, h, w_, c0, c1, cout = 2, 16, 16, 128, 64, 128
