@@ -36,9 +36,10 @@ constexpr int FA_TILE = 128 * 128;  // bytes of a [128][64] 16-bit tile
 //   * row max with 3-input FMNMX; the two threads of a row exchange their half maxima through shared memory
 //     (one 64-thread named barrier per warp pair and block), so both take identical rescale decisions;
 //   * exp2 on packed fp32x2 lanes (FFMA2 / FADD2).  At head_dim 64 one ex2 per score costs twice the tensor-pipe
-//     time of the score's two MMAs (16 MUFU results / clk / SM), so a quarter of the columns take their 2^x from
-//     the FMA pipe instead (Cody-Waite split + degree-3 minimax polynomial, |rel err| <= 7.5e-5, below the
-//     fp16 rounding of P): the MUFU pipe, not the tensor pipe, is this kernel's roofline;
+//     time of the score's two MMAs (16 MUFU results / clk / SM), so every POLY-th group of four columns (default: an
+//     eighth of them -- measured optimum, SA_FA_POLY) takes its 2^x from the FMA pipe instead (Cody-Waite split +
+//     degree-3 minimax polynomial, |rel err| <= 7.5e-5, below the fp16 rounding of P): the MUFU pipe, not the
+//     tensor pipe, is this kernel's roofline;
 //   * P goes back into TMEM (its own 64 columns per tile, tcgen05.st) as fp16 pairs: P is in (0, 256], so half
 //     precision holds it with an 11-bit significand (bf16: 8).  kind::f16 needs A and B in the same format (a
 //     mixed fp16 x bf16 descriptor traps), so the V block of qkv is fp16 too: the q|k|v projection writes it
