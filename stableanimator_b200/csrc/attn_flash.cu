@@ -138,8 +138,8 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm, int S, int C, __nv_bfl
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars->s_full[i], 1);
       mbar_init(&bars->o_full[i], 1);
-      mbar_init(&bars->s_free[i], 256);
-      mbar_init(&bars->p_full[i], 256);
+      mbar_init(&bars->s_free[i], 8);   // one elected arrival per softmax warp of the tile (8 warps), not one per thread:
+      mbar_init(&bars->p_full[i], 8);   // 256 arrivals on one mbarrier serialise on the same shared-memory word
     }
     fence_barrier_init();
   }
@@ -249,7 +249,8 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm, int S, int C, __nv_bfl
         }
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(&bars->s_free[t]);  // the tensor core may overwrite S_t with S_t(j+1) now
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->s_free[t]);  // the tensor core may overwrite S_t with S_t(j+1) now
         if (kv_left < 64) {
 #pragma unroll
           for (int c = 0; c < 64; ++c)
@@ -325,7 +326,8 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm, int S, int C, __nv_bfl
         l2 = add2(l2, add2(la, lb));
         tmem_st_wait();              // P (and a rescaled O) are in TMEM
         tc_fence_before();
-        mbar_arrive(&bars->p_full[t]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->p_full[t]);
       }
       // all P V accumulated: total row sum = this thread's half + the partner's
       const float2 lf = unpack2(l2);

@@ -130,16 +130,18 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       mbar_init(&empty_bar[s], 2);   // the MMA warps of both CTAs of the pair
     }
     mbar_init(a_full, 1);
-    mbar_init(a_ready, FF_EW * 32);
+    // epilogue-side barriers count WARPS (one elected arrival after __syncwarp), not threads: hundreds of arrivals on
+    // one mbarrier serialise on the same shared-memory word
+    mbar_init(a_ready, FF_EW);
     mbar_init(a_empty, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_free[i], FF_EW * 16);
-      mbar_init(&p_full[i], FF_EW * 16);
+      mbar_init(&s_free[i], FF_EW / 2);
+      mbar_init(&p_full[i], FF_EW / 2);
       mbar_init(&p_free[i], 1);
     }
     mbar_init(o_full, 1);
-    mbar_init(o_free, FF_EW * 32);
+    mbar_init(o_free, FF_EW);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -348,7 +350,8 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             *reinterpret_cast<uint4*>(q) = make_uint4(o[0], o[1], o[2], o[3]);
           }
         fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's operand reads
-        mbar_arrive(a_ready);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_ready);
       }
 
       // ---- hidden chunks: P(i) = GEGLU(S(i) + b1).  The two warp sets (epilogue warps 0-3 / 4-7, one warp per TMEM lane
@@ -364,7 +367,8 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         tmem_ld_32x32(lane_addr + 64 + 32 * ch, g);     // and 32 gate columns
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(&s_free[half]);   // the tensor core may start S(i+1)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[half]);   // the tensor core may start S(i+1)
         // P buffer free?  (O(i-2) has read it; the first chunk of a tile reuses the buffer of the previous tile)
         if (c >= 2) mbar_wait(&p_free[half], ((c >> 1) & 1) ^ 1);
         uint8_t* prow = sP + half * FF_P_BYTES + r * 128;
@@ -385,7 +389,8 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
               make_uint4(pack16x2_f2(v0, f16), pack16x2_f2(v1, f16), pack16x2_f2(v2, f16), pack16x2_f2(v3, f16));
         }
         fence_proxy_async();
-        mbar_arrive(&p_full[half]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[half]);
         if (ch == 0 && quad == 0 && lane == 0) FF_TRACE(3, i);
       }
       ci += NH;
@@ -402,7 +407,8 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       const uint64_t al2 = pack2(p.alpha, p.alpha), be2 = pack2(1.0f - p.alpha, 1.0f - p.alpha);
       if ((ew >> 2) >= OCH) {   // narrow tiles: this warp has no output chunk, the accumulator is not its business
         tc_fence_before();
-        mbar_arrive(o_free);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(o_free);
       }
       for (int oc = ew >> 2; oc < OCH; oc += 4) {
         uint32_t o[32];
@@ -410,7 +416,8 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         tmem_ld_wait();
         if (oc + 4 >= OCH) {   // last O chunk of this warp: release the accumulator
           tc_fence_before();
-          mbar_arrive(o_free);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(o_free);
         }
         uint64_t v2[16];
         const float4* b4 = reinterpret_cast<const float4*>(sB2 + oc * 32);
