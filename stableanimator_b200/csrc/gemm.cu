@@ -387,7 +387,7 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], EW * 32 * (PAIR ? 2 : 1));   // PAIR: the epilogue threads of both CTAs, on the leader
+      mbar_init(&acc_empty[i], EW * (PAIR ? 2 : 1));   // one elected arrival per epilogue warp (PAIR: of both CTAs, on the leader)
     }
     for (int i = 0; i < EW * (EPI_RO_SLOTS + EPI_X_SLOTS); ++i) mbar_init(&epi_bar[i], 1);
     fence_barrier_init();
@@ -509,9 +509,12 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
     const float alpha = p.alpha, beta = 1.0f - p.alpha, gs = p.out_scale;
     const int my_tiles = (item_count - item_first + item_stride - 1) / item_stride;
     const uint32_t acc_empty_l0 = PAIR ? mapa_u32(&acc_empty[0], 0) : 0u, acc_empty_l1 = PAIR ? mapa_u32(&acc_empty[1], 0) : 0u;
-    auto release_acc = [&](int ab) {   // this thread has read its part of accumulator ab
-      if constexpr (PAIR) mbar_arrive_cluster(ab ? acc_empty_l1 : acc_empty_l0);
-      else mbar_arrive(&acc_empty[ab]);
+    auto release_acc = [&](int ab) {   // this warp has read its part of accumulator ab (tcgen05.wait::ld is warp-collective)
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_cluster(ab ? acc_empty_l1 : acc_empty_l0);
+        else mbar_arrive(&acc_empty[ab]);
+      }
     };
     const int cpw = (CPT - half + CSTRIDE - 1) / CSTRIDE;  // chunks of a tile handled by this warp
     const int total_chunks = my_tiles * cpw;
