@@ -62,9 +62,10 @@ class UNetB200:
                 raise ValueError(f"{k}: shape {tuple(state_dict[k].shape)} != {shp}")
         self.w: Dict[str, torch.Tensor] = {}
         # GroupNorm statistics accumulated by the producing convolution's epilogue instead of a separate statistics
-        # pass.  Correct and B-invariant (tests/test_gemm_gpu.py), but measured 0.5 ms SLOWER per B=2 call at 64x64x16
-        # (tools/unet_ab.py: the statistics pass re-reads a tensor that is still L2-resident, the epilogue work is
-        # not free) -- off by default, SA_GN_FUSE=1 turns it on
+        # pass (82 of the 105 GroupNorm sites then run the normalise pass only).  B-invariant (tests/test_gemm_gpu.py).
+        # Round 1's version was 0.5 ms slower than the separate pass (~400 k same-address fp64 atomics per launch); the
+        # round-2 epilogue (packed fp32 column sums, one fp64 atomic set per tile and group) is 0.45 ms faster per B=2
+        # call at 64x64x16 (tools/unet_env_ab.py fuse_gn_stats).  SA_GN_FUSE=0: two-pass statistics, for A/B
         self.fuse_gn_stats = os.environ.get("SA_GN_FUSE", "1") == "1"
         # zero-context (unconditional CFG branch) shortcut of the ID cross-attention; SA_SKIP_ZERO_CTX=0 for A/B
         self.skip_zero_context = os.environ.get("SA_SKIP_ZERO_CTX", "1") != "0"
