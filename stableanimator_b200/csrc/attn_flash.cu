@@ -148,6 +148,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm, int S, int C, __nv_bfl
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_slot;
+  grid_dep_sync();   // programmatic dependent launch: the set-up above overlapped the previous kernel's tail
   // Register rebalancing: the two branches below never re-join (each ends with its own CTA-wide barrier and return),
   // so ptxas allocates them under different budgets.
   if (warp >= SW) {
@@ -392,16 +393,15 @@ extern "C" int sa_attn_spatial(const void* qkv, int32_t ld, int32_t frames, int3
   __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
   if (nt == 1) {
     dim3 grid((S + FA_BM - 1) / FA_BM, heads, frames);
-    if (poly == 0) attn_flash_kernel<0, 1><<<grid, Fa3Cfg<1>::THREADS, fa3_smem<1>(), stream>>>(*tm, S, C, o, ldo, act_f16);
-    else attn_flash_kernel<8, 1><<<grid, Fa3Cfg<1>::THREADS, fa3_smem<1>(), stream>>>(*tm, S, C, o, ldo, act_f16);
+    if (poly == 0) SA_CUDA_CHECK(launch_k(attn_flash_kernel<0, 1>, grid, dim3(Fa3Cfg<1>::THREADS), fa3_smem<1>(), stream, 1, true, *tm, S, C, o, ldo, act_f16));
+    else SA_CUDA_CHECK(launch_k(attn_flash_kernel<8, 1>, grid, dim3(Fa3Cfg<1>::THREADS), fa3_smem<1>(), stream, 1, true, *tm, S, C, o, ldo, act_f16));
   } else {
     dim3 grid((S + 2 * FA_BM - 1) / (2 * FA_BM), heads, frames);
     switch (poly) {
-      case 0: attn_flash_kernel<0, 2><<<grid, Fa3Cfg<2>::THREADS, fa3_smem<2>(), stream>>>(*tm, S, C, o, ldo, act_f16); break;
-      case 4: attn_flash_kernel<4, 2><<<grid, Fa3Cfg<2>::THREADS, fa3_smem<2>(), stream>>>(*tm, S, C, o, ldo, act_f16); break;
-      default: attn_flash_kernel<8, 2><<<grid, Fa3Cfg<2>::THREADS, fa3_smem<2>(), stream>>>(*tm, S, C, o, ldo, act_f16); break;
+      case 0: SA_CUDA_CHECK(launch_k(attn_flash_kernel<0, 2>, grid, dim3(Fa3Cfg<2>::THREADS), fa3_smem<2>(), stream, 1, true, *tm, S, C, o, ldo, act_f16)); break;
+      case 4: SA_CUDA_CHECK(launch_k(attn_flash_kernel<4, 2>, grid, dim3(Fa3Cfg<2>::THREADS), fa3_smem<2>(), stream, 1, true, *tm, S, C, o, ldo, act_f16)); break;
+      default: SA_CUDA_CHECK(launch_k(attn_flash_kernel<8, 2>, grid, dim3(Fa3Cfg<2>::THREADS), fa3_smem<2>(), stream, 1, true, *tm, S, C, o, ldo, act_f16)); break;
     }
   }
-  SA_CUDA_CHECK(cudaGetLastError());
   return SA_OK;
 }

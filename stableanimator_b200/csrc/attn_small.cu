@@ -72,6 +72,7 @@ template <bool F16>   // F16: q | k | v and out hold IEEE fp16 instead of bf16
 __global__ void __launch_bounds__(AT_WARPS * 32)
 attn_temporal_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, int B, int F, int S, int C,
                      int heads, __nv_bfloat16* __restrict__ out, int ldo) {
+  grid_dep_sync();
   __shared__ __align__(128) uint8_t sm[AT_WARPS][3][AT_TILE];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long task = static_cast<long long>(blockIdx.x) * AT_WARPS + warp;
@@ -217,6 +218,7 @@ attn_id_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const float* __rest
                const float* __restrict__ iv, long long tok_stride, long long batch_stride, int F, int S,
                int C, int heads,
                __nv_bfloat16* __restrict__ out, int ldo, double* __restrict__ stats, int f16_) {
+  grid_dep_sync();
   const bool f16 = f16_ != 0;   // q / out hold IEEE fp16 instead of bf16
   extern __shared__ float sm_kv[];  // [2][NTOK][C]
   __shared__ double red[2][8];
@@ -333,6 +335,7 @@ attn_id_finalize_kernel(const double* __restrict__ stats, const float* __restric
                         long long vclip_bstride, const float* __restrict__ wv, const float* __restrict__ w_rowsum,
                         const float* __restrict__ bias, int F, int S, int C,
                         float* __restrict__ row_scale, float* __restrict__ row_bias) {
+  grid_dep_sync();
   __shared__ double red[2][8];
   __shared__ float s_a, s_shift;
   const int frame = blockIdx.x;
@@ -393,12 +396,11 @@ extern "C" int sa_attn_temporal(const void* qkv, int32_t ld, int32_t B, int32_t 
   const long long ntasks = static_cast<long long>(B) * S * heads;
   const unsigned grid = static_cast<unsigned>((ntasks + AT_WARPS - 1) / AT_WARPS);
   if (act_f16)
-    attn_temporal_kernel<true><<<grid, AT_WARPS * 32, 0, stream>>>(static_cast<const __nv_bfloat16*>(qkv), ld, B, F, S, C,
-                                                                   heads, static_cast<__nv_bfloat16*>(out), ldo);
+    SA_CUDA_CHECK(launch_k(attn_temporal_kernel<true>, dim3(grid), dim3(AT_WARPS * 32), 0, stream, 1, false,
+                           static_cast<const __nv_bfloat16*>(qkv), ld, B, F, S, C, heads, static_cast<__nv_bfloat16*>(out), ldo));
   else
-    attn_temporal_kernel<false><<<grid, AT_WARPS * 32, 0, stream>>>(static_cast<const __nv_bfloat16*>(qkv), ld, B, F, S, C,
-                                                                    heads, static_cast<__nv_bfloat16*>(out), ldo);
-  SA_CUDA_CHECK(cudaGetLastError());
+    SA_CUDA_CHECK(launch_k(attn_temporal_kernel<false>, dim3(grid), dim3(AT_WARPS * 32), 0, stream, 1, false,
+                           static_cast<const __nv_bfloat16*>(qkv), ld, B, F, S, C, heads, static_cast<__nv_bfloat16*>(out), ldo));
   return SA_OK;
 }
 
@@ -420,11 +422,9 @@ extern "C" int sa_attn_id(const void* q, int32_t ldq, const float* ik, const flo
     return rc;
   SA_CUDA_CHECK(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * B * F, stream));
   dim3 grid((S + 31) / 32, B * F, 1);
-  attn_id_kernel<4><<<grid, 256, smem, stream>>>(static_cast<const __nv_bfloat16*>(q), ldq, ik, iv,
-                                                 kv_tok_stride, kv_batch_stride, F, S, C,
-                                                 heads, static_cast<__nv_bfloat16*>(out), ldo,
-                                                 static_cast<double*>(stats), act_f16);
-  SA_CUDA_CHECK(cudaGetLastError());
+  SA_CUDA_CHECK(launch_k(attn_id_kernel<4>, grid, dim3(256), smem, stream, 1, false, static_cast<const __nv_bfloat16*>(q), ldq, ik, iv,
+                         static_cast<long long>(kv_tok_stride), static_cast<long long>(kv_batch_stride), F, S, C, heads,
+                         static_cast<__nv_bfloat16*>(out), ldo, static_cast<double*>(stats), act_f16));
   return SA_OK;
 }
 
@@ -435,9 +435,7 @@ extern "C" int sa_attn_id_finalize(const void* stats, const float* vclip, int64_
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!stats || !vclip || !wv || !w_rowsum || !bias || !row_scale || !row_bias)
     return fail(SA_ERR_INVALID, "sa_attn_id_finalize: null pointer");
-  attn_id_finalize_kernel<<<B * F, 256, 0, stream>>>(static_cast<const double*>(stats), vclip,
-                                                     vclip_batch_stride, wv, w_rowsum,
-                                                     bias, F, S, C, row_scale, row_bias);
-  SA_CUDA_CHECK(cudaGetLastError());
+  SA_CUDA_CHECK(launch_k(attn_id_finalize_kernel, dim3(B * F), dim3(256), 0, stream, 1, false, static_cast<const double*>(stats), vclip,
+                         static_cast<long long>(vclip_batch_stride), wv, w_rowsum, bias, F, S, C, row_scale, row_bias));
   return SA_OK;
 }

@@ -1,6 +1,7 @@
 // Error text, TMA tensor-map encode (driver entry point resolved at run time, no -lcuda) + cache.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <list>
@@ -138,6 +139,11 @@ int num_sms() {
     cache[dev & 63].store(n, std::memory_order_relaxed);
   }
   return n;
+}
+
+int pdl_level() {
+  const char* e = getenv("SA_PDL");   // read per launch (captured graphs keep what they were captured with)
+  return e ? (e[0] == '0' ? 0 : e[0] == '2' ? 2 : 1) : 1;
 }
 
 }  // namespace sa

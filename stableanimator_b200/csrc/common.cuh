@@ -6,6 +6,7 @@
 
 #include <atomic>
 #include <mutex>
+#include <utility>
 
 #include "../../include/sa_b200.h"
 
@@ -55,5 +56,41 @@ struct DeviceOnce {
     return rc;
   }
 };
+
+
+// Programmatic dependent launch (ptx.cuh `grid_dep_sync`).  SA_PDL = 0: off; 1 (default): the kernels with a long set-up
+// (barrier rings, TMEM allocation, tensor-map prefetch: tapped GEMM, fused feed-forward, flash attention), where the overlap
+// pays (-0.8 us per launch inside a graph); 2: every kernel -- the light ones get SLOWER (+1.6 us per launch,
+// `tools/pdl_probe.py`), so that is for measurement only.
+int pdl_level();
+
+// One launch path for the kernels of the denoising call: optional cluster (cluster_x > 1) and, for `heavy` kernels, the
+// programmatic-launch attribute.  ONLY for kernels whose every global-memory access follows a `grid_dep_wait()`.
+template <class... P, class... A>
+inline cudaError_t launch_k(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, unsigned cluster_x,
+                            bool heavy, A&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[2];
+  unsigned n = 0;
+  if (cluster_x > 1) {
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = cluster_x;
+    at[n].val.clusterDim.y = 1;
+    at[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_level() >= (heavy ? 1 : 2)) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<A>(args)...);
+}
 
 }  // namespace sa

@@ -152,6 +152,7 @@ ff_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   cluster_sync();   // the partner's barriers are initialised before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  grid_dep_sync();   // the set-up above overlapped the previous kernel's tail (programmatic dependent launch)
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -499,20 +500,7 @@ static int launch_ff(const CUtensorMap* tx, const CUtensorMap* tw1, const CUtens
   int pairs = num_sms() / 2;
   const int pair_tiles = (p.m_tiles + 1) / 2;
   if (pairs > pair_tiles) pairs = pair_tiles;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(2 * pairs, 1, 1);
-  cfg.blockDim = dim3(64 + 32 * FF_EW, 1, 1);
-  cfg.dynamicSmemBytes = L::TOTAL;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  SA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, ff_fused_kernel<KC>, *tx, *tw1, *tw2, *to, p));
+  SA_CUDA_CHECK(launch_k(ff_fused_kernel<KC>, dim3(2 * pairs), dim3(64 + 32 * FF_EW), L::TOTAL, stream, 2, true, *tx, *tw1, *tw2, *to, p));
   return SA_OK;
 }
 

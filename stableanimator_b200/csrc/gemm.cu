@@ -407,6 +407,7 @@ gemm_tap_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
   if constexpr (PAIR) cluster_sync();   // the partner's barriers exist before anything is signalled on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  grid_dep_sync();   // everything above overlapped the previous kernel's tail (programmatic dependent launch)
 
   auto tile_origin = [&](int tile, int& n0, int& q1, int& q2, int& q3) {
     uint32_t mt, nt, a, b, c;
@@ -974,10 +975,11 @@ static int launch_persist(const CUtensorMap* a0, const CUtensorMap* a1, const CU
   const bool plain = !p.row_scale && !p.row_bias && p.out_scale == 1.0f && !p.residual && !p.blend_x && p.f16_from == 0 &&
                      !p.gn_stats;
   if (plain)
-    gemm_tap_persist_kernel<BN, STP, GEGLU, EW, true><<<grid, 64 + 32 * EW, LP::TOTAL, stream>>>(*a0, *a1, *b, *o, *r, *x, p);
+    SA_CUDA_CHECK(launch_k(gemm_tap_persist_kernel<BN, STP, GEGLU, EW, true>, dim3(grid), dim3(64 + 32 * EW), LP::TOTAL, stream, 1, true,
+                           *a0, *a1, *b, *o, *r, *x, p));
   else
-    gemm_tap_persist_kernel<BN, STAGES, GEGLU, EW, false><<<grid, 64 + 32 * EW, L::TOTAL, stream>>>(*a0, *a1, *b, *o, *r, *x, p);
-  SA_CUDA_CHECK(cudaGetLastError());
+    SA_CUDA_CHECK(launch_k(gemm_tap_persist_kernel<BN, STAGES, GEGLU, EW, false>, dim3(grid), dim3(64 + 32 * EW), L::TOTAL, stream,
+                           1, true, *a0, *a1, *b, *o, *r, *x, p));
   return SA_OK;
 }
 
@@ -1007,23 +1009,13 @@ static int launch_pair(const CUtensorMap* a0, const CUtensorMap* a1, const CUten
   if (pairs > p.total_tiles) pairs = p.total_tiles;
   const bool plain = !p.row_scale && !p.row_bias && p.out_scale == 1.0f && !p.residual && !p.blend_x && p.f16_from == 0 &&
                      !p.gn_stats;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(2 * pairs, 1, 1);
-  cfg.blockDim = dim3(64 + 32 * EW, 1, 1);
-  cfg.dynamicSmemBytes = plain ? LP::TOTAL : L::TOTAL;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  const dim3 grid(2 * pairs), block(64 + 32 * EW);
   if (plain)
-    SA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tap_persist_kernel<BN, STAGES + 1, false, EW, true, true>, *a0, *a1, *b, *o, *r, *x, p));
+    SA_CUDA_CHECK(launch_k(gemm_tap_persist_kernel<BN, STAGES + 1, false, EW, true, true>, grid, block, LP::TOTAL, stream, 2, true,
+                           *a0, *a1, *b, *o, *r, *x, p));
   else
-    SA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tap_persist_kernel<BN, STAGES, false, EW, false, true>, *a0, *a1, *b, *o, *r, *x, p));
+    SA_CUDA_CHECK(launch_k(gemm_tap_persist_kernel<BN, STAGES, false, EW, false, true>, grid, block, L::TOTAL, stream, 2, true,
+                           *a0, *a1, *b, *o, *r, *x, p));
   return SA_OK;
 }
 

@@ -38,6 +38,7 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x0,
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
   if (tid < 64) sm[tid >> 1][tid & 1] = 0.0;
   __syncthreads();
+  grid_dep_sync();
   const int c = threadIdx.x * 8;
   const long long ns = blockIdx.y;
   const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
@@ -109,6 +110,7 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0,
                                 const double* __restrict__ stats, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, float eps, int do_silu,
                                 __nv_bfloat16* __restrict__ out, int ldo, int f16) {
+  grid_dep_sync();
   const int c = threadIdx.x * 8;
   const long long ns = blockIdx.y;
   const double n = static_cast<double>(P) * cpg;
@@ -179,6 +181,7 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, int ldx, long long M, int 
                  const float* __restrict__ addv, int rows_per_group,
                  __nv_bfloat16* __restrict__ x_out, int ldxo, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y, int ldy, int f16) {
+  grid_dep_sync();
   constexpr int RPW = 32 / LPR;  // rows per warp
   const int lane = threadIdx.x & 31;
   const int sub = lane / LPR, l = lane % LPR;
@@ -300,6 +303,7 @@ layernorm_stream_kernel(const __nv_bfloat16* __restrict__ x, long long M, const 
     fence_barrier_init();
   }
   __syncthreads();
+  grid_dep_sync();
   auto tile_bytes = [&](long long tile) -> uint32_t {
     long long rows = M - tile * L::TILE_ROWS;
     if (rows > L::TILE_ROWS) rows = L::TILE_ROWS;
@@ -459,6 +463,7 @@ gn_stream_kernel(const GnStreamP p) {
   }
   if (!APPLY && threadIdx.x < 64) sm_stats[threadIdx.x] = 0.0;
   __syncthreads();
+  grid_dep_sync();
 
   if (warp == GN_CW) {
     // ------------------------------------------------------------ producer / store issuer
@@ -694,25 +699,21 @@ static int groupnorm_impl(const void* x0, const void* x1, int32_t c0, int32_t c1
       if (g1 > sp.n_tiles) g1 = sp.n_tiles;
       if (g2 > sp.n_tiles) g2 = sp.n_tiles;
       if (!have_stats) {
-        gn_stream_kernel<false><<<static_cast<unsigned>(g1), GN_CT + 32, smem_stats, stream>>>(sp);
-        SA_CUDA_CHECK(cudaGetLastError());
+        SA_CUDA_CHECK(launch_k(gn_stream_kernel<false>, dim3(static_cast<unsigned>(g1)), dim3(GN_CT + 32), smem_stats, stream, 1, false, sp));
       }
-      gn_stream_kernel<true><<<static_cast<unsigned>(g2), GN_CT + 32, smem_apply, stream>>>(sp);
-      SA_CUDA_CHECK(cudaGetLastError());
+      SA_CUDA_CHECK(launch_k(gn_stream_kernel<true>, dim3(static_cast<unsigned>(g2)), dim3(GN_CT + 32), smem_apply, stream, 1, false, sp));
       return SA_OK;
     }
   }
   if (!have_stats) {
-    gn_stats_kernel<<<grid, block, 0, stream>>>(
-        static_cast<const __nv_bfloat16*>(x0), static_cast<const __nv_bfloat16*>(x1), c0, c1, ld0, ld1,
-        rows_per_stat, cpg, rpc, static_cast<double*>(stats_ws), f16);
-    SA_CUDA_CHECK(cudaGetLastError());
+    SA_CUDA_CHECK(launch_k(gn_stats_kernel, grid, block, 0, stream, 1, false, static_cast<const __nv_bfloat16*>(x0),
+                           static_cast<const __nv_bfloat16*>(x1), c0, c1, ld0, ld1, static_cast<long long>(rows_per_stat), cpg, rpc,
+                           static_cast<double*>(stats_ws), f16));
   }
-  gn_apply_kernel<<<grid, block, 0, stream>>>(
-      static_cast<const __nv_bfloat16*>(x0), static_cast<const __nv_bfloat16*>(x1), c0, c1, ld0, ld1,
-      rows_per_stat, cpg, rpc, static_cast<const double*>(stats_ws), gamma, beta, eps, do_silu,
-      static_cast<__nv_bfloat16*>(out), ldo, f16);
-  SA_CUDA_CHECK(cudaGetLastError());
+  SA_CUDA_CHECK(launch_k(gn_apply_kernel, grid, block, 0, stream, 1, false, static_cast<const __nv_bfloat16*>(x0),
+                         static_cast<const __nv_bfloat16*>(x1), c0, c1, ld0, ld1, static_cast<long long>(rows_per_stat), cpg, rpc,
+                         static_cast<const double*>(stats_ws), gamma, beta, eps, do_silu, static_cast<__nv_bfloat16*>(out), ldo,
+                         f16));
   return SA_OK;
 }
 
@@ -771,15 +772,15 @@ extern "C" int sa_layernorm(const void* x, int32_t ldx, int64_t rows, int32_t c,
     const long long nt = (rows + L::TILE_ROWS - 1) / L::TILE_ROWS;                                        \
     long long g = static_cast<long long>(n_sm) * (L::SMEM <= 110 * 1024 ? 2 : 1);                         \
     if (g > nt) g = nt;                                                                                   \
-    layernorm_stream_kernel<LPR, OPL, XO><<<static_cast<unsigned>(g), 32 * (LN_CW + 1), L::SMEM, stream>>>( \
-        xp, rows, addv, rpg, xo, gamma, beta, eps, yp, act_f16);                                          \
+    SA_CUDA_CHECK(launch_k(layernorm_stream_kernel<LPR, OPL, XO>, dim3(static_cast<unsigned>(g)), dim3(32 * (LN_CW + 1)), \
+                           L::SMEM, stream, 1, false, xp, rows, addv, rpg, xo, gamma, beta, eps, yp, act_f16));  \
   } while (0)
 #define SA_LN(LPR, OPL)                                                                               \
   if (dense && LnStream<LPR, OPL, true>::SMEM <= 227 * 1024) {                                        \
     if (xo) SA_LN_STREAM(LPR, OPL, true); else SA_LN_STREAM(LPR, OPL, false);                         \
   } else                                                                                              \
-    layernorm_kernel<LPR, OPL><<<grid, warps * 32, 0, stream>>>(xp, ldx, rows, c, addv, rpg, xo, ldxo, \
-                                                                gamma, beta, eps, yp, ldy, act_f16)
+    SA_CUDA_CHECK(launch_k(layernorm_kernel<LPR, OPL>, dim3(grid), dim3(warps * 32), 0, stream, 1, false, xp, ldx, rows, c, addv, rpg, \
+                           xo, ldxo, gamma, beta, eps, yp, ldy, act_f16))
 #define SA_LN_ROW(LPR)                                                         \
   switch (opl) {                                                               \
     case 1: SA_LN(LPR, 1); break;                                              \

@@ -122,6 +122,18 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
 }
+// Programmatic dependent launch (launch attribute programmaticStreamSerialization, common.cuh `launch_k`): a kernel
+// launched with it may start while its predecessor in the stream is still running.  `grid_dep_launch` lets the successor
+// of THIS grid be scheduled once every CTA of this grid has executed it (or exited) -- call it after the CTA's own TMEM
+// allocation, or a co-resident successor CTA could take the columns and then block in its wait; `grid_dep_wait` returns
+// when the predecessor grid has completed and its writes are visible -- no global memory the predecessor may write OR
+// read may be touched before it.  Both are no-ops under a plain launch.
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_sync() {
+  grid_dep_launch();
+  grid_dep_wait();
+}
 __device__ __forceinline__ void cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }

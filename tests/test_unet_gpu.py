@@ -148,3 +148,25 @@ def test_unet_fused_groupnorm_statistics_option():
     print(f"fused-statistics UNet vs reference: {rel_l2(fused, ref):.3e} (two-pass: {rel_l2(plain, ref):.3e})")
     assert rel_l2(fused, ref) <= 1e-2
     assert torch.equal(both[:1], a) and torch.equal(both[1:], fused)
+
+
+def test_programmatic_dependent_launch_keeps_the_bits(monkeypatch):
+    """SA_PDL (common.cuh `launch_k`): the tensor-core kernels start under the tail of their predecessor and wait in
+    `griddepcontrol.wait` before touching global memory.  Eager and graph-replayed calls give the bits of plain launches."""
+    c = load_golden("tiny_cond_f4_16x16")
+    m = model(c["cfg"], c["gold"]["seed"])
+    pl = c["pose_latents"].cuda()
+    args = (c["sample"].cuda(), c["t"], c["ehs"].cuda(), c["ati"].cuda())
+    outs = {}
+    for level in ("0", "1", "2"):
+        monkeypatch.setenv("SA_PDL", level)
+        outs[level] = m(*args, pose_latents=pl)[0].clone()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            o = m(*args, pose_latents=pl)[0]
+        for _ in range(3):
+            g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(o, outs[level]), f"graph replay differs from the eager call at SA_PDL={level}"
+    assert torch.equal(outs["1"], outs["0"]) and torch.equal(outs["2"], outs["0"])

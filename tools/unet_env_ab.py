@@ -1,5 +1,7 @@
 """A/B of env-selected UNet options in ONE process (graphs replayed alternately): python tools/unet_env_ab.py ATTR
-where ATTR is a boolean attribute of UNetB200 (upsample_phases, fuse_gn_stats, skip_zero_context)."""
+where ATTR is a boolean attribute of UNetB200 (upsample_phases, fuse_gn_stats, skip_zero_context) or env:NAME=v1,v2,...
+for an environment switch the library reads per launch (env:SA_PDL=0,1,2)."""
+import os
 import sys
 from pathlib import Path
 
@@ -21,8 +23,18 @@ ati = inp["added_time_ids"][:B].cuda()
 x = torch.randn(B * F, h, w, 8, device="cuda").bfloat16()
 t = torch.tensor(1.0, device="cuda")
 graphs, outs, ctxs = {}, {}, {}   # ctxs: the graphs read these buffers, keep them alive
-for val in (True, False):
-    setattr(unet, attr, val)
+vals = (True, False)
+if attr.startswith("env:"):
+    attr, _, vs = attr[4:].partition("=")
+    vals = tuple(vs.split(","))
+    env = True
+else:
+    env = False
+for val in vals:
+    if env:
+        os.environ[attr] = val
+    else:
+        setattr(unet, attr, val)
     ctx = ctxs[val] = unet.prepare_context(inp["encoder_hidden_states"][:B].cuda())
     unet.forward_nhwc(x, t, ctx, ati, B, F, h, w)
     torch.cuda.synchronize()
@@ -31,7 +43,7 @@ for val in (True, False):
         outs[val] = unet.forward_nhwc(x, t, ctx, ati, B, F, h, w)
     graphs[val] = g
 times = {k: [] for k in graphs}
-for _ in range(8):
+for _ in range(12):
     for val, g in graphs.items():
         g.replay()
         torch.cuda.synchronize()
@@ -45,5 +57,7 @@ for _ in range(8):
 for val, ts in times.items():
     ts = sorted(ts)
     print(f"{attr}={val!s:5s}: median {ts[len(ts) // 2]:.3f} ms  min {ts[0]:.3f}  max {ts[-1]:.3f}")
-d = (outs[True][:, :4].double() - outs[False][:, :4].double()).norm() / outs[False][:, :4].double().norm()
-print(f"output rel-L2 between the two: {d.item():.3e}")
+ref = outs[vals[-1]][:, :4].double()
+for val in vals[:-1]:
+    d = (outs[val][:, :4].double() - ref).norm() / ref.norm()
+    print(f"output rel-L2 {attr}={val} vs {attr}={vals[-1]}: {d.item():.3e}")
