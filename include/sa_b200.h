@@ -84,7 +84,7 @@ typedef struct sa_gemm_args {
   int32_t f16_from_col;  /* > 0: output columns >= this (multiple of 32) are stored as fp16; 0 = all bf16 */
   /* Fused GroupNorm statistics of the OUTPUT (the tensor the next nn.GroupNorm normalises, unet.py:1632-1643, */
   /* :1709-1731, :575): when gn_stats != NULL the epilogue adds Sum / Sum^2 of the bf16-rounded results into    */
-  /* gn_stats fp64 [M / gn_rows_per_stat, n_out / gn_cpg, 2] (zeroed by the call) -- exactly what the statistics */
+  /* gn_stats fp64 [M / gn_rows_per_stat, n_out / gn_cpg, 2] (zeroed by the call unless gn_stats_zeroed) -- exactly what the statistics */
   /* pass of sa_groupnorm would read back from HBM; consume them with sa_groupnorm_apply.  bf16 output only      */
   /* (no geglu / out_f32 / f16_from_col), n % tile == 0, M % gn_rows_per_stat == 0, n_out % gn_cpg == 0.         */
   void* gn_stats;
@@ -102,6 +102,9 @@ typedef struct sa_gemm_args {
   /* 16-bit format of a0 / a1 / w / residual / blend_x / out: 0 = bf16, 1 = IEEE fp16 (the reference's default inference  */
   /* dtype, inference_basic.py:486); fp16 stores saturate at +-65504.  f16_from_col is implied for every column.        */
   int32_t act_f16;
+  /* 1: the caller has already zeroed gn_stats (e.g. one fill for all the statistics buffers of a UNet call), so the call */
+  /* issues no memset of its own in front of the kernel; 0: gn_stats is zeroed by the call.                              */
+  int32_t gn_stats_zeroed;
 } sa_gemm_args;
 
 int sa_gemm_tap(const sa_gemm_args* args, void* stream);

@@ -47,6 +47,7 @@ class GemmArgs(C.Structure):
         ("ldc2", C.c_int64), ("ldc3", C.c_int64),
         ("in_stride", C.c_int32),
         ("act_f16", C.c_int32),
+        ("gn_stats_zeroed", C.c_int32),
     ]
 
 

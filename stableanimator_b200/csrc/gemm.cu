@@ -1176,7 +1176,8 @@ extern "C" int sa_gemm_tap(const sa_gemm_args* a, void* stream_) {
     p.gn_groups = a->n / a->gn_cpg;
     p.fd_gcpg.init(static_cast<uint32_t>(a->gn_cpg));
     p.fd_grps.init(static_cast<uint32_t>(a->gn_rows_per_stat));
-    SA_CUDA_CHECK(cudaMemsetAsync(a->gn_stats, 0, sizeof(double) * 2 * p.gn_groups * (M / a->gn_rows_per_stat), stream));
+    if (!a->gn_stats_zeroed)
+      SA_CUDA_CHECK(cudaMemsetAsync(a->gn_stats, 0, sizeof(double) * 2 * p.gn_groups * (M / a->gn_rows_per_stat), stream));
   }
   if (v2_ok) {
     // epilogue tensor maps: [n_out cols, d1, d2, d3]; box = (32 columns) x the 32-row sub-box

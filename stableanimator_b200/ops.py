@@ -119,6 +119,7 @@ def gemm_tap(
     gn_stats: Optional[torch.Tensor] = None,
     gn_rows_per_stat: int = 0,
     in_stride: int = 1,
+    gn_stats_zeroed: bool = False,
 ) -> torch.Tensor:
     """``out = epilogue(sum_taps A(shifted) @ W^T)`` -- see ``sa_gemm_tap`` in include/sa_b200.h.
 
@@ -202,6 +203,7 @@ def gemm_tap(
                 gn_stats.numel() != rows // gn_rows_per_stat * 64:
             raise ValueError("gn_stats must be a contiguous fp64 [rows / gn_rows_per_stat, 32, 2] tensor")
         args.gn_stats, args.gn_cpg, args.gn_rows_per_stat = gn_stats.data_ptr(), n_out // 32, int(gn_rows_per_stat)
+        args.gn_stats_zeroed = int(bool(gn_stats_zeroed))  # the caller filled it with zeros: no memset in front of the kernel
     check(lib().sa_gemm_tap(C.byref(args), _stream()), "sa_gemm_tap")
     return out
 

@@ -39,6 +39,26 @@ class _Ctx:
     __slots__ = ("all", "wv", "tconst", "b", "zero_prefix", "ffaddv")
 
 
+class _StatsArena:
+    """fp64 [n, 32, 2] GroupNorm-statistics buffers of ONE UNet call, carved from chunks that are zeroed with one fill each
+    (``gemm_tap(gn_stats_zeroed=self.stats_arena)``): inside a CUDA graph that is one memset node for the whole call instead of one
+    in front of every convolution -- a memset node between two kernels also keeps the convolution from starting
+    under its predecessor's tail (SA_PDL)."""
+    CHUNK = 1 << 18  # doubles (2 MB): a B=2, F=16 call uses ~0.8 MB
+
+    def __init__(self, dev):
+        self.dev, self.buf, self.used = dev, None, 0
+
+    def take(self, n: int) -> torch.Tensor:
+        need = n * 64
+        if self.buf is None or self.used + need > self.buf.numel():
+            self.buf = torch.zeros(max(self.CHUNK, need), device=self.dev, dtype=torch.float64)
+            self.used = 0
+        out = self.buf[self.used:self.used + need].view(n, 32, 2)
+        self.used += need
+        return out
+
+
 class UNetB200:
     """Weights packed for the kernels + the forward orchestration."""
 
@@ -67,6 +87,8 @@ class UNetB200:
         # round-2 epilogue (packed fp32 column sums, one fp64 atomic set per tile and group) is 0.45 ms faster per B=2
         # call at 64x64x16 (tools/unet_env_ab.py fuse_gn_stats).  SA_GN_FUSE=0: two-pass statistics, for A/B
         self.fuse_gn_stats = os.environ.get("SA_GN_FUSE", "1") == "1"
+        # one fill of all the statistics buffers per call instead of a memset in front of every convolution (A/B: False)
+        self.stats_arena = os.environ.get("SA_STATS_ARENA", "1") == "1"
         # zero-context (unconditional CFG branch) shortcut of the ID cross-attention; SA_SKIP_ZERO_CTX=0 for A/B
         self.skip_zero_context = os.environ.get("SA_SKIP_ZERO_CTX", "1") != "0"
         # LayerNorm + GEGLU feed-forward + residual (+ blend) as ONE kernel where the channel count allows it (C <= 320: the
@@ -253,7 +275,7 @@ class UNetB200:
         return self._pos_cache[key]
 
     # ------------------------------------------------------------------ blocks
-    def _res_block(self, r: ResSpec, x0, x1, temb, B, F, h, wd, x0_stats=None, out_stats=None):
+    def _res_block(self, r: ResSpec, x0, x1, temb, B, F, h, wd, arena, x0_stats=None, out_stats=None):
         """SpatioTemporalResBlock.forward (unet.py:1579-1608) on NHWC tokens.  x0 [M, C0] (+ skip x1).
         The statistics of the three inner GroupNorms are accumulated by the epilogue of the convolution that
         produces their input (sa_gemm_args.gn_stats), so each of them is a single normalise pass.  ``x0_stats``:
@@ -264,14 +286,15 @@ class UNetB200:
         s_, t_ = f"{r.name}.spatial_res_block", f"{r.name}.temporal_res_block"
         grid2d, gridt = (wd, h, B * F), (S, F, B)
         fuse = self.fuse_gn_stats
-        st_f = torch.empty((B * F, 32, 2), device=self.dev, dtype=torch.float64) if fuse else None   # per frame
-        st_t1 = torch.empty((B, 32, 2), device=self.dev, dtype=torch.float64) if fuse else None      # whole tile
-        st_t2 = torch.empty((B, 32, 2), device=self.dev, dtype=torch.float64) if fuse else None
+        st_f = arena.take(B * F) if fuse else None   # per frame
+        st_t1 = arena.take(B) if fuse else None      # whole tile
+        st_t2 = arena.take(B) if fuse else None
         n1 = ops.groupnorm(x0, w[f"{s_}.norm1.g"], w[f"{s_}.norm1.b"], r.eps, S, x1=x1, silu=True,
                            stats_ws=x0_stats, stats_ready=x0_stats is not None)
         o_s = self.temb_off[s_]
         h1 = ops.gemm_tap(n1, w[f"{s_}.conv1.w"], grid=grid2d, taps=ops.TAPS_3X3, bias=w[f"{s_}.conv1.b"],
-                          row_bias=temb[:, o_s:o_s + r.cout], rows_per_group=F * S, gn_stats=st_f, gn_rows_per_stat=S)
+                          row_bias=temb[:, o_s:o_s + r.cout], rows_per_group=F * S, gn_stats=st_f, gn_rows_per_stat=S,
+                          gn_stats_zeroed=self.stats_arena)
         n2 = ops.groupnorm(h1, w[f"{s_}.norm2.g"], w[f"{s_}.norm2.b"], r.eps, S, silu=True, stats_ws=st_f,
                            stats_ready=fuse)
         if r.shortcut:
@@ -279,20 +302,21 @@ class UNetB200:
         else:
             sc = x0
         xs = ops.gemm_tap(n2, w[f"{s_}.conv2.w"], grid=grid2d, taps=ops.TAPS_3X3, bias=w[f"{s_}.conv2.b"],
-                          residual=sc, gn_stats=st_t1, gn_rows_per_stat=F * S)
+                          residual=sc, gn_stats=st_t1, gn_rows_per_stat=F * S, gn_stats_zeroed=self.stats_arena)
         # temporal: GroupNorm statistics over the whole tile (5-D input, unet.py:1749), 3-tap conv over frames
         n3 = ops.groupnorm(xs, w[f"{t_}.norm1.g"], w[f"{t_}.norm1.b"], r.eps, F * S, silu=True, stats_ws=st_t1,
                            stats_ready=fuse)
         o_t = self.temb_off[t_]
         h2 = ops.gemm_tap(n3, w[f"{t_}.conv1.w"], grid=gridt, taps=ops.TAPS_T3, bias=w[f"{t_}.conv1.b"],
                           row_bias=temb[:, o_t:o_t + r.cout], rows_per_group=F * S, gn_stats=st_t2,
-                          gn_rows_per_stat=F * S)
+                          gn_rows_per_stat=F * S, gn_stats_zeroed=self.stats_arena)
         n4 = ops.groupnorm(h2, w[f"{t_}.norm2.g"], w[f"{t_}.norm2.b"], r.eps, F * S, silu=True, stats_ws=st_t2,
                            stats_ready=fuse)
         # conv2 + residual (xs), then AlphaBlender: alpha*xs + (1-alpha)*(xs + conv2) == xs + (1-alpha)*conv2,
         # one epilogue with a single residual read
         return ops.gemm_tap(n4, w[f"{t_}.conv2.w"], grid=gridt, taps=ops.TAPS_T3, bias=w[f"{t_}.conv2.b"],
-                            residual=xs, out_scale=1.0 - w[f"{r.name}.alpha"], gn_stats=out_stats, gn_rows_per_stat=S)
+                            residual=xs, out_scale=1.0 - w[f"{r.name}.alpha"], gn_stats=out_stats, gn_rows_per_stat=S,
+                            gn_stats_zeroed=self.stats_arena)
 
     def _tst(self, t: TstSpec, x, ctx: _Ctx, B, F, h, wd, x_stats=None):
         """TransformerSpatioTemporalModel.forward (unet.py:623-708) on NHWC tokens x [M, C].  ``x_stats``: per-frame
@@ -376,9 +400,6 @@ class UNetB200:
                               alpha=w[f"{t.name}.alpha"])
         return ops.gemm_tap(z4, w[f"{t.name}.proj_out.w"], bias=w[f"{t.name}.proj_out.b"], residual=x)
 
-    def _frame_stats(self, n: int) -> Optional[torch.Tensor]:
-        return torch.empty((n, 32, 2), device=self.dev, dtype=torch.float64) if self.fuse_gn_stats else None
-
     def _conv_in(self, x_in: torch.Tensor, pose: Optional[torch.Tensor], pose_from: int) -> torch.Tensor:
         """conv_in (unet.py:283) + pose residual on the frames >= pose_from (:284-286) -> tokens [M, C0].
         K = 72 is gathered to a [M, 128] operand and runs on the tensor-core GEMM (two launches when only
@@ -411,7 +432,8 @@ class UNetB200:
         if ctx.b != B:
             raise ValueError("context batch does not match")
         temb = self._time_embedding(timestep, added_time_ids, B)
-        c0 = cfg.block_out_channels[0]
+        arena = _StatsArena(self.dev)
+        fstats = (lambda: arena.take(B * F)) if self.fuse_gn_stats else (lambda: None)  # per-frame statistics of a block output
         x = self._conv_in(x_in.reshape(B * F, h, wd, cfg.in_channels), pose_nhwc, pose_batch_from * F)
         if taps is not None:
             taps["conv_in"] = x
@@ -420,8 +442,8 @@ class UNetB200:
         for st in self.stages:
             if st.kind == "down":
                 for r, t in zip(st.res, st.tst):
-                    xst = self._frame_stats(B * F) if t is not None else None
-                    x = self._res_block(r, x, None, temb, B, F, ch, cw, out_stats=xst)
+                    xst = fstats() if t is not None else None
+                    x = self._res_block(r, x, None, temb, B, F, ch, cw, arena, out_stats=xst)
                     if taps is not None:
                         taps[r.name] = x
                     if t is not None:
@@ -443,16 +465,16 @@ class UNetB200:
                     ch, cw = ch // 2, cw // 2
                     skips.append(x)
             elif st.kind == "mid":
-                xst = self._frame_stats(B * F)
-                x = self._res_block(st.res[0], x, None, temb, B, F, ch, cw, out_stats=xst)
+                xst = fstats()
+                x = self._res_block(st.res[0], x, None, temb, B, F, ch, cw, arena, out_stats=xst)
                 x = self._tst(st.tst[0], x, ctx, B, F, ch, cw, x_stats=xst)
-                x = self._res_block(st.res[1], x, None, temb, B, F, ch, cw)
+                x = self._res_block(st.res[1], x, None, temb, B, F, ch, cw, arena)
                 if taps is not None:
                     taps["mid_block"] = x
             else:
                 for r, t in zip(st.res, st.tst):
-                    xst = self._frame_stats(B * F) if t is not None else None
-                    x = self._res_block(r, x, skips.pop(), temb, B, F, ch, cw, out_stats=xst)
+                    xst = fstats() if t is not None else None
+                    x = self._res_block(r, x, skips.pop(), temb, B, F, ch, cw, arena, out_stats=xst)
                     if t is not None:
                         x = self._tst(t, x, ctx, B, F, ch, cw, x_stats=xst)
                     if taps is not None:

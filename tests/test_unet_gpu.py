@@ -153,18 +153,23 @@ def test_unet_fused_groupnorm_statistics_option():
 def test_programmatic_dependent_launch_keeps_the_bits(monkeypatch):
     """SA_PDL (common.cuh `launch_k`): the tensor-core kernels start under the tail of their predecessor and wait in
     `griddepcontrol.wait` before touching global memory.  Eager and graph-replayed calls give the bits of plain launches."""
+    from stableanimator_b200 import ops
     c = load_golden("tiny_cond_f4_16x16")
     m = model(c["cfg"], c["gold"]["seed"])
-    pl = c["pose_latents"].cuda()
-    args = (c["sample"].cuda(), c["t"], c["ehs"].cuda(), c["ati"].cuda())
+    B, F, _, h, w = c["sample"].shape
+    x = ops.nchw_to_nhwc(c["sample"].cuda().reshape(B * F, -1, h, w).contiguous(), dtype=m.dtype)
+    pose = ops.nchw_to_nhwc(c["pose_latents"].cuda().contiguous(), dtype=m.dtype)
+    t = torch.tensor(float(c["t"]), device="cuda")
+    ctx, ati = m.prepare_context(c["ehs"].cuda()), c["ati"].cuda()
+    run = lambda: m.forward_nhwc(x, t, ctx, ati, B, F, h, w, pose, 0)  # noqa: E731
     outs = {}
     for level in ("0", "1", "2"):
         monkeypatch.setenv("SA_PDL", level)
-        outs[level] = m(*args, pose_latents=pl)[0].clone()
+        outs[level] = run().clone()
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            o = m(*args, pose_latents=pl)[0]
+            o = run()
         for _ in range(3):
             g.replay()
         torch.cuda.synchronize()
