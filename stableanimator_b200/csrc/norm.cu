@@ -103,6 +103,15 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x0,
   if (tid < 64) atomicAdd(&stats[(ns * 32 + (tid >> 1)) * 2 + (tid & 1)], sm[tid >> 1][tid & 1]);
 }
 
+// (rstd, -mean * rstd) of one group from its fp64 (Sum, Sum^2): three fp64 operations, the rest in fp32
+__device__ __forceinline__ float2 gn_group_scale(const double* __restrict__ st, double inv_n, float eps) {
+  const double mean = st[0] * inv_n;
+  double var = st[1] * inv_n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = rsqrtf(static_cast<float>(var) + eps);
+  return make_float2(rstd, -static_cast<float>(mean) * rstd);
+}
+
 // ------------------------------------------------------------------ GroupNorm apply (+SiLU)
 __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0,
                                 const __nv_bfloat16* __restrict__ x1, int C0, int C1, int ld0,
@@ -113,18 +122,21 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0,
   grid_dep_sync();
   const int c = threadIdx.x * 8;
   const long long ns = blockIdx.y;
-  const double n = static_cast<double>(P) * cpg;
+  // mean / rstd of the 32 groups once per CTA (fp64 only for the cancellation in E[x^2] - mean^2; fp64 division and
+  // square root in every thread used to be most of this kernel's fixed cost)
+  __shared__ float2 s_mr[32];   // (rstd, -mean * rstd)
+  {
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    if (tid < 32) s_mr[tid] = gn_group_scale(stats + (ns * 32 + tid) * 2, 1.0 / (static_cast<double>(P) * cpg), eps);
+    __syncthreads();
+  }
   float a[8], b[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    const int g = (c + k) / cpg;
-    const double mean = stats[(ns * 32 + g) * 2] / n;
-    double var = stats[(ns * 32 + g) * 2 + 1] / n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float2 mr = s_mr[(c + k) / cpg];
     const float ga = gamma[c + k];
-    a[k] = rstd * ga;
-    b[k] = beta[c + k] - static_cast<float>(mean) * rstd * ga;
+    a[k] = mr.x * ga;
+    b[k] = fmaf(mr.y, ga, beta[c + k]);
   }
   const __nv_bfloat16* src;
   long long ld;
@@ -334,60 +346,93 @@ layernorm_stream_kernel(const __nv_bfloat16* __restrict__ x, long long M, const 
           issue_load(i - 1 + LN_ST);
         }
       }
-      tma_store_wait_all();
+      tma_store_wait_read<0>();   // shared memory may go once the stores have read it; the writes land by grid end
     }
   } else {
     // ------------------------------------------------------------ consumers
+    // packed fp32x2 arithmetic throughout (add2 / fma2): the pass is bound by its instruction stream, not by HBM
     constexpr int RPW = L::RPW;
     const int sub = lane / LPR, l = lane % LPR;
+    const bool h16 = f16 != 0;
+    // group (addv row) of the current tile's row, tracked without a 64-bit division per tile
+    long long grp = 0, grp_row = 0;   // grp_row = first row of group `grp`
+    if (addv) {
+      const long long row0 = t_begin * L::TILE_ROWS + warp * RPW + sub;
+      grp = row0 / rows_per_group;
+      grp_row = grp * rows_per_group;
+    }
     for (int i = 0; i < my_tiles; ++i) {
       const int s = i % LN_ST;
       const long long row = (t_begin + i) * L::TILE_ROWS + warp * RPW + sub;
       const bool active = row < M;
       uint8_t* base = smem + s * L::STAGE_BYTES + (warp * RPW + sub) * (C * 2);
+      const float* av = nullptr;
+      if (addv && active) {
+        while (row >= grp_row + rows_per_group) {
+          ++grp;
+          grp_row += rows_per_group;
+        }
+        av = addv + grp * C;
+      }
       mbar_wait(&full[s], (i / LN_ST) & 1);
-      float v[OPL][8];
-      float sum = 0.f;
-      const float* av = (addv && active) ? addv + (row / rows_per_group) * C : nullptr;
+      uint64_t v[OPL][4];
+      uint64_t sum2 = 0ull;   // (0.f, 0.f)
 #pragma unroll
       for (int o = 0; o < OPL; ++o) {
         const int oc = l + LPR * o;
         if (active) {
-          load8s(base + oc * 16, v[o], f16);
+          const uint4 q = *reinterpret_cast<const uint4*>(base + oc * 16);
+          v[o][0] = h16x2_to_f32x2(q.x, h16);
+          v[o][1] = h16x2_to_f32x2(q.y, h16);
+          v[o][2] = h16x2_to_f32x2(q.z, h16);
+          v[o][3] = h16x2_to_f32x2(q.w, h16);
         } else {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) v[o][k] = 0.f;
+          for (int k = 0; k < 4; ++k) v[o][k] = 0ull;
         }
         if (av) {
           const float4 a0 = __ldg(reinterpret_cast<const float4*>(av + oc * 8));
           const float4 a1 = __ldg(reinterpret_cast<const float4*>(av + oc * 8 + 4));
-          v[o][0] += a0.x; v[o][1] += a0.y; v[o][2] += a0.z; v[o][3] += a0.w;
-          v[o][4] += a1.x; v[o][5] += a1.y; v[o][6] += a1.z; v[o][7] += a1.w;
+          v[o][0] = add2(v[o][0], pack2(a0.x, a0.y));
+          v[o][1] = add2(v[o][1], pack2(a0.z, a0.w));
+          v[o][2] = add2(v[o][2], pack2(a1.x, a1.y));
+          v[o][3] = add2(v[o][3], pack2(a1.z, a1.w));
           if (XOUT) {
-            store8s(base + L::TILE_BYTES + oc * 16, v[o], f16);
-            // keep the rounded value: it is what every later consumer of the stream reads
+            // store x + addv and keep the ROUNDED value: it is what every later consumer of the stream reads
+            uint32_t w[4];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[o][k] = round16(v[o][k], f16);
+            for (int k = 0; k < 4; ++k) {
+              w[k] = pack16x2_f2(v[o][k], h16);
+              v[o][k] = h16x2_to_f32x2(w[k], h16);
+            }
+            *reinterpret_cast<uint4*>(base + L::TILE_BYTES + oc * 16) = make_uint4(w[0], w[1], w[2], w[3]);
           }
         }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) sum += v[o][k];
+        for (int k = 0; k < 4; ++k) sum2 = add2(sum2, v[o][k]);
       }
+      const float2 sf = unpack2(sum2);
+      float sum = sf.x + sf.y;
 #pragma unroll
       for (int d = LPR / 2; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
       const float mean = sum / static_cast<float>(C);
-      float var = 0.f;
+      const uint64_t nmean2 = pack2(-mean, -mean);
+      uint64_t var2 = 0ull;
 #pragma unroll
       for (int o = 0; o < OPL; ++o) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float d = v[o][k] - mean;
-          var += d * d;
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t d2 = add2(v[o][k], nmean2);
+          var2 = fma2(d2, d2, var2);
+          v[o][k] = d2;   // keep the centred value: the normalise step is one multiply
         }
       }
+      const float2 vf = unpack2(var2);
+      float var = vf.x + vf.y;
 #pragma unroll
       for (int d = LPR / 2; d > 0; d >>= 1) var += __shfl_xor_sync(0xffffffffu, var, d);
       const float rstd = rsqrtf(var / static_cast<float>(C) + eps);
+      const uint64_t rstd2 = pack2(rstd, rstd);
       if (active) {
 #pragma unroll
         for (int o = 0; o < OPL; ++o) {
@@ -396,12 +441,11 @@ layernorm_stream_kernel(const __nv_bfloat16* __restrict__ x, long long M, const 
           const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + oc * 8 + 4));
           const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + oc * 8));
           const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + oc * 8 + 4));
-          const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-          float o8[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) o8[k] = fmaf((v[o][k] - mean) * rstd, g[k], bb[k]);
-          store8s(base + oc * 16, o8, f16);
+          const uint32_t w0 = pack16x2_f2(fma2(mul2(v[o][0], rstd2), pack2(g0.x, g0.y), pack2(b0.x, b0.y)), h16);
+          const uint32_t w1 = pack16x2_f2(fma2(mul2(v[o][1], rstd2), pack2(g0.z, g0.w), pack2(b0.z, b0.w)), h16);
+          const uint32_t w2 = pack16x2_f2(fma2(mul2(v[o][2], rstd2), pack2(g1.x, g1.y), pack2(b1.x, b1.y)), h16);
+          const uint32_t w3 = pack16x2_f2(fma2(mul2(v[o][3], rstd2), pack2(g1.z, g1.w), pack2(b1.z, b1.w)), h16);
+          *reinterpret_cast<uint4*>(base + oc * 16) = make_uint4(w0, w1, w2, w3);
         }
       }
       fence_proxy_async();  // our generic-proxy writes must be visible to the bulk store
@@ -436,6 +480,7 @@ struct GnStreamP {
   int do_silu;
   __nv_bfloat16* out;       // apply only, dense [rows, C0 + C1]
   int f16;                  // 16-bit tensors are IEEE fp16 instead of bf16
+  double inv_n;             // 1 / (P * cpg)
 };
 
 template <bool APPLY>
@@ -491,7 +536,7 @@ gn_stream_kernel(const GnStreamP p) {
           issue_load(i + GN_ST);
         }
       }
-      if (APPLY) tma_store_wait_all();
+      if (APPLY) tma_store_wait_read<0>();   // shared memory may go once the stores have read it; the writes land by grid end
     }
     return;
   }
@@ -549,26 +594,34 @@ gn_stream_kernel(const GnStreamP p) {
       for (int k = 0; k < 8; ++k) a[cs][k] = b[cs][k] = 0.f;
   }
 
+  // statistics group of the current tile, tracked incrementally (a 64-bit division per tile was a third of the apply
+  // pass's instruction stream)
+  long long ns = t_begin / tiles_per_stat, in_stat = t_begin - ns * tiles_per_stat;
   for (int i = 0; i < my_tiles; ++i) {
     const int s = i % GN_ST;
-    const long long ns = (t_begin + i) / tiles_per_stat;
+    if (i > 0 && ++in_stat == tiles_per_stat) {
+      in_stat = 0;
+      ++ns;
+    }
     if (ns != cur_stat) {
       if (APPLY) {
-        const double n = static_cast<double>(p.P) * p.cpg;
+        // mean / rstd of the 32 groups once per CTA and statistics group (every consumer thread reaches this at the same
+        // tile); doing the fp64 division / square root in each thread cost ~10 us per launch
+        float2* s_mr = reinterpret_cast<float2*>(sm_stats);   // [32] (rstd, -mean * rstd)
+        named_bar_sync(1, GN_CT);   // nobody still reads the previous group's values
+        if (t < 32) s_mr[t] = gn_group_scale(p.stats + (ns * 32 + t) * 2, p.inv_n, p.eps);
+        named_bar_sync(1, GN_CT);
 #pragma unroll
         for (int cs = 0; cs < GN_MAXCOL; ++cs) {
           const int oc = oc_first + cs * GN_CT;
           if (cs < ncol && oc < noct && lane_active) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-              const int c = oc * 8 + k, g = c / p.cpg;
-              const double mean = p.stats[(ns * 32 + g) * 2] / n;
-              double var = p.stats[(ns * 32 + g) * 2 + 1] / n - mean * mean;
-              if (var < 0.0) var = 0.0;
-              const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(p.eps)));
+              const int c = oc * 8 + k;
+              const float2 mr = s_mr[c / p.cpg];
               const float ga = p.gamma[c];
-              a[cs][k] = rstd * ga;
-              b[cs][k] = p.beta[c] - static_cast<float>(mean) * rstd * ga;
+              a[cs][k] = mr.x * ga;
+              b[cs][k] = fmaf(mr.y, ga, p.beta[c]);
             }
           }
         }
@@ -683,6 +736,7 @@ static int groupnorm_impl(const void* x0, const void* x1, int32_t c0, int32_t c1
       sp.do_silu = do_silu;
       sp.out = static_cast<__nv_bfloat16*>(out);
       sp.f16 = f16;
+      sp.inv_n = 1.0 / (static_cast<double>(rows_per_stat) * cpg);
       const int tile = R * C * 2;
       const int smem_stats = GN_ST * tile + 2 * GN_ST * 8 + 64 * 8 + 128;
       const int smem_apply = GN_ST * tile * (c1 > 0 ? 2 : 1) + 2 * GN_ST * 8 + 64 * 8 + 128;
