@@ -210,64 +210,92 @@ attn_temporal_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, int B, int F
   }
 }
 
-// ID cross-attention: grid (ceil(S/32), B*F); 256 threads; task = (row in chunk, head), lanes of a
-// warp share the head so K/V smem reads broadcast.  ik/iv: fp32 [B, NTOK, C].
-template <int NTOK>
-__global__ void __launch_bounds__(256)
+// ID cross-attention: grid (ceil(S / rc), B*F); thread = (row lane, channel octet): the octet's K / V values of the four
+// tokens stay in registers for all rows of the CTA, q is read and the result written with one coalesced 16-byte access per
+// thread and row, and the 64-channel dot products of a head are reduced over its 8 neighbouring lanes (three shuffles).
+// ik / iv: fp32 [B, NTOK, C].  (Round 1: thread = (row, head) with 128 registers of q / o per thread, one CTA of 8 warps
+// per SM and 640-byte lane strides: 1.7 TB/s.)
+template <int NTOK, int RPT>
+__global__ void __launch_bounds__(320, 2)
 attn_id_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const float* __restrict__ ik,
                const float* __restrict__ iv, long long tok_stride, long long batch_stride, int F, int S,
-               int C, int heads,
+               int C, int rl_n, int nb,
                __nv_bfloat16* __restrict__ out, int ldo, double* __restrict__ stats, int f16_) {
   grid_dep_sync();
   const bool f16 = f16_ != 0;   // q / out hold IEEE fp16 instead of bf16
-  extern __shared__ float sm_kv[];  // [2][NTOK][C]
-  __shared__ double red[2][8];
+  __shared__ double red[2][32];
   const int frame = blockIdx.y;
   const int b = frame / F;
-  float* sk = sm_kv;
-  float* sv = sm_kv + NTOK * C;
-  for (int t = threadIdx.x; t < NTOK * C; t += blockDim.x) {
-    const long long off = static_cast<long long>(b) * batch_stride + (t / C) * tok_stride + (t % C);
-    sk[t] = ik[off];
-    sv[t] = iv[off];
+  const int noct = C >> 3;
+  const int oc = threadIdx.x % noct, rl = threadIdx.x / noct;
+  float kk[NTOK][8], vv[NTOK][8];
+  const bool kv_vec = ((reinterpret_cast<uintptr_t>(ik) | reinterpret_cast<uintptr_t>(iv)) & 15) == 0 && (tok_stride & 3) == 0 &&
+                      (batch_stride & 3) == 0;
+#pragma unroll
+  for (int j = 0; j < NTOK; ++j) {
+    const long long off = static_cast<long long>(b) * batch_stride + j * tok_stride + oc * 8;
+    if (kv_vec) {
+      const float4 k0 = __ldg(reinterpret_cast<const float4*>(ik + off)), k1 = __ldg(reinterpret_cast<const float4*>(ik + off + 4));
+      const float4 v0 = __ldg(reinterpret_cast<const float4*>(iv + off)), v1 = __ldg(reinterpret_cast<const float4*>(iv + off + 4));
+      kk[j][0] = k0.x; kk[j][1] = k0.y; kk[j][2] = k0.z; kk[j][3] = k0.w;
+      kk[j][4] = k1.x; kk[j][5] = k1.y; kk[j][6] = k1.z; kk[j][7] = k1.w;
+      vv[j][0] = v0.x; vv[j][1] = v0.y; vv[j][2] = v0.z; vv[j][3] = v0.w;
+      vv[j][4] = v1.x; vv[j][5] = v1.y; vv[j][6] = v1.z; vv[j][7] = v1.w;
+    } else {
+#pragma unroll
+      for (int d = 0; d < 8; ++d) {   // views with unaligned strides: scalar loads
+        kk[j][d] = __ldg(ik + off + d);
+        vv[j][d] = __ldg(iv + off + d);
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < 8; ++d) kk[j][d] *= 0.125f;   // the 1/sqrt(64) of the scores is folded into K
   }
-  __syncthreads();
-  const int s0 = blockIdx.x * 32;
+  // RPT rows per thread, all q loads issued before the first is used: with one load in flight per thread the kernel
+  // ran at the memory latency (1.7 TB/s)
   double lsum = 0.0, lsq = 0.0;
-  for (int t = threadIdx.x; t < 32 * heads; t += blockDim.x) {
-    const int r = t & 31, h = t >> 5;
-    const int s = s0 + r;
-    if (s >= S) continue;
-    const long long row = static_cast<long long>(frame) * S + s;
-    float qv[64];
+  for (int bt = 0; bt < nb; ++bt) {   // nb batches of rl_n * RPT rows per CTA: K / V are loaded once for all of them
+  const int s0 = (blockIdx.x * nb + bt) * (rl_n * RPT);
+  if (s0 >= S) break;
+  float fsum = 0.f, fsq = 0.f;   // this thread's RPT rows x 8 channels in fp32, then fp64
+  uint4 qraw[RPT];
+#pragma unroll
+  for (int i = 0; i < RPT; ++i) {
+    const int sidx = s0 + rl + i * rl_n;
+    qraw[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (sidx < S) qraw[i] = __ldg(reinterpret_cast<const uint4*>(q + (static_cast<long long>(frame) * S + sidx) * ldq + oc * 8));
+  }
+#pragma unroll
+  for (int i = 0; i < RPT; ++i) {   // same trip count for every lane of a warp (the shuffles below)
+    const int sidx = s0 + rl + i * rl_n;
+    const bool valid = sidx < S;
+    const long long row = static_cast<long long>(frame) * S + (valid ? sidx : 0);
+    float qv[8];
     {
-      const uint4* qp = reinterpret_cast<const uint4*>(q + row * ldq + h * 64);
+      const uint32_t w[4] = {qraw[i].x, qraw[i].y, qraw[i].z, qraw[i].w};
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const uint4 u = __ldg(qp + i);
-        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float2 f = unpack16x2(w[k], f16);
-          qv[8 * i + 2 * k] = f.x;
-          qv[8 * i + 2 * k + 1] = f.y;
-        }
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = unpack16x2(w[k], f16);
+        qv[2 * k] = f.x;
+        qv[2 * k + 1] = f.y;
       }
     }
     float sc[NTOK];
-    float mx = -INFINITY;
 #pragma unroll
     for (int j = 0; j < NTOK; ++j) {
-      const float4* kp = reinterpret_cast<const float4*>(sk + j * C + h * 64);
       float p = 0.f;
 #pragma unroll
-      for (int d = 0; d < 16; ++d) {
-        const float4 kk = kp[d];
-        p += qv[4 * d] * kk.x + qv[4 * d + 1] * kk.y + qv[4 * d + 2] * kk.z + qv[4 * d + 3] * kk.w;
-      }
-      sc[j] = p * 0.125f;
-      mx = fmaxf(mx, sc[j]);
+      for (int d = 0; d < 8; ++d) p = fmaf(qv[d], kk[j][d], p);
+      sc[j] = p;
     }
+#pragma unroll
+    for (int d = 1; d < 8; d <<= 1) {
+#pragma unroll
+      for (int j = 0; j < NTOK; ++j) sc[j] += __shfl_xor_sync(0xffffffffu, sc[j], d);
+    }
+    float mx = sc[0];
+#pragma unroll
+    for (int j = 1; j < NTOK; ++j) mx = fmaxf(mx, sc[j]);
     float l = 0.f;
 #pragma unroll
     for (int j = 0; j < NTOK; ++j) {
@@ -275,35 +303,27 @@ attn_id_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const float* __rest
       l += sc[j];
     }
     const float inv = 1.0f / l;
-    float o[64];
+    float o[8];
 #pragma unroll
-    for (int d = 0; d < 64; ++d) o[d] = 0.f;
+    for (int d = 0; d < 8; ++d) o[d] = 0.f;
 #pragma unroll
     for (int j = 0; j < NTOK; ++j) {
-      const float4* vp = reinterpret_cast<const float4*>(sv + j * C + h * 64);
       const float p = sc[j] * inv;
 #pragma unroll
-      for (int d = 0; d < 16; ++d) {
-        const float4 vv = vp[d];
-        o[4 * d] += p * vv.x;
-        o[4 * d + 1] += p * vv.y;
-        o[4 * d + 2] += p * vv.z;
-        o[4 * d + 3] += p * vv.w;
+      for (int d = 0; d < 8; ++d) o[d] = fmaf(p, vv[j][d], o[d]);
+    }
+    if (valid) {
+#pragma unroll
+      for (int d = 0; d < 8; ++d) {
+        fsum += o[d];
+        fsq = fmaf(o[d], o[d], fsq);
       }
+      *reinterpret_cast<uint4*>(out + row * ldo + oc * 8) =
+          make_uint4(pack16x2(o[0], o[1], f16), pack16x2(o[2], o[3], f16), pack16x2(o[4], o[5], f16), pack16x2(o[6], o[7], f16));
     }
-    float ts = 0.f, tq = 0.f;
-#pragma unroll
-    for (int d = 0; d < 64; ++d) {
-      ts += o[d];
-      tq += o[d] * o[d];
-    }
-    lsum += ts;
-    lsq += tq;
-    uint4* dst = reinterpret_cast<uint4*>(out + row * ldo + h * 64);
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-      dst[i] = make_uint4(pack16x2(o[8 * i], o[8 * i + 1], f16), pack16x2(o[8 * i + 2], o[8 * i + 3], f16),
-                          pack16x2(o[8 * i + 4], o[8 * i + 5], f16), pack16x2(o[8 * i + 6], o[8 * i + 7], f16));
+  }
+  lsum += static_cast<double>(fsum);
+  lsq += static_cast<double>(fsq);
   }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) {
@@ -413,17 +433,23 @@ extern "C" int sa_attn_id(const void* q, int32_t ldq, const float* ik, const flo
   if (!q || !ik || !iv || !out || !stats) return fail(SA_ERR_INVALID, "sa_attn_id: null pointer");
   if (num_tokens != 4) return fail(SA_ERR_INVALID, "sa_attn_id: num_tokens must be 4");
   if (C != heads * 64 || ldq % 8 || ldo % 8) return fail(SA_ERR_INVALID, "sa_attn_id: head_dim must be 64");
-  const size_t smem = sizeof(float) * 2 * 4 * C;
-  static DeviceOnce once;
-  if (int rc = once.run([&]() -> int {
-        SA_CUDA_CHECK(cudaFuncSetAttribute(attn_id_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        return SA_OK;
-      }))
-    return rc;
+  // thread = (row lane, channel octet): ~320 threads, a whole number of warps, every 8-lane head group inside one warp
+  const int noct = C / 8;
+  if (noct > 320) return fail(SA_ERR_INVALID, "sa_attn_id: C=%d unsupported (<= 2560)", C);
+  int rl_n = 320 / noct;
+  while (rl_n > 1 && (rl_n * noct) % 32) --rl_n;
+  if ((rl_n * noct) % 32) return fail(SA_ERR_INVALID, "sa_attn_id: C=%d unsupported", C);
   SA_CUDA_CHECK(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * B * F, stream));
-  dim3 grid((S + 31) / 32, B * F, 1);
-  SA_CUDA_CHECK(launch_k(attn_id_kernel<4>, grid, dim3(256), smem, stream, 1, false, static_cast<const __nv_bfloat16*>(q), ldq, ik, iv,
-                         static_cast<long long>(kv_tok_stride), static_cast<long long>(kv_batch_stride), F, S, C, heads,
+  // 4 rows per thread and up to 8 batches per CTA while the launch still fills the GPU a few times over
+  const long long want = 4ll * num_sms();
+  const bool big = static_cast<long long>((S + rl_n * 4 - 1) / (rl_n * 4)) * B * F >= want;
+  const int rows_b = rl_n * (big ? 4 : 1);
+  int nb = 8;
+  while (nb > 1 && static_cast<long long>((S + rows_b * nb - 1) / (rows_b * nb)) * B * F < want) nb >>= 1;
+  dim3 grid((S + rows_b * nb - 1) / (rows_b * nb), B * F, 1);
+  auto* kern = big ? attn_id_kernel<4, 4> : attn_id_kernel<4, 1>;
+  SA_CUDA_CHECK(launch_k(kern, grid, dim3(rl_n * noct), 0, stream, 1, false, static_cast<const __nv_bfloat16*>(q), ldq, ik, iv,
+                         static_cast<long long>(kv_tok_stride), static_cast<long long>(kv_batch_stride), F, S, C, rl_n, nb,
                          static_cast<__nv_bfloat16*>(out), ldo, static_cast<double*>(stats), act_f16));
   return SA_OK;
 }
