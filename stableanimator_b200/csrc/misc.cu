@@ -12,59 +12,93 @@ namespace sa {
 // act_out: 0 none, 1 SiLU, 2 exact GELU (FusionFaceId proj / FeedForward, id_encoder.py:57-64,116-120).
 // TimestepEmbedding (unet.py:429-436), time_emb_proj(silu(temb)) (:1669-1670, :1754-1755), the
 // K/V projections of the 5 context tokens (:1974-1975, :1999-2000, :1834-1835).
+constexpr int SL_NPW = 4;   // output columns per warp: four weight rows in flight per lane, the input rows read once for all
 template <int MT>
 __global__ void __launch_bounds__(256)
 small_linear_kernel(const float* __restrict__ x, int ldx, int M, const __nv_bfloat16* __restrict__ w,
                     int K, int N, const float* __restrict__ bias, int silu_in, int silu_out,
-                    int accumulate, float* __restrict__ out, int ldo) {
+                    int accumulate, float* __restrict__ out, int ldo, int x_smem) {
+  // the MT input rows (SiLU applied once, not once per output column) staged in shared memory when they fit (x_smem)
+  extern __shared__ float sl_x[];   // [MT][K]
   const int lane = threadIdx.x & 31;
-  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int n0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * SL_NPW;
   const int m0 = blockIdx.y * MT;
-  if (n >= N) return;
-  float acc[MT];
+  if (x_smem) {
+    for (int i = threadIdx.x; i < MT * K; i += blockDim.x) {
+      const int m = i / K, k = i - m * K;
+      float v = 0.f;
+      if (m0 + m < M) {
+        v = x[static_cast<long long>(m0 + m) * ldx + k];
+        if (silu_in) v = v / (1.0f + expf(-v));
+      }
+      sl_x[i] = v;
+    }
+    __syncthreads();
+  }
+  if (n0 >= N) return;
+  float acc[SL_NPW][MT];
 #pragma unroll
-  for (int m = 0; m < MT; ++m) acc[m] = 0.f;
-  const __nv_bfloat16* wr = w + static_cast<long long>(n) * K;
+  for (int j = 0; j < SL_NPW; ++j)
+#pragma unroll
+    for (int m = 0; m < MT; ++m) acc[j][m] = 0.f;
   for (int k = lane * 8; k < K; k += 256) {
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(wr + k));
-    const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
-    float wf[8];
+    uint4 u[SL_NPW];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const float2 f = unpack_bf16x2(ww[t]);
-      wf[2 * t] = f.x;
-      wf[2 * t + 1] = f.y;
+    for (int j = 0; j < SL_NPW; ++j) {
+      const int n = n0 + j < N ? n0 + j : N - 1;   // a clamped duplicate row, discarded below
+      u[j] = __ldg(reinterpret_cast<const uint4*>(w + static_cast<long long>(n) * K + k));
     }
 #pragma unroll
     for (int m = 0; m < MT; ++m) {
       if (m0 + m < M) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(x + static_cast<long long>(m0 + m) * ldx + k));
-        const float4 b = __ldg(reinterpret_cast<const float4*>(x + static_cast<long long>(m0 + m) * ldx + k + 4));
+        float4 a, b;
+        if (x_smem) {
+          a = *reinterpret_cast<const float4*>(sl_x + m * K + k);
+          b = *reinterpret_cast<const float4*>(sl_x + m * K + k + 4);
+        } else {
+          a = __ldg(reinterpret_cast<const float4*>(x + static_cast<long long>(m0 + m) * ldx + k));
+          b = __ldg(reinterpret_cast<const float4*>(x + static_cast<long long>(m0 + m) * ldx + k + 4));
+        }
         float xv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        if (silu_in) {
+        if (silu_in && !x_smem) {
 #pragma unroll
           for (int t = 0; t < 8; ++t) xv[t] = xv[t] / (1.0f + expf(-xv[t]));
         }
 #pragma unroll
-        for (int t = 0; t < 8; ++t) acc[m] += xv[t] * wf[t];
+        for (int j = 0; j < SL_NPW; ++j) {
+          const uint32_t ww[4] = {u[j].x, u[j].y, u[j].z, u[j].w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float2 f = unpack_bf16x2(ww[t]);
+            acc[j][m] = fmaf(xv[2 * t], f.x, acc[j][m]);
+            acc[j][m] = fmaf(xv[2 * t + 1], f.y, acc[j][m]);
+          }
+        }
       }
     }
   }
 #pragma unroll
-  for (int m = 0; m < MT; ++m) {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], d);
-  }
-  if (lane == 0) {
-    const float b = bias ? bias[n] : 0.f;
+  for (int j = 0; j < SL_NPW; ++j)
 #pragma unroll
     for (int m = 0; m < MT; ++m) {
-      if (m0 + m < M) {
-        float v = acc[m] + b;
-        if (silu_out == 1) v = v / (1.0f + expf(-v));
-        else if (silu_out == 2) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));  // exact GELU
-        float* dst = out + static_cast<long long>(m0 + m) * ldo + n;
-        *dst = accumulate ? *dst + v : v;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) acc[j][m] += __shfl_xor_sync(0xffffffffu, acc[j][m], d);
+    }
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < SL_NPW; ++j) {
+      const int n = n0 + j;
+      if (n >= N) break;
+      const float b = bias ? bias[n] : 0.f;
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        if (m0 + m < M) {
+          float v = acc[j][m] + b;
+          if (silu_out == 1) v = v / (1.0f + expf(-v));
+          else if (silu_out == 2) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));  // exact GELU
+          float* dst = out + static_cast<long long>(m0 + m) * ldo + n;
+          *dst = accumulate ? *dst + v : v;
+        }
       }
     }
   }
@@ -437,13 +471,18 @@ extern "C" int sa_small_linear(const float* x, int32_t ldx, int32_t m, const voi
   if (!x || !w || !out) return fail(SA_ERR_INVALID, "sa_small_linear: null pointer");
   if (k % 8 || ldx % 4 || m < 1) return fail(SA_ERR_INVALID, "sa_small_linear: k %% 8, ldx %% 4 required");
   const __nv_bfloat16* wp = static_cast<const __nv_bfloat16*>(w);
-  const unsigned gx = (n + 7) / 8;
+  const unsigned gx = (n + 8 * SL_NPW - 1) / (8 * SL_NPW);
+  // input rows staged in shared memory when MT * K floats fit the default 48 KB
+  const int mt = m <= 2 ? 2 : m <= 4 ? 4 : 8;
+  const size_t xs = static_cast<size_t>(mt) * k * sizeof(float);
+  const int x_smem = xs <= 48 * 1024 ? 1 : 0;
+  const size_t smem = x_smem ? xs : 0;
   if (m <= 2) {
-    small_linear_kernel<2><<<dim3(gx, (m + 1) / 2), 256, 0, stream>>>(x, ldx, m, wp, k, n, bias, silu_in, silu_out, accumulate, out, ldo);
+    small_linear_kernel<2><<<dim3(gx, (m + 1) / 2), 256, smem, stream>>>(x, ldx, m, wp, k, n, bias, silu_in, silu_out, accumulate, out, ldo, x_smem);
   } else if (m <= 4) {
-    small_linear_kernel<4><<<dim3(gx, (m + 3) / 4), 256, 0, stream>>>(x, ldx, m, wp, k, n, bias, silu_in, silu_out, accumulate, out, ldo);
+    small_linear_kernel<4><<<dim3(gx, (m + 3) / 4), 256, smem, stream>>>(x, ldx, m, wp, k, n, bias, silu_in, silu_out, accumulate, out, ldo, x_smem);
   } else {
-    small_linear_kernel<8><<<dim3(gx, (m + 7) / 8), 256, 0, stream>>>(x, ldx, m, wp, k, n, bias, silu_in, silu_out, accumulate, out, ldo);
+    small_linear_kernel<8><<<dim3(gx, (m + 7) / 8), 256, smem, stream>>>(x, ldx, m, wp, k, n, bias, silu_in, silu_out, accumulate, out, ldo, x_smem);
   }
   SA_CUDA_CHECK(cudaGetLastError());
   return SA_OK;
