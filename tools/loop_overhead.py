@@ -40,12 +40,12 @@ def main():
         for _ in range(25):
             run()
     only = timed(replays)
-    setup = timed(lambda: s(inp["latents"], inp["image_latents"], inp["encoder_hidden_states"], inp["added_time_ids"],
-                            inp["pose"], steps_to_run=0))
     one = timed(lambda: s(inp["latents"], inp["image_latents"], inp["encoder_hidden_states"], inp["added_time_ids"],
                           inp["pose"], steps_to_run=1))
-    print(f"per-video setup (PoseNet, context, noise tiling; 0 steps): {setup:.2f} ms; 1 step: {one:.2f} ms; "
-          f"one bare replay: {timed(run, 5):.2f} ms")
+    two = timed(lambda: s(inp["latents"], inp["image_latents"], inp["encoder_hidden_states"], inp["added_time_ids"],
+                          inp["pose"], steps_to_run=2))
+    print(f"1 step: {one:.2f} ms; 2 steps: {two:.2f} ms -> per-video setup (PoseNet, context, noise tiling) "
+          f"{2 * one - two:.2f} ms, one step {two - one:.2f} ms; one bare replay: {timed(run, 5):.2f} ms")
     print(f"sampler call (25 steps): {full:.1f} ms; 25 bare graph replays: {only:.1f} ms; difference {full - only:.1f} ms "
           f"({(full - only) / 25 * 1e3:.0f} us per step)")
 
