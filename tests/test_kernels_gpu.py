@@ -83,6 +83,37 @@ def test_attn_id_processor(b, f, s, heads):
     assert_close(out, ref, what="attn_id_processor")
 
 
+@pytest.mark.parametrize("b,f,s,heads,view", [(1, 2, 100, 3, "dense"), (2, 16, 4096, 5, "dense"), (1, 3, 37, 1, "offset"),
+                                              (2, 2, 520, 20, "strided")])
+def test_attn_id_kernel_shapes(b, f, s, heads, view):
+    """sa_attn_id alone against softmax(q k^T / 8) v in fp32 torch (unet.py:1999-2010) and its fp64 (Sum, Sum^2):
+    ragged S, a thread block that is not 320 threads (C = 192), the many-batches-per-CTA path (131072 rows), the
+    one-row-per-thread path, K / V views that are only 4-byte aligned (scalar loads) or strided (ctx.all slices)."""
+    from stableanimator_b200 import ops
+    c = heads * 64
+    q = rnd(b * f * s, c, seed=11)
+    g = torch.Generator(device="cuda").manual_seed(12)
+    if view == "dense":
+        ik, iv = (torch.randn(b, 4, c, generator=g, device="cuda") for _ in range(2))
+    elif view == "offset":   # 4-byte-aligned base: the scalar K / V load path
+        base = torch.randn(2, b, 4, c + 1, generator=g, device="cuda")
+        ik, iv = base[0, :, :, 1:], base[1, :, :, 1:]
+    else:                    # slices of one [b, 5, n] context tensor, as UNetB200.prepare_context hands them over
+        base = torch.randn(b, 5, 2 * c + 64, generator=g, device="cuda")
+        ik, iv = base[:, 1:, 64:64 + c], base[:, 1:, 64 + c:64 + 2 * c]
+    stats = torch.empty(b * f, 2, device="cuda", dtype=torch.float64)
+    out = ops.attn_id(q, ik, iv, b, f, s, heads, stats)
+    qh = q.float().reshape(b, f * s, heads, 64)
+    kh, vh = ik.float().reshape(b, 4, heads, 64), iv.float().reshape(b, 4, heads, 64)
+    p = torch.softmax(torch.einsum("bqhd,bkhd->bhqk", qh, kh) * 0.125, dim=-1)
+    ref = torch.einsum("bhqk,bkhd->bqhd", p, vh).reshape(b * f * s, c)
+    assert_close(out, ref, what=f"attn_id {view}")
+    r = ref.double().reshape(b * f, -1)
+    got = stats.cpu()
+    want = torch.stack([r.sum(1), (r * r).sum(1)], 1).cpu()
+    assert torch.allclose(got, want, rtol=2e-5, atol=1e-3), (got, want)
+
+
 def test_attn_id_uncond_zero_context():
     """ehs == 0 (uncond branch): both branches vanish, output == to_out bias."""
     from stableanimator_b200 import ops
