@@ -357,7 +357,7 @@ attn_id_finalize_kernel(const double* __restrict__ stats, const float* __restric
                         float* __restrict__ row_scale, float* __restrict__ row_bias) {
   grid_dep_sync();
   __shared__ double red[2][8];
-  __shared__ float s_a, s_shift;
+  __shared__ float s_shift;
   const int frame = blockIdx.x;
   const int b = frame / F;
   const float* vc = vclip + static_cast<long long>(b) * vclip_bstride;
@@ -392,7 +392,6 @@ attn_id_finalize_kernel(const double* __restrict__ stats, const float* __restric
     double var_i = (stats[2 * frame + 1] - n * mean_i * mean_i) / (n - 1.0);
     if (var_i < 0.0) var_i = 0.0;
     const double a = sqrt(var_l) / (sqrt(var_i) + 1e-5);
-    s_a = static_cast<float>(a);
     s_shift = static_cast<float>(mean_l - a * mean_i);
     row_scale[frame] = static_cast<float>(a);
   }

@@ -286,10 +286,6 @@ __device__ __forceinline__ void load8s(const uint8_t* p, float (&v)[8], bool f16
     v[2 * t + 1] = f.y;
   }
 }
-__device__ __forceinline__ void store8s(uint8_t* p, const float (&v)[8], bool f16) {
-  *reinterpret_cast<uint4*>(p) = make_uint4(pack16x2(v[0], v[1], f16), pack16x2(v[2], v[3], f16),
-                                            pack16x2(v[4], v[5], f16), pack16x2(v[6], v[7], f16));
-}
 
 template <int LPR, int OPL, bool XOUT>
 __global__ void __launch_bounds__(32 * (LN_CW + 1))
