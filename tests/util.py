@@ -10,7 +10,9 @@ bf16-valued result -- including the reference's own bf16 path.  We therefore bou
   * rel_l2   = ||out - ref||_2 / ||ref||_2                    <= 2^-8   (sanity bound: pure bf16 output
                rounding alone gives ~1.6e-3; a kernel with one internal bf16 operand, e.g. the
                attention probabilities P, ~2.3e-3 -- the same as any bf16 flash attention)
-For fp32 outputs ``excess`` degenerates to the plain max-norm relative error and both use ``tol``.
+For fp32 outputs ``excess`` degenerates to the plain max-norm relative error and both use ``tol``.  fp16 outputs (the
+reference's default dtype, ``act_f16`` mode) carry 11 significant bits: their allowance is 2^-11 = 4.9e-4 and the rel-L2 bound is
+``tol`` itself, i.e. the fp16-mode tests hold north_star's 2e-3 almost literally.
 """
 import torch
 
@@ -25,7 +27,7 @@ def rel_l2(out, ref):
 
 def excess(out, ref):
     o, r = out.double(), ref.double()
-    quant = 0.0 if out.dtype == torch.float32 else 2.0 ** -8
+    quant = {torch.float32: 0.0, torch.float64: 0.0, torch.float16: 2.0 ** -11}.get(out.dtype, 2.0 ** -8)
     e = ((o - r).abs() - quant * r.abs()).clamp_min(0)
     return (e.max() / r.abs().max().clamp_min(1e-30)).item()
 
@@ -34,6 +36,6 @@ def assert_close(out, ref, tol=TOL, what=""):
     assert out.shape == ref.shape, f"{what}: shape {tuple(out.shape)} vs {tuple(ref.shape)}"
     assert torch.isfinite(out.float()).all(), f"{what}: non-finite output"
     l2, ex = rel_l2(out, ref), excess(out, ref)
-    l2_tol = tol if out.dtype == torch.float32 else max(tol, L2_TOL_BF16)
+    l2_tol = max(tol, L2_TOL_BF16) if out.dtype == torch.bfloat16 else tol
     assert ex <= tol and l2 <= l2_tol, f"{what}: excess_max={ex:.3e} (tol {tol}) rel_l2={l2:.3e} (tol {l2_tol:.1e})"
     return l2, ex
