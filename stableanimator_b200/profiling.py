@@ -99,13 +99,20 @@ def family_times(run: Callable, families: Iterable[str] = FAMILIES, reps: int = 
 
 
 def _rotating_us(fn: Callable, nbuf: int, iters: int = 12) -> float:
+    """Device time per launch of ``fn(i)`` over rotating inputs, replayed from a CUDA graph: launched eagerly from Python these
+    30-50 us kernels are bound by the host's launch rate, not by the device."""
     for i in range(nbuf):
         fn(i)
     torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(iters):
+            fn(i % nbuf)
+    g.replay()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(iters):
-        fn(i % nbuf)
+    g.replay()
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / iters * 1e3
@@ -117,7 +124,7 @@ def memory_bound_gbs(dev, frames: int = 32, s: int = 4096, c: int = 320, hbm_gbs
     rows = frames * s
     nbuf = max(2, int(300e6 // (rows * c * 2)) + 1)
     xs = [torch.randn(rows, c, device=dev).bfloat16() for _ in range(nbuf)]
-    y = torch.empty(rows, c, device=dev, dtype=torch.bfloat16)
+    ys = [torch.empty(rows, c, device=dev, dtype=torch.bfloat16) for _ in range(nbuf)]   # outputs rotate too: cold writes
     g, b = torch.randn(c, device=dev), torch.randn(c, device=dev)
     byt = 2.0 * rows * c * 2
     out = {}
@@ -127,12 +134,12 @@ def memory_bound_gbs(dev, frames: int = 32, s: int = 4096, c: int = 320, hbm_gbs
                      "bytes": int(nbytes)}
 
     ws = torch.zeros(frames, 32, 2, device=dev, dtype=torch.float64)
-    rec("groupnorm_silu_two_pass", _rotating_us(lambda i: ops.groupnorm(xs[i], g, b, 1e-5, s, silu=True, stats_ws=ws, out=y), nbuf), byt)
-    ops.groupnorm(xs[0], g, b, 1e-5, s, silu=True, stats_ws=ws, out=y)   # valid statistics for the apply-only pass
-    rec("groupnorm_silu_apply", _rotating_us(lambda i: ops.groupnorm(xs[i], g, b, 1e-5, s, silu=True, stats_ws=ws, out=y,
+    rec("groupnorm_silu_two_pass", _rotating_us(lambda i: ops.groupnorm(xs[i], g, b, 1e-5, s, silu=True, stats_ws=ws, out=ys[i]), nbuf), byt)
+    ops.groupnorm(xs[0], g, b, 1e-5, s, silu=True, stats_ws=ws, out=ys[0])   # valid statistics for the apply-only pass
+    rec("groupnorm_silu_apply", _rotating_us(lambda i: ops.groupnorm(xs[i], g, b, 1e-5, s, silu=True, stats_ws=ws, out=ys[i],
                                                                       stats_ready=True), nbuf), byt)
-    rec("layernorm", _rotating_us(lambda i: ops.layernorm(xs[i], g, b, out=y), nbuf), byt)
-    del xs, y
+    rec("layernorm", _rotating_us(lambda i: ops.layernorm(xs[i], g, b, out=ys[i]), nbuf), byt)
+    del xs, ys
     # fused normalise + CFG + Euler step (sampler_step): 2 reads eps + 1 read x + 1 write x, fp32 [F, 4, h, w]
     f_, hw = 16, s
     noise = torch.randn(2, f_, 4, hw, device=dev)

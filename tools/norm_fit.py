@@ -1,5 +1,6 @@
 """Fixed cost vs streaming rate of the streamed LayerNorm / GroupNorm kernels: time at several row counts (C = 320),
-inputs rotating over > 126 MB, and fit t = t0 + bytes / BW.  Also a plain device copy of the same bytes as the ceiling."""
+inputs AND outputs rotating over > 126 MB (cold reads, cold writes), and fit t = t0 + bytes / BW.  Also torch's device copy of
+the same bytes for comparison."""
 import sys
 from pathlib import Path
 
@@ -34,19 +35,19 @@ def main():
     for rows in (16384, 32768, 65536, 131072, 262144, 524288):
         nbuf = max(2, int(400e6 // (rows * c * 2)) + 1)
         xs = [torch.randn(rows, c, device=dev).bfloat16() for _ in range(nbuf)]
-        y = torch.empty(rows, c, device=dev, dtype=torch.bfloat16)
+        ys = [torch.empty(rows, c, device=dev, dtype=torch.bfloat16) for _ in range(nbuf)]
         ws = torch.zeros(rows // 4096, 32, 2, device=dev, dtype=torch.float64)
         mb = 2.0 * rows * c * 2 / 1e6
-        t_ln = timeit(lambda i: ops.layernorm(xs[i], g, b, out=y), nbuf)
-        t_gn = timeit(lambda i: ops.groupnorm(xs[i], g, b, 1e-5, 4096, silu=True, stats_ws=ws, out=y, stats_ready=True), nbuf)
-        t_cp = timeit(lambda i: y.copy_(xs[i]), nbuf)
+        t_ln = timeit(lambda i: ops.layernorm(xs[i], g, b, out=ys[i]), nbuf)
+        t_gn = timeit(lambda i: ops.groupnorm(xs[i], g, b, 1e-5, 4096, silu=True, stats_ws=ws, out=ys[i], stats_ready=True), nbuf)
+        t_cp = timeit(lambda i: ys[i].copy_(xs[i]), nbuf)
         res[rows] = (mb, t_ln, t_gn, t_cp)
         print(f"rows {rows:7d} ({mb:6.1f} MB r+w): layernorm {t_ln:6.1f} us  groupnorm-apply {t_gn:6.1f} us  copy {t_cp:6.1f} us")
-        del xs
+        del xs, ys
     (m0, *a), (m1, *bb) = res[131072], res[524288]
     for name, t0, t1 in zip(("layernorm", "groupnorm-apply", "copy"), a, bb):
         bw = (m1 - m0) / (t1 - t0)
-        print(f"{name:16s}: streaming {bw / 1e3 * 1e3:6.0f} GB/s, fixed cost {t0 - m0 / bw:5.1f} us per launch (in a graph)")
+        print(f"{name:16s}: streaming {bw:5.2f} TB/s, fixed cost {t0 - m0 / bw:5.1f} us per launch (in a graph)")
 
 
 if __name__ == "__main__":
