@@ -72,7 +72,7 @@ template <bool F16>   // F16: q | k | v and out hold IEEE fp16 instead of bf16
 __global__ void __launch_bounds__(AT_WARPS * 32)
 attn_temporal_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, int B, int F, int S, int C,
                      int heads, __nv_bfloat16* __restrict__ out, int ldo) {
-  grid_dep_sync();
+  grid_dep_sync_light();
   __shared__ __align__(128) uint8_t sm[AT_WARPS][3][AT_TILE];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long task = static_cast<long long>(blockIdx.x) * AT_WARPS + warp;
@@ -221,7 +221,7 @@ attn_id_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const float* __rest
                const float* __restrict__ iv, long long tok_stride, long long batch_stride, int F, int S,
                int C, int rl_n, int nb,
                __nv_bfloat16* __restrict__ out, int ldo, double* __restrict__ stats, int f16_) {
-  grid_dep_sync();
+  grid_dep_sync_light();
   const bool f16 = f16_ != 0;   // q / out hold IEEE fp16 instead of bf16
   __shared__ double red[2][32];
   const int frame = blockIdx.y;
@@ -355,7 +355,7 @@ attn_id_finalize_kernel(const double* __restrict__ stats, const float* __restric
                         long long vclip_bstride, const float* __restrict__ wv, const float* __restrict__ w_rowsum,
                         const float* __restrict__ bias, int F, int S, int C,
                         float* __restrict__ row_scale, float* __restrict__ row_bias) {
-  grid_dep_sync();
+  grid_dep_sync_light();
   __shared__ double red[2][8];
   __shared__ float s_shift;
   const int frame = blockIdx.x;

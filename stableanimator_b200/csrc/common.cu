@@ -143,7 +143,7 @@ int num_sms() {
 
 int pdl_level() {
   const char* e = getenv("SA_PDL");   // read per launch (captured graphs keep what they were captured with)
-  return e ? (e[0] == '0' ? 0 : e[0] == '2' ? 2 : 1) : 1;
+  return e ? (e[0] == '0' ? 0 : e[0] == '1' ? 1 : 2) : 2;
 }
 
 }  // namespace sa

@@ -58,14 +58,16 @@ struct DeviceOnce {
 };
 
 
-// Programmatic dependent launch (ptx.cuh `grid_dep_sync`).  SA_PDL = 0: off; 1 (default): the kernels with a long set-up
-// (barrier rings, TMEM allocation, tensor-map prefetch: tapped GEMM, fused feed-forward, flash attention), where the overlap
-// pays (-0.8 us per launch inside a graph); 2: every kernel -- the light ones get SLOWER (+1.6 us per launch,
-// `tools/pdl_probe.py`), so that is for measurement only.
+// Programmatic dependent launch (ptx.cuh `grid_dep_sync` / `grid_dep_sync_light`).  SA_PDL = 2 (default): every kernel of the
+// denoising call; 1: only the kernels with a long set-up (barrier rings, TMEM allocation, tensor-map prefetch: tapped GEMM,
+// fused feed-forward, flash attention); 0: plain launches.  The heavy kernels release their successor right after their own
+// set-up, the light (memory-bound) ones only when their CTAs exit -- released early they got SLOWER (+1.6 us per launch in a
+// chain of LayerNorms, `tools/pdl_probe.py`); with the late release the chain gains 0.2 us per launch and the UNet call
+// 0.4 ms over level 1 (0.7 ms over plain launches).
 int pdl_level();
 
-// One launch path for the kernels of the denoising call: optional cluster (cluster_x > 1) and, for `heavy` kernels, the
-// programmatic-launch attribute.  ONLY for kernels whose every global-memory access follows a `grid_dep_wait()`.
+// One launch path for the kernels of the denoising call: optional cluster (cluster_x > 1) and the programmatic-launch
+// attribute (`heavy` = released at level 1 already).  ONLY for kernels whose every global-memory access follows a `grid_dep_wait()`.
 template <class... P, class... A>
 inline cudaError_t launch_k(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, unsigned cluster_x,
                             bool heavy, A&&... args) {

@@ -38,7 +38,7 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x0,
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
   if (tid < 64) sm[tid >> 1][tid & 1] = 0.0;
   __syncthreads();
-  grid_dep_sync();
+  grid_dep_sync_light();
   const int c = threadIdx.x * 8;
   const long long ns = blockIdx.y;
   const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
@@ -119,7 +119,7 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0,
                                 const double* __restrict__ stats, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, float eps, int do_silu,
                                 __nv_bfloat16* __restrict__ out, int ldo, int f16) {
-  grid_dep_sync();
+  grid_dep_sync_light();
   const int c = threadIdx.x * 8;
   const long long ns = blockIdx.y;
   // mean / rstd of the 32 groups once per CTA (fp64 only for the cancellation in E[x^2] - mean^2; fp64 division and
@@ -193,7 +193,7 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, int ldx, long long M, int 
                  const float* __restrict__ addv, int rows_per_group,
                  __nv_bfloat16* __restrict__ x_out, int ldxo, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y, int ldy, int f16) {
-  grid_dep_sync();
+  grid_dep_sync_light();
   constexpr int RPW = 32 / LPR;  // rows per warp
   const int lane = threadIdx.x & 31;
   const int sub = lane / LPR, l = lane % LPR;
@@ -311,7 +311,7 @@ layernorm_stream_kernel(const __nv_bfloat16* __restrict__ x, long long M, const 
     fence_barrier_init();
   }
   __syncthreads();
-  grid_dep_sync();
+  grid_dep_sync_light();
   auto tile_bytes = [&](long long tile) -> uint32_t {
     long long rows = M - tile * L::TILE_ROWS;
     if (rows > L::TILE_ROWS) rows = L::TILE_ROWS;
@@ -504,7 +504,7 @@ gn_stream_kernel(const GnStreamP p) {
   }
   if (!APPLY && threadIdx.x < 64) sm_stats[threadIdx.x] = 0.0;
   __syncthreads();
-  grid_dep_sync();
+  grid_dep_sync_light();
 
   if (warp == GN_CW) {
     // ------------------------------------------------------------ producer / store issuer

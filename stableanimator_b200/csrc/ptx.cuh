@@ -134,6 +134,9 @@ __device__ __forceinline__ void grid_dep_sync() {
   grid_dep_launch();
   grid_dep_wait();
 }
+// The light (memory-bound) kernels: wait only; their successor is released when the CTAs exit (implicit trigger) -- an early
+// release made chains of light kernels slower (common.cuh).
+__device__ __forceinline__ void grid_dep_sync_light() { grid_dep_wait(); }
 __device__ __forceinline__ void cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }

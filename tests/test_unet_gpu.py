@@ -151,8 +151,9 @@ def test_unet_fused_groupnorm_statistics_option():
 
 
 def test_programmatic_dependent_launch_keeps_the_bits(monkeypatch):
-    """SA_PDL (common.cuh `launch_k`): the tensor-core kernels start under the tail of their predecessor and wait in
-    `griddepcontrol.wait` before touching global memory.  Eager and graph-replayed calls give the bits of plain launches."""
+    """SA_PDL (common.cuh `launch_k`): kernels start under the tail of their predecessor and wait in `griddepcontrol.wait`
+    before touching global memory (2, the default: all of them; 1: the tensor-core kernels; 0: plain launches).  Eager and
+    graph-replayed calls give the bits of plain launches."""
     from stableanimator_b200 import ops
     c = load_golden("tiny_cond_f4_16x16")
     m = model(c["cfg"], c["gold"]["seed"])
