@@ -53,8 +53,8 @@ CONFIGS = {
 }
 # average DRAM bytes (read + write) per GEMM-family launch (sa_gemm_tap + sa_ff_fused) in one B=2 UNet call at 64x64x16,
 # re-measured at round-2 HEAD with the ncu pass `--metrics dram__bytes_read.sum,dram__bytes_write.sum` over all 333
-# launches of the family (profiles/r2_v3_launches_unet_b2_64x64x16.csv, summary next to it; round 1: 132.2 MB over 343)
-GEMM_DRAM_BYTES_PER_LAUNCH = 102.7e6
+# launches of the family (profiles/r2_v10_launches_unet_b2_64x64x16.csv, summary next to it; r2_v3: 102.7 MB; round 1: 132.2 MB over 343)
+GEMM_DRAM_BYTES_PER_LAUNCH = 102.5e6
 
 
 def peaks():
