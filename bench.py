@@ -52,8 +52,8 @@ CONFIGS = {
     4: (128, 72, 128, "576x1024 (w x h), 128-frame long video, tile 16 / overlap 4, (tile, CFG branch) units over the ranks"),
 }
 # average DRAM bytes (read + write) per GEMM-family launch (sa_gemm_tap + sa_ff_fused) in one B=2 UNet call at 64x64x16,
-# re-measured at round-2 HEAD with the ncu pass `--metrics dram__bytes_read.sum,dram__bytes_write.sum` over all 333
-# launches of the family (profiles/r2_v10_launches_unet_b2_64x64x16.csv, summary next to it; r2_v3: 102.7 MB; round 1: 132.2 MB over 343)
+# re-measured at round-2 HEAD with the ncu pass `--metrics dram__bytes_read.sum,dram__bytes_write.sum` over the 313 tapped-GEMM
+# launches of the call (profiles/r2_v10_launches_unet_b2_64x64x16.csv, summary next to it; r2_v3: 102.7 MB; round 1: 132.2 MB over 343)
 GEMM_DRAM_BYTES_PER_LAUNCH = 102.5e6
 
 
