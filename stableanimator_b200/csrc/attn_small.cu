@@ -212,17 +212,17 @@ attn_temporal_kernel(const __nv_bfloat16* __restrict__ qkv, int ld, int B, int F
 
 // ID cross-attention: grid (ceil(S / rc), B*F); thread = (row lane, channel octet): the octet's K / V values of the four
 // tokens stay in registers for all rows of the CTA, q is read and the result written with one coalesced 16-byte access per
-// thread and row, and the 64-channel dot products of a head are reduced over its 8 neighbouring lanes (three shuffles).
+// thread and row, and the 64-channel dot products of a head are reduced over its 8 neighbouring lanes (three shuffles); RPT rows are loaded before the first is used.
 // ik / iv: fp32 [B, NTOK, C].  (Round 1: thread = (row, head) with 128 registers of q / o per thread, one CTA of 8 warps
 // per SM and 640-byte lane strides: 1.7 TB/s.)
-template <int NTOK, int RPT>
+template <int NTOK, int RPT, bool F16>
 __global__ void __launch_bounds__(320, 2)
 attn_id_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const float* __restrict__ ik,
                const float* __restrict__ iv, long long tok_stride, long long batch_stride, int F, int S,
                int C, int rl_n, int nb,
-               __nv_bfloat16* __restrict__ out, int ldo, double* __restrict__ stats, int f16_) {
+               __nv_bfloat16* __restrict__ out, int ldo, double* __restrict__ stats) {
   grid_dep_sync_light();
-  const bool f16 = f16_ != 0;   // q / out hold IEEE fp16 instead of bf16
+  constexpr bool f16 = F16;   // q / out hold IEEE fp16 instead of bf16
   __shared__ double red[2][32];
   const int frame = blockIdx.y;
   const int b = frame / F;
@@ -439,17 +439,19 @@ extern "C" int sa_attn_id(const void* q, int32_t ldq, const float* ik, const flo
   while (rl_n > 1 && (rl_n * noct) % 32) --rl_n;
   if ((rl_n * noct) % 32) return fail(SA_ERR_INVALID, "sa_attn_id: C=%d unsupported", C);
   SA_CUDA_CHECK(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * B * F, stream));
-  // 4 rows per thread and up to 8 batches per CTA while the launch still fills the GPU a few times over
+  // 2 rows per thread (4 spill under the 2-CTA register cap: 82 vs 67 us at [131072, 320]) and up to 8 batches per CTA while
+  // the launch still fills the GPU a few times over
   const long long want = 4ll * num_sms();
-  const bool big = static_cast<long long>((S + rl_n * 4 - 1) / (rl_n * 4)) * B * F >= want;
-  const int rows_b = rl_n * (big ? 4 : 1);
+  const bool big = static_cast<long long>((S + rl_n * 2 - 1) / (rl_n * 2)) * B * F >= want;
+  const int rows_b = rl_n * (big ? 2 : 1);
   int nb = 8;
   while (nb > 1 && static_cast<long long>((S + rows_b * nb - 1) / (rows_b * nb)) * B * F < want) nb >>= 1;
   dim3 grid((S + rows_b * nb - 1) / (rows_b * nb), B * F, 1);
-  auto* kern = big ? attn_id_kernel<4, 4> : attn_id_kernel<4, 1>;
+  auto* kern = big ? (act_f16 ? attn_id_kernel<4, 2, true> : attn_id_kernel<4, 2, false>)
+                   : (act_f16 ? attn_id_kernel<4, 1, true> : attn_id_kernel<4, 1, false>);
   SA_CUDA_CHECK(launch_k(kern, grid, dim3(rl_n * noct), 0, stream, 1, false, static_cast<const __nv_bfloat16*>(q), ldq, ik, iv,
                          static_cast<long long>(kv_tok_stride), static_cast<long long>(kv_batch_stride), F, S, C, rl_n, nb,
-                         static_cast<__nv_bfloat16*>(out), ldo, static_cast<double*>(stats), act_f16));
+                         static_cast<__nv_bfloat16*>(out), ldo, static_cast<double*>(stats)));
   return SA_OK;
 }
 

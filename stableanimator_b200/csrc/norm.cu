@@ -7,6 +7,8 @@
 // the tile), and nn.LayerNorm at :499,510,521,892,898,907,916.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -346,108 +348,115 @@ layernorm_stream_kernel(const __nv_bfloat16* __restrict__ x, long long M, const 
     }
   } else {
     // ------------------------------------------------------------ consumers
-    // packed fp32x2 arithmetic throughout (add2 / fma2): the pass is bound by its instruction stream, not by HBM
-    constexpr int RPW = L::RPW;
-    const int sub = lane / LPR, l = lane % LPR;
-    const bool h16 = f16 != 0;
-    // group (addv row) of the current tile's row, tracked without a 64-bit division per tile
-    long long grp = 0, grp_row = 0;   // grp_row = first row of group `grp`
-    if (addv) {
-      const long long row0 = t_begin * L::TILE_ROWS + warp * RPW + sub;
-      grp = row0 / rows_per_group;
-      grp_row = grp * rows_per_group;
-    }
-    for (int i = 0; i < my_tiles; ++i) {
-      const int s = i % LN_ST;
-      const long long row = (t_begin + i) * L::TILE_ROWS + warp * RPW + sub;
-      const bool active = row < M;
-      uint8_t* base = smem + s * L::STAGE_BYTES + (warp * RPW + sub) * (C * 2);
-      const float* av = nullptr;
-      if (addv && active) {
-        while (row >= grp_row + rows_per_group) {
-          ++grp;
-          grp_row += rows_per_group;
-        }
-        av = addv + grp * C;
+    // packed fp32x2 arithmetic throughout (add2 / fma2), gamma / beta / addv loaded as 64-bit pairs, and the 16-bit format
+    // hoisted out of the loop (one instantiation of the body per format): the first packed version still executed 620
+    // instructions per warp and tile, a third of them moves between scalar and paired registers and the conversions of BOTH
+    // formats
+    auto consume = [&](auto fmt) {
+      constexpr bool H16 = decltype(fmt)::value;
+      constexpr int RPW = L::RPW;
+      const int sub = lane / LPR, l = lane % LPR;
+      // group (addv row) of the current tile's row, tracked without a 64-bit division per tile
+      long long grp = 0, grp_row = 0;   // grp_row = first row of group `grp`
+      if (addv) {
+        const long long row0 = t_begin * L::TILE_ROWS + warp * RPW + sub;
+        grp = row0 / rows_per_group;
+        grp_row = grp * rows_per_group;
       }
-      mbar_wait(&full[s], (i / LN_ST) & 1);
-      uint64_t v[OPL][4];
-      uint64_t sum2 = 0ull;   // (0.f, 0.f)
-#pragma unroll
-      for (int o = 0; o < OPL; ++o) {
-        const int oc = l + LPR * o;
-        if (active) {
-          const uint4 q = *reinterpret_cast<const uint4*>(base + oc * 16);
-          v[o][0] = h16x2_to_f32x2(q.x, h16);
-          v[o][1] = h16x2_to_f32x2(q.y, h16);
-          v[o][2] = h16x2_to_f32x2(q.z, h16);
-          v[o][3] = h16x2_to_f32x2(q.w, h16);
-        } else {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) v[o][k] = 0ull;
-        }
-        if (av) {
-          const float4 a0 = __ldg(reinterpret_cast<const float4*>(av + oc * 8));
-          const float4 a1 = __ldg(reinterpret_cast<const float4*>(av + oc * 8 + 4));
-          v[o][0] = add2(v[o][0], pack2(a0.x, a0.y));
-          v[o][1] = add2(v[o][1], pack2(a0.z, a0.w));
-          v[o][2] = add2(v[o][2], pack2(a1.x, a1.y));
-          v[o][3] = add2(v[o][3], pack2(a1.z, a1.w));
-          if (XOUT) {
-            // store x + addv and keep the ROUNDED value: it is what every later consumer of the stream reads
-            uint32_t w[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              w[k] = pack16x2_f2(v[o][k], h16);
-              v[o][k] = h16x2_to_f32x2(w[k], h16);
-            }
-            *reinterpret_cast<uint4*>(base + L::TILE_BYTES + oc * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+      for (int i = 0; i < my_tiles; ++i) {
+        const int s = i % LN_ST;
+        const long long row = (t_begin + i) * L::TILE_ROWS + warp * RPW + sub;
+        const bool active = row < M;
+        uint8_t* base = smem + s * L::STAGE_BYTES + (warp * RPW + sub) * (C * 2);
+        const float* av = nullptr;
+        if (addv && active) {
+          while (row >= grp_row + rows_per_group) {
+            ++grp;
+            grp_row += rows_per_group;
           }
+          av = addv + grp * C;
         }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) sum2 = add2(sum2, v[o][k]);
-      }
-      const float2 sf = unpack2(sum2);
-      float sum = sf.x + sf.y;
-#pragma unroll
-      for (int d = LPR / 2; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
-      const float mean = sum / static_cast<float>(C);
-      const uint64_t nmean2 = pack2(-mean, -mean);
-      uint64_t var2 = 0ull;
-#pragma unroll
-      for (int o = 0; o < OPL; ++o) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t d2 = add2(v[o][k], nmean2);
-          var2 = fma2(d2, d2, var2);
-          v[o][k] = d2;   // keep the centred value: the normalise step is one multiply
-        }
-      }
-      const float2 vf = unpack2(var2);
-      float var = vf.x + vf.y;
-#pragma unroll
-      for (int d = LPR / 2; d > 0; d >>= 1) var += __shfl_xor_sync(0xffffffffu, var, d);
-      const float rstd = rsqrtf(var / static_cast<float>(C) + eps);
-      const uint64_t rstd2 = pack2(rstd, rstd);
-      if (active) {
+        mbar_wait(&full[s], (i / LN_ST) & 1);
+        uint64_t v[OPL][4];
+        uint64_t sum2 = 0ull;   // (0.f, 0.f)
 #pragma unroll
         for (int o = 0; o < OPL; ++o) {
           const int oc = l + LPR * o;
-          const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + oc * 8));
-          const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + oc * 8 + 4));
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + oc * 8));
-          const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + oc * 8 + 4));
-          const uint32_t w0 = pack16x2_f2(fma2(mul2(v[o][0], rstd2), pack2(g0.x, g0.y), pack2(b0.x, b0.y)), h16);
-          const uint32_t w1 = pack16x2_f2(fma2(mul2(v[o][1], rstd2), pack2(g0.z, g0.w), pack2(b0.z, b0.w)), h16);
-          const uint32_t w2 = pack16x2_f2(fma2(mul2(v[o][2], rstd2), pack2(g1.x, g1.y), pack2(b1.x, b1.y)), h16);
-          const uint32_t w3 = pack16x2_f2(fma2(mul2(v[o][3], rstd2), pack2(g1.z, g1.w), pack2(b1.z, b1.w)), h16);
-          *reinterpret_cast<uint4*>(base + oc * 16) = make_uint4(w0, w1, w2, w3);
+          if (active) {
+            const uint4 q = *reinterpret_cast<const uint4*>(base + oc * 16);
+            v[o][0] = h16x2_to_f32x2(q.x, H16);
+            v[o][1] = h16x2_to_f32x2(q.y, H16);
+            v[o][2] = h16x2_to_f32x2(q.z, H16);
+            v[o][3] = h16x2_to_f32x2(q.w, H16);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[o][k] = 0ull;
+          }
+          if (av) {
+            const ulonglong2 a0 = __ldg(reinterpret_cast<const ulonglong2*>(av + oc * 8));
+            const ulonglong2 a1 = __ldg(reinterpret_cast<const ulonglong2*>(av + oc * 8 + 4));
+            v[o][0] = add2(v[o][0], a0.x);
+            v[o][1] = add2(v[o][1], a0.y);
+            v[o][2] = add2(v[o][2], a1.x);
+            v[o][3] = add2(v[o][3], a1.y);
+            if (XOUT) {
+              // store x + addv and keep the ROUNDED value: it is what every later consumer of the stream reads
+              uint32_t w[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                w[k] = pack16x2_f2(v[o][k], H16);
+                v[o][k] = h16x2_to_f32x2(w[k], H16);
+              }
+              *reinterpret_cast<uint4*>(base + L::TILE_BYTES + oc * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) sum2 = add2(sum2, v[o][k]);
         }
+        const float2 sf = unpack2(sum2);
+        float sum = sf.x + sf.y;
+#pragma unroll
+        for (int d = LPR / 2; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+        const float mean = sum / static_cast<float>(C);
+        const uint64_t nmean2 = pack2(-mean, -mean);
+        uint64_t var2 = 0ull;
+#pragma unroll
+        for (int o = 0; o < OPL; ++o) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t d2 = add2(v[o][k], nmean2);
+            var2 = fma2(d2, d2, var2);
+            v[o][k] = d2;   // keep the centred value: the normalise step is one multiply
+          }
+        }
+        const float2 vf = unpack2(var2);
+        float var = vf.x + vf.y;
+#pragma unroll
+        for (int d = LPR / 2; d > 0; d >>= 1) var += __shfl_xor_sync(0xffffffffu, var, d);
+        const float rstd = rsqrtf(var / static_cast<float>(C) + eps);
+        const uint64_t rstd2 = pack2(rstd, rstd);
+        if (active) {
+#pragma unroll
+          for (int o = 0; o < OPL; ++o) {
+            const int oc = l + LPR * o;
+            const ulonglong2 g0 = __ldg(reinterpret_cast<const ulonglong2*>(gamma + oc * 8));
+            const ulonglong2 g1 = __ldg(reinterpret_cast<const ulonglong2*>(gamma + oc * 8 + 4));
+            const ulonglong2 b0 = __ldg(reinterpret_cast<const ulonglong2*>(beta + oc * 8));
+            const ulonglong2 b1 = __ldg(reinterpret_cast<const ulonglong2*>(beta + oc * 8 + 4));
+            const uint32_t w0 = pack16x2_f2(fma2(mul2(v[o][0], rstd2), g0.x, b0.x), H16);
+            const uint32_t w1 = pack16x2_f2(fma2(mul2(v[o][1], rstd2), g0.y, b0.y), H16);
+            const uint32_t w2 = pack16x2_f2(fma2(mul2(v[o][2], rstd2), g1.x, b1.x), H16);
+            const uint32_t w3 = pack16x2_f2(fma2(mul2(v[o][3], rstd2), g1.y, b1.y), H16);
+            *reinterpret_cast<uint4*>(base + oc * 16) = make_uint4(w0, w1, w2, w3);
+          }
+        }
+        fence_proxy_async();  // our generic-proxy writes must be visible to the bulk store
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&done[s]);
       }
-      fence_proxy_async();  // our generic-proxy writes must be visible to the bulk store
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&done[s]);
-    }
+    };
+    if (f16) consume(std::true_type{});
+    else consume(std::false_type{});
   }
 }
 
@@ -593,6 +602,10 @@ gn_stream_kernel(const GnStreamP p) {
   // statistics group of the current tile, tracked incrementally (a 64-bit division per tile was a third of the apply
   // pass's instruction stream)
   long long ns = t_begin / tiles_per_stat, in_stat = t_begin - ns * tiles_per_stat;
+  // the 16-bit format and the SiLU switch are hoisted out of the tile loop (one instantiation of the body per combination):
+  // tested per element, the conversions of BOTH formats were executed
+  auto run_tiles = [&](auto fmt, auto act) {
+  constexpr bool H16 = decltype(fmt)::value, SILU = decltype(act)::value;
   for (int i = 0; i < my_tiles; ++i) {
     const int s = i % GN_ST;
     if (i > 0 && ++in_stat == tiles_per_stat) {
@@ -639,7 +652,7 @@ gn_stream_kernel(const GnStreamP p) {
           uint8_t* dst = two_src ? slot + in_bytes + oc * 16 : slot + oc * 16;
           for (int r = rl; r < p.R; r += rl_n) {
             float v[8];
-            load8s(src + r * src_ld, v, p.f16 != 0);
+            load8s(src + r * src_ld, v, H16);
             if (APPLY) {
               // packed fp32x2 lanes; silu2: one MUFU (tanh) per element
               uint32_t w[4];
@@ -647,7 +660,7 @@ gn_stream_kernel(const GnStreamP p) {
               for (int k = 0; k < 8; k += 2) {
                 const uint64_t y2 = fma2(pack2(v[k], v[k + 1]), pack2(a[cs][k], a[cs][k + 1]),
                                          pack2(b[cs][k], b[cs][k + 1]));
-                w[k >> 1] = pack16x2_f2(p.do_silu ? silu2(y2) : y2, p.f16 != 0);
+                w[k >> 1] = pack16x2_f2(SILU ? silu2(y2) : y2, H16);
               }
               *reinterpret_cast<uint4*>(dst + r * (C * 2)) = make_uint4(w[0], w[1], w[2], w[3]);
             } else {
@@ -664,6 +677,14 @@ gn_stream_kernel(const GnStreamP p) {
     if (APPLY) fence_proxy_async();  // normalised rows visible to the bulk store
     __syncwarp();
     if (lane == 0) mbar_arrive(&done[s]);
+  }
+  };
+  if (p.f16) {
+    if (APPLY && p.do_silu) run_tiles(std::true_type{}, std::true_type{});
+    else run_tiles(std::true_type{}, std::false_type{});
+  } else {
+    if (APPLY && p.do_silu) run_tiles(std::false_type{}, std::true_type{});
+    else run_tiles(std::false_type{}, std::false_type{});
   }
   if (!APPLY && cur_stat >= 0) flush_stats(cur_stat);
 }

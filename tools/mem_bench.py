@@ -11,13 +11,19 @@ from stableanimator_b200 import ops  # noqa: E402
 
 
 def timeit(fn, nbuf, iters=12):
+    """Device time per launch, replayed from a CUDA graph (eager Python launches of 30-60 us kernels are host-bound)."""
     for i in range(nbuf):
         fn(i)
     torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(iters):
+            fn(i % nbuf)
+    g.replay()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(iters):
-        fn(i % nbuf)
+    g.replay()
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / iters * 1e3  # us
