@@ -46,6 +46,12 @@ def main():
                           inp["pose"], steps_to_run=2))
     print(f"1 step: {one:.2f} ms; 2 steps: {two:.2f} ms -> per-video setup (PoseNet, context, noise tiling) "
           f"{2 * one - two:.2f} ms, one step {two - one:.2f} ms; one bare replay: {timed(run, 5):.2f} ms")
+    def replays_with_fill():   # one tiny eager kernel in front of every replay, as the step loop has
+        for _ in range(25):
+            run.t.fill_(1.0)
+            run()
+    fill = timed(replays_with_fill)
+    print(f"25 x (one eager fill_ + graph replay): {fill:.1f} ms ({(fill - only) / 25 * 1e3:.0f} us per step over bare replays)")
     print(f"sampler call (25 steps): {full:.1f} ms; 25 bare graph replays: {only:.1f} ms; difference {full - only:.1f} ms "
           f"({(full - only) / 25 * 1e3:.0f} us per step)")
 
